@@ -1,0 +1,784 @@
+// ONNXGraph mirror: init / graph walk / fusion / weight upload / per-batch plan / encode.
+// See engine.h for the reference map.
+#include "engine.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+namespace smelter {
+
+namespace {
+thread_local std::string g_last_error;
+}
+void set_last_error(const std::string& msg) { g_last_error = msg; }
+const std::string& last_error_string() { return g_last_error; }
+int fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+// ---- host helpers -------------------------------------------------------------------------------------------
+
+void reformat_conv_weight(const void* src, void* dst, int elem_size, int c_out, int c_in, int k_h, int k_w, bool is_transpose) {
+    // Index maps of Array+Extensions.swift:63-90: plain (OIHW->OHWI) and ConvTranspose (IOHW->OHWI, 180 degree flip).
+    // Loop order is output-major so the writes stream; same result as the reference's scalar 4-deep loop.
+    const char* s = static_cast<const char*>(src);
+    char* d = static_cast<char*>(dst);
+    const size_t khw = size_t(k_h) * k_w;
+    for (int oc = 0; oc < c_out; ++oc)
+        for (int kh = 0; kh < k_h; ++kh)
+            for (int kw = 0; kw < k_w; ++kw) {
+                const int dkh = is_transpose ? k_h - 1 - kh : kh;
+                const int dkw = is_transpose ? k_w - 1 - kw : kw;
+                char* drow = d + ((size_t(oc) * k_h + dkh) * k_w + dkw) * c_in * elem_size;
+                for (int ic = 0; ic < c_in; ++ic) {
+                    const size_t in_idx = is_transpose ? (size_t(ic) * c_out + oc) * khw + size_t(kh) * k_w + kw
+                                                       : (size_t(oc) * c_in + ic) * khw + size_t(kh) * k_w + kw;
+                    memcpy(drow + size_t(ic) * elem_size, s + in_idx * elem_size, size_t(elem_size));
+                }
+            }
+}
+
+int conv_output_size(int in, int k, int stride, int dil, int pad_lo, int pad_hi, int out_pad, bool is_transpose) {
+    if (is_transpose) return (in - 1) * stride - pad_lo - pad_hi + dil * (k - 1) + 1 + out_pad;  // ONNXConvolutionPadding.swift:97-103
+    const int num = in + pad_lo + pad_hi - (dil * (k - 1) + 1);                                   // :105-110, with the dilation term
+    if (num < 0) return 0;
+    return num / stride + 1;
+}
+
+int pool_output_size(int in, int k, int stride, int pad) {
+    // Int(Float(in + 2p - k) / Float(stride) + 1.0)  (PyTorchPoolPadding.swift:94-103): truncation toward zero
+    return int(float(in + 2 * pad - k) / float(stride) + 1.0f);
+}
+
+void pack_weights_ohwi(const float* w, int c_out, int c_in, int k_h, int k_w, int c_in_pitch, uint16_t* dst) {
+    const int taps = k_h * k_w;
+    for (int o = 0; o < c_out; ++o)
+        for (int t = 0; t < taps; ++t) {
+            const float* src = w + (size_t(o) * taps + t) * c_in;
+            uint16_t* d = dst + (size_t(o) * taps + t) * c_in_pitch;
+            for (int c = 0; c < c_in; ++c) d[c] = onnx::float_to_half(src[c]);
+            for (int c = c_in; c < c_in_pitch; ++c) d[c] = 0;
+        }
+}
+void pack_weights_rows(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst) {
+    for (int o = 0; o < c_out; ++o)
+        for (int r = 0; r < k_h; ++r)
+            for (int s = 0; s < k_w; ++s) {
+                const float* src = w + ((size_t(o) * k_h + r) * k_w + s) * c_in;
+                uint16_t* d = dst + ((size_t(o) * k_h + r) * k_w + s) * 8;
+                for (int c = 0; c < 8; ++c) d[c] = c < c_in ? onnx::float_to_half(src[c]) : uint16_t(0);
+            }
+}
+void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch, uint16_t* dst) {
+    const int taps = k_h * k_w;  // w: OHWI with I = 1 -> [c][taps]
+    for (int t = 0; t < taps; ++t)
+        for (int ch = 0; ch < c_pitch; ++ch) dst[size_t(t) * c_pitch + ch] = ch < c ? onnx::float_to_half(w[size_t(ch) * taps + t]) : uint16_t(0);
+}
+
+int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride_h, int stride_w, int dil_w, const int pads[4]) {
+    if (groups != 1) {
+        if (groups == c_in && groups == c_out) return 4;  // depthwise, multiplier 1 (Converters.swift:57)
+        return -1;
+    }
+    if (c_in <= 8 && dil_w == 1 && k_w * 8 <= 256 && k_h * k_w > 1) return k::CONV_MODE_PACKED_ROW;
+    if (k_h == 1 && k_w == 1 && stride_h == 1 && stride_w == 1 && !pads[0] && !pads[1] && !pads[2] && !pads[3]) return k::CONV_MODE_TILED;
+    return k::CONV_MODE_IM2COL;
+}
+
+// ---- ONNXGraph ------------------------------------------------------------------------------------------------
+
+struct Step {
+    std::function<cudaError_t(cudaStream_t)> run;
+    std::string desc;
+    double flops = 0, bytes = 0;
+};
+
+struct Plan {
+    int batch = 0;
+    std::vector<Step> steps;
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    std::vector<__half**> src_slots;          // where each graph input's current NCHW device pointer is read from
+    std::vector<const __half*> captured_src;  // pointers baked into the captured CUDA graph
+    std::vector<std::unique_ptr<__half*>> src_ptr_storage;
+    std::vector<ImageShape> src_shapes;
+    Tensor result;
+    cudaGraphExec_t exec = nullptr;
+    ~Plan() {
+        if (exec) cudaGraphExecDestroy(exec);
+        if (arena) cudaFree(arena);
+    }
+};
+
+ONNXGraph::~ONNXGraph() {
+    plans_.clear();
+    if (weight_arena_) cudaFree(weight_arena_);
+}
+
+int ONNXGraph::init(const uint8_t* data, size_t len, const smelter_config& cfg) {
+    if (!data || !len) return fail(SMELTER_ERR_INVALID_ARGUMENT, "empty model data");
+    bytes_.assign(data, data + len);
+    std::string perr;
+    if (!onnx::parse_model(bytes_.data(), bytes_.size(), &model_, &perr)) return fail(SMELTER_ERR_PARSE, perr);  // ONNXGraph.swift:96
+    format_ = model_.producer_name == "ONNX2MPS" ? SMELTER_FORMAT_MPS_FLAVOR : SMELTER_FORMAT_ONNX;             // :98-103
+    cfg_ = cfg;
+    for (const auto& t : model_.graph.initializer) tensors_[t.name] = &t;                                         // :106-108
+    registerBuiltins();                                                                                          // :110-155
+    return SMELTER_OK;
+}
+
+int ONNXGraph::output(const std::string& name) const {
+    auto it = outputs_.find(name);
+    return it == outputs_.end() ? -1 : it->second;
+}
+const ImageShape* ONNXGraph::shape(const std::string& name) const {
+    auto it = outputs_.find(name);
+    return it == outputs_.end() ? nullptr : &values_[size_t(it->second)].shape;
+}
+const onnx::TensorProto* ONNXGraph::tensor(const std::string& name) const {
+    auto it = tensors_.find(name);
+    return it == tensors_.end() ? nullptr : it->second;
+}
+
+int ONNXGraph::addFilter(Filter&& f, const ImageShape& shape, const std::vector<std::string>& outputs) {
+    if (outputs.empty()) return fail(SMELTER_ERR_INCONSISTENT_STATE, "filter without outputs");
+    Value v;
+    v.name = outputs[0];
+    v.shape = shape;
+    values_.push_back(v);
+    const int id = int(values_.size()) - 1;
+    f.out = id;
+    filters_.push_back(std::move(f));
+    for (const auto& o : outputs) outputs_[o] = id;  // ONNXGraph.swift:269-272: every output name maps to the same image
+    return SMELTER_OK;
+}
+
+int ONNXGraph::addAlias(int value, const ImageShape& shape, const std::vector<std::string>& outputs) {
+    if (outputs.empty()) return fail(SMELTER_ERR_INCONSISTENT_STATE, "alias without outputs");
+    Value v;
+    v.name = outputs[0];
+    v.shape = shape;
+    v.alias_of = value;
+    values_.push_back(v);
+    const int id = int(values_.size()) - 1;
+    for (const auto& o : outputs) outputs_[o] = id;
+    return SMELTER_OK;
+}
+
+// ONNXGraph.swift:197-251
+int ONNXGraph::initOutputs() {
+    for (const auto& vi : model_.graph.input) {
+        if (tensor(vi.name)) continue;  // :199 initializers listed as inputs are not images
+        std::vector<int64_t> dims = vi.dims;
+        for (int i = 0; i < cfg_.n_dims && i < 8; ++i) {  // :200-202 Configuration.dims overrides by axis index
+            const int axis = cfg_.dims_axis[i];
+            if (axis >= 0 && size_t(axis) < dims.size()) dims[size_t(axis)] = cfg_.dims_value[i];
+        }
+        ImageShape s;
+        if (dims.size() == 3) { s.c = int(dims[0]); s.h = int(dims[1]); s.w = int(dims[2]); }        // :205-208
+        else if (dims.size() == 4) { s.c = int(dims[1]); s.h = int(dims[2]); s.w = int(dims[3]); }   // :209-212 (N dropped)
+        else return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "graph input '" + vi.name + "' must have rank 3 or 4");  // :213-214
+        if (s.c <= 0 || s.h <= 0 || s.w <= 0) return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "graph input '" + vi.name + "' has unknown dims");
+        if (cfg_.input_constraint != SMELTER_INPUT_NONE)
+            return fail(SMELTER_ERR_UNSUPPORTED, "forceInputScale is not implemented (SURVEY §8f N4)");  // :219-241
+        Value v;
+        v.name = vi.name;
+        v.shape = s;
+        v.is_input = true;
+        values_.push_back(v);
+        outputs_[vi.name] = int(values_.size()) - 1;
+        input_values_.push_back(int(values_.size()) - 1);
+    }
+    return SMELTER_OK;
+}
+
+int ONNXGraph::consumers_of(int value) const {
+    int n = 0;
+    for (const auto& f : filters_) {
+        if (f.removed) continue;
+        for (int i : f.in) n += (i == value);
+        n += (f.residual == value);
+    }
+    for (const auto& v : values_) n += (v.alias_of == value) * 2;  // aliased values are never fused through
+    if (value == output_value_) n += 2;
+    return n;
+}
+
+// Fusion (what ONNX2MPS.py's fuse_bn_into_conv does offline, ONNX2MPS.py:104-109, plus epilogue fusion that
+// MPSNNGraph performs internally): Conv+BN fold, Conv(+Add)+activation, norm/add + ReLU.
+void ONNXGraph::fuse() {
+    auto producer = [&](int value) -> Filter* {
+        for (auto& f : filters_)
+            if (!f.removed && f.out == value) return &f;
+        return nullptr;
+    };
+    auto redirect = [&](int from, int to) {  // every reader of `from` now reads `to`
+        for (auto& f : filters_) {
+            for (int& i : f.in) if (i == from) i = to;
+            if (f.residual == from) f.residual = to;
+        }
+        for (auto& v : values_) if (v.alias_of == from) v.alias_of = to;
+        if (output_value_ == from) output_value_ = to;
+    };
+    // 1. BatchNorm directly after a Conv that has no other reader and no fused epilogue yet.
+    for (auto& bn : filters_) {
+        if (bn.removed || bn.kind != FilterKind::BatchNorm) continue;
+        Filter* conv = producer(bn.in[0]);
+        if (!conv || conv->kind != FilterKind::Conv || conv->act != k::ACT_NONE || conv->residual >= 0) continue;
+        if (consumers_of(conv->out) != 1) continue;
+        const size_t per_out = conv->w.size() / size_t(conv->c_out);
+        for (int o = 0; o < conv->c_out; ++o) {  // W' = W * s ; b' = b * s + shift
+            const float s = bn.p0[size_t(o)];
+            float* w = conv->w.data() + size_t(o) * per_out;
+            for (size_t i = 0; i < per_out; ++i) w[i] *= s;
+            conv->bias[size_t(o)] = conv->bias[size_t(o)] * s + bn.p1[size_t(o)];
+        }
+        bn.removed = true;
+        redirect(bn.out, conv->out);
+    }
+    // 2. Conv -> Add(residual) : the other operand must already exist when the conv runs.
+    for (size_t ai = 0; ai < filters_.size(); ++ai) {
+        Filter& add = filters_[ai];
+        if (add.removed || add.kind != FilterKind::Binary || add.sub != k::BIN_ADD || add.act != k::ACT_NONE) continue;
+        for (int side = 0; side < 2; ++side) {
+            Filter* conv = producer(add.in[size_t(side)]);
+            const int other = add.in[size_t(1 - side)];
+            if (!conv || conv->kind != FilterKind::Conv || conv->act != k::ACT_NONE || conv->residual >= 0) continue;
+            if (conv->groups != 1 || consumers_of(conv->out) != 1 || other == conv->out) continue;
+            // `other` must be produced before the conv in filter order (or be a graph input)
+            size_t conv_idx = size_t(conv - filters_.data());
+            int root = other;
+            while (values_[size_t(root)].alias_of >= 0) root = values_[size_t(root)].alias_of;
+            bool ok = values_[size_t(root)].is_input;
+            for (size_t j = 0; j < conv_idx && !ok; ++j) ok = !filters_[j].removed && filters_[j].out == root;
+            if (!ok) continue;
+            conv->residual = other;
+            add.removed = true;
+            redirect(add.out, conv->out);
+            break;
+        }
+    }
+    // 3. trailing activation into Conv / BatchNorm / InstanceNorm / Add.
+    for (auto& act : filters_) {
+        if (act.removed || act.kind != FilterKind::Unary) continue;
+        if (act.sub != k::UN_RELU && act.sub != k::UN_CLIP && act.sub != k::UN_SIGMOID) continue;
+        Filter* p = producer(act.in[0]);
+        if (!p || p->act != k::ACT_NONE || consumers_of(p->out) != 1) continue;
+        if (p->kind == FilterKind::Conv) {
+            p->act = act.sub == k::UN_RELU ? k::ACT_RELU : (act.sub == k::UN_CLIP ? k::ACT_CLIP : k::ACT_SIGMOID);
+            p->clip_lo = act.alpha; p->clip_hi = act.beta;
+        } else if ((p->kind == FilterKind::BatchNorm || p->kind == FilterKind::InstanceNorm ||
+                    (p->kind == FilterKind::Binary && p->sub == k::BIN_ADD)) && act.sub == k::UN_RELU) {
+            p->act = k::ACT_RELU;
+        } else {
+            continue;
+        }
+        act.removed = true;
+        redirect(act.out, p->out);
+    }
+}
+
+int ONNXGraph::build() {
+    if (built_) return SMELTER_OK;
+    int rc = initOutputs();  // ONNXGraph.swift:170
+    if (rc) return rc;
+    for (int i = 0; i < num_nodes(); ++i) {  // :172-176 file order = topological order
+        const auto& n = node(i);
+        auto it = converters_.find(n.op_type);
+        if (it == converters_.end()) return fail(SMELTER_ERR_UNKNOWN_NODE_OP_TYPE, n.op_type);
+        rc = it->second(*this, i);
+        if (rc) return rc;
+    }
+    if (model_.graph.output.size() != 1) return fail(SMELTER_ERR_UNSUPPORTED_OUTPUT, "exactly one graph output is supported");  // :178-180
+    output_value_ = output(model_.graph.output[0].name);
+    if (output_value_ < 0) return fail(SMELTER_ERR_NO_SUCH_OUTPUT, "graph output '" + model_.graph.output[0].name + "' was not produced");  // :182-183
+    if (input_values_.empty()) return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "graph has no image input");
+    if (cfg_.enable_fusion) fuse();
+    for (auto& f : filters_) {
+        if (f.removed || f.kind != FilterKind::Conv) continue;
+        f.conv_mode = pick_conv_mode(f.c_in_g * f.groups, f.c_out, f.groups, f.k_h, f.k_w, f.stride_h, f.stride_w, f.dil_w, f.pads);
+        if (f.conv_mode < 0)
+            return fail(SMELTER_ERR_UNSUPPORTED, "grouped convolution other than depthwise (groups=" + std::to_string(f.groups) + ")");
+    }
+    rc = upload_weights();  // MPSNNGraph(device:resultImage:) pulls weights from the data sources (:185-190)
+    if (rc) return fail(SMELTER_ERR_GRAPH_INTERNAL, "weight upload failed: " + last_error_string());
+    built_ = true;
+    // host copies of the weights and the model bytes are no longer needed
+    for (auto& f : filters_) { std::vector<float>().swap(f.w); }
+    return SMELTER_OK;
+}
+
+int ONNXGraph::upload_weights() {
+    SM_CUDA(cudaSetDevice(ctx_->device));
+    auto align = [](size_t v) { return (v + 255) & ~size_t(255); };
+    size_t total = 0;
+    for (auto& f : filters_) {
+        if (f.removed) continue;
+        if (f.kind == FilterKind::Conv) {
+            const int c_in = f.c_in_g * f.groups;
+            size_t wbytes;
+            if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
+            else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) wbytes = size_t(f.c_out) * f.k_h * f.k_w * 8 * 2;
+            else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
+            f.w_off = total; total = align(total + wbytes);
+            f.bias_off = total; total = align(total + size_t(round_up(f.c_out, 256)) * 4);
+        } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {
+            const size_t n = size_t(round_up(int(f.p0.size()), 8)) * 4;
+            f.p0_off = total; total = align(total + n);
+            f.p1_off = total; total = align(total + n);
+        }
+    }
+    weight_bytes_ = std::max<size_t>(total, 256);
+    std::vector<uint8_t> host(weight_bytes_, 0);
+    for (auto& f : filters_) {
+        if (f.removed) continue;
+        if (f.kind == FilterKind::Conv) {
+            const int c_in = f.c_in_g * f.groups;
+            uint16_t* w = reinterpret_cast<uint16_t*>(host.data() + f.w_off);
+            if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
+            else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) pack_weights_rows(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
+            else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
+            memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
+        } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {
+            memcpy(host.data() + f.p0_off, f.p0.data(), f.p0.size() * 4);
+            memcpy(host.data() + f.p1_off, f.p1.data(), f.p1.size() * 4);
+        }
+    }
+    SM_CUDA(cudaMalloc(&weight_arena_, weight_bytes_));
+    SM_CUDA(cudaMemcpy(weight_arena_, host.data(), weight_bytes_, cudaMemcpyHostToDevice));
+    return SMELTER_OK;
+}
+
+// ---- per-batch plan ---------------------------------------------------------------------------------------------
+
+namespace {
+
+struct ArenaAlloc {
+    struct Block { size_t off, size; };
+    std::vector<Block> free_list;
+    size_t top = 0;
+    static size_t align(size_t v) { return (v + 1023) & ~size_t(1023); }
+    size_t alloc(size_t bytes) {
+        bytes = align(std::max<size_t>(bytes, 16));
+        int best = -1;
+        for (size_t i = 0; i < free_list.size(); ++i)
+            if (free_list[i].size >= bytes && (best < 0 || free_list[i].size < free_list[size_t(best)].size)) best = int(i);
+        if (best >= 0) {
+            Block b = free_list[size_t(best)];
+            free_list.erase(free_list.begin() + best);
+            if (b.size > bytes) free_list.push_back({b.off + bytes, b.size - bytes});
+            return b.off;
+        }
+        const size_t off = top;
+        top += bytes;
+        return off;
+    }
+    void release(size_t off, size_t bytes) {
+        bytes = align(std::max<size_t>(bytes, 16));
+        free_list.push_back({off, bytes});
+        // coalesce
+        std::sort(free_list.begin(), free_list.end(), [](const Block& a, const Block& b) { return a.off < b.off; });
+        std::vector<Block> merged;
+        for (const Block& b : free_list) {
+            if (!merged.empty() && merged.back().off + merged.back().size == b.off) merged.back().size += b.size;
+            else merged.push_back(b);
+        }
+        free_list.swap(merged);
+        if (!free_list.empty() && free_list.back().off + free_list.back().size == top) {
+            top = free_list.back().off;
+            free_list.pop_back();
+        }
+    }
+};
+
+}  // namespace
+
+int ONNXGraph::plan_for(int batch, Plan** out) {
+    if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
+    auto it = plans_.find(batch);
+    if (it != plans_.end()) { *out = it->second.get(); return SMELTER_OK; }
+    SM_CUDA(cudaSetDevice(ctx_->device));
+    auto plan = std::make_unique<Plan>();
+    plan->batch = batch;
+    const int N = batch;
+    const int num_sms = ctx_->num_sms;
+    const char* wbase = static_cast<const char*>(weight_arena_);
+
+    auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
+    auto pitch_of = [&](int v) { return round_up(values_[size_t(v)].shape.c, 8); };
+    auto bytes_of = [&](int v) { const ImageShape& s = values_[size_t(v)].shape; return size_t(N) * s.h * s.w * round_up(s.c, 8) * 2; };
+
+    // ---- which convs read a graph input / need a materialised padded input (packed-row mode) ----
+    // last use of every root value (filter index); the output value lives forever
+    std::vector<int> last_use(values_.size(), -1);
+    for (size_t fi = 0; fi < filters_.size(); ++fi) {
+        const Filter& f = filters_[fi];
+        if (f.removed) continue;
+        for (int i : f.in) last_use[size_t(root_of(i))] = int(fi);
+        if (f.residual >= 0) last_use[size_t(root_of(f.residual))] = int(fi);
+    }
+    const int out_root = root_of(output_value_);
+    last_use[size_t(out_root)] = int(filters_.size()) + 1;
+
+    // ---- offsets (two passes: first compute offsets, then allocate, then bind pointers) ----
+    ArenaAlloc arena;
+    std::vector<size_t> off(values_.size(), size_t(-1));
+    struct Scratch { size_t off, bytes; };
+    std::vector<Scratch> scratch(filters_.size(), Scratch{size_t(-1), 0});   // per-filter temporary (padded input copy, IN partials, NCHW staging)
+    std::vector<Scratch> scratch2(filters_.size(), Scratch{size_t(-1), 0});
+
+    // graph inputs: NHWC copies produced by the boundary conversion
+    for (int v : input_values_) off[size_t(v)] = arena.alloc(bytes_of(v));
+    for (size_t fi = 0; fi < filters_.size(); ++fi) {
+        const Filter& f = filters_[fi];
+        if (f.removed) continue;
+        // temporaries first (live only during this filter)
+        if (f.kind == FilterKind::Conv && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3])) {
+            const ImageShape& s = values_[size_t(f.in[0])].shape;
+            scratch[fi].bytes = size_t(N) * (s.h + f.pads[0] + f.pads[2]) * (s.w + f.pads[1] + f.pads[3]) * 8 * 2;
+            scratch[fi].off = arena.alloc(scratch[fi].bytes);
+        }
+        if (f.kind == FilterKind::InstanceNorm) {
+            const ImageShape& s = values_[size_t(f.in[0])].shape;
+            scratch[fi].bytes = size_t(N) * k::instance_norm_splits(s.h * s.w, round_up(s.c, 8)) * round_up(s.c, 8) * 2 * sizeof(float);
+            scratch[fi].off = arena.alloc(scratch[fi].bytes);
+        }
+        if (f.kind == FilterKind::Reshape) {
+            const ImageShape& a = values_[size_t(f.in[0])].shape;
+            const ImageShape& b = values_[size_t(f.out)].shape;
+            const bool view = a.h == 1 && a.w == 1 && b.h == 1 && b.w == 1;
+            if (!view) {
+                scratch[fi].bytes = size_t(N) * a.c * a.h * a.w * 2;  // dense NCHW staging
+                scratch[fi].off = arena.alloc(scratch[fi].bytes);
+            }
+        }
+        off[size_t(f.out)] = arena.alloc(bytes_of(f.out));
+        if (scratch[fi].off != size_t(-1)) arena.release(scratch[fi].off, scratch[fi].bytes);
+        // release inputs whose last use is this filter
+        std::vector<int> roots;
+        for (int i : f.in) roots.push_back(root_of(i));
+        if (f.residual >= 0) roots.push_back(root_of(f.residual));
+        std::sort(roots.begin(), roots.end());
+        roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
+        for (int r : roots)
+            if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1)) arena.release(off[size_t(r)], bytes_of(r));
+    }
+    // result tensor (NCHW) unless the output value is already NCHW-compatible
+    const ImageShape& os = values_[size_t(output_value_)].shape;
+    const bool result_is_view = os.h == 1 && os.w == 1 && os.c % 8 == 0;
+    size_t result_off = size_t(-1);
+    if (!result_is_view) result_off = arena.alloc(size_t(N) * os.c * os.h * os.w * 2);
+
+    plan->arena_bytes = std::max<size_t>(arena.top, 1024);
+    SM_CUDA(cudaMalloc(&plan->arena, plan->arena_bytes));
+    char* abase = static_cast<char*>(plan->arena);
+    auto ptr_of = [&](int v) { return reinterpret_cast<__half*>(abase + off[size_t(root_of(v))]); };
+
+    // ---- steps ----
+    auto add_step = [&](std::string desc, std::function<cudaError_t(cudaStream_t)> fn, double flops = 0, double bytes = 0) {
+        Step st;
+        st.desc = std::move(desc);
+        st.run = std::move(fn);
+        st.flops = flops;
+        st.bytes = bytes;
+        plan->steps.push_back(std::move(st));
+    };
+    // boundary: NCHW source -> NHWC (the source pointer is read at launch time through a stable slot)
+    for (int v : input_values_) {
+        plan->src_ptr_storage.push_back(std::make_unique<__half*>(nullptr));
+        __half** slot = plan->src_ptr_storage.back().get();
+        plan->src_slots.push_back(slot);
+        const ImageShape s = values_[size_t(v)].shape;
+        plan->src_shapes.push_back(s);
+        __half* dst = ptr_of(v);
+        const int cp = pitch_of(v);
+        add_step("nchw_to_nhwc " + values_[size_t(v)].name, [=](cudaStream_t st) { return k::nchw_to_nhwc(*slot, dst, N, s.c, s.h, s.w, cp, 0, 0, 0, 0, st); },
+                 0, double(N) * s.h * s.w * (s.c + cp) * 2);
+    }
+
+    for (size_t fi = 0; fi < filters_.size(); ++fi) {
+        const Filter& f = filters_[fi];
+        if (f.removed) continue;
+        const ImageShape is = values_[size_t(f.in[0])].shape;
+        const ImageShape osz = values_[size_t(f.out)].shape;
+        const int icp = round_up(is.c, 8), ocp = round_up(osz.c, 8);
+        const __half* x = ptr_of(f.in[0]);
+        __half* y = ptr_of(f.out);
+        const std::string name = f.op_type + " " + values_[size_t(f.out)].name;
+        const double io_bytes = double(N) * (double(is.h) * is.w * icp + double(osz.h) * osz.w * ocp) * 2;
+        switch (f.kind) {
+            case FilterKind::Conv: {
+                const float* bias = reinterpret_cast<const float*>(wbase + f.bias_off);
+                const __half* w = reinterpret_cast<const __half*>(wbase + f.w_off);
+                const __half* res = f.residual >= 0 ? ptr_of(f.residual) : nullptr;
+                std::string suffix = f.act == k::ACT_RELU ? "+relu" : f.act == k::ACT_CLIP ? "+clip" : f.act == k::ACT_SIGMOID ? "+sigmoid" : "";
+                if (res) suffix = "+add" + suffix;
+                const double flops = 2.0 * N * osz.h * osz.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w;
+                if (f.conv_mode == 4) {
+                    const Filter* fp = &f;
+                    add_step("depthwise" + suffix + " " + name, [=](cudaStream_t st) {
+                        return k::depthwise_conv(x, w, bias, y, N, is.h, is.w, icp, osz.h, osz.w, fp->k_h, fp->k_w, fp->stride_h, fp->stride_w, fp->dil_h,
+                                                 fp->dil_w, fp->pads[0], fp->pads[1], fp->act, fp->clip_lo, fp->clip_hi, st);
+                    }, flops, io_bytes);
+                    break;
+                }
+                k::ConvTcProblem q{};
+                q.mode = f.conv_mode;
+                q.n = N; q.h = is.h; q.w = is.w;
+                q.c_in = f.c_in_g; q.c_in_pitch = icp;
+                if (f.is_gemm) { q.h = q.w = 1; q.c_in_pitch = round_up(is.c * is.h * is.w, 8); }
+                q.c_out = f.c_out; q.c_out_pitch = ocp;
+                q.k_h = f.k_h; q.k_w = f.k_w; q.stride_h = f.stride_h; q.stride_w = f.stride_w; q.dil_h = f.dil_h; q.dil_w = f.dil_w;
+                q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
+                q.x = x; q.w_packed = w; q.bias = bias; q.residual = res; q.y = y;
+                q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
+                if (f.conv_mode == k::CONV_MODE_PACKED_ROW && scratch[fi].off != size_t(-1)) {
+                    // materialise the zero padding so one K block can span a whole filter row
+                    __half* padded = reinterpret_cast<__half*>(abase + scratch[fi].off);
+                    const Filter* fp = &f;
+                    add_step("pad0 " + name, [=](cudaStream_t st) {
+                        return k::pad2d(x, padded, N, is.h, is.w, 8, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], k::PAD_CONSTANT, 0.f, st);
+                    }, 0, double(scratch[fi].bytes) + double(N) * is.h * is.w * 16);
+                    q.x = padded;
+                    q.h = is.h + f.pads[0] + f.pads[2];
+                    q.w = is.w + f.pads[1] + f.pads[3];
+                    q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+                }
+                auto L = std::make_shared<k::ConvTcLaunch>();
+                std::string cerr;
+                if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
+                const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : "rows";
+                add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + "]" + suffix + " " + name,
+                         [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,
+                         io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0));
+                break;
+            }
+            case FilterKind::BatchNorm: {
+                const float* sc = reinterpret_cast<const float*>(wbase + f.p0_off);
+                const float* sh = reinterpret_cast<const float*>(wbase + f.p1_off);
+                const int act = f.act;
+                add_step("scale_shift " + name, [=](cudaStream_t st) { return k::scale_shift(x, y, size_t(N) * is.h * is.w, icp, sc, sh, act, st); }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::InstanceNorm: {
+                const float* ga = reinterpret_cast<const float*>(wbase + f.p0_off);
+                const float* be = reinterpret_cast<const float*>(wbase + f.p1_off);
+                float* partials = reinterpret_cast<float*>(abase + scratch[fi].off);
+                const int act = f.act;
+                const float eps = f.eps;
+                add_step("instance_norm " + name, [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st); }, 0,
+                         io_bytes + double(N) * is.h * is.w * icp * 2);
+                break;
+            }
+            case FilterKind::Unary: {
+                const int kind = f.sub;
+                const float a = f.alpha, b = f.beta;
+                add_step("unary " + name, [=](cudaStream_t st) { return k::unary(x, y, size_t(N) * is.h * is.w * icp, kind, a, b, st); }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::Binary: {
+                const __half* x2 = ptr_of(f.in[1]);
+                const int kind = f.sub, act = f.act;
+                add_step("binary " + name, [=](cudaStream_t st) { return k::binary(x, x2, y, size_t(N) * is.h * is.w * icp, kind, act, st); }, 0,
+                         io_bytes + double(N) * is.h * is.w * icp * 2);
+                break;
+            }
+            case FilterKind::Pool: {
+                const Filter* fp = &f;
+                add_step("pool " + name, [=](cudaStream_t st) {
+                    return k::pool2d(x, y, N, is.h, is.w, icp, osz.h, osz.w, fp->k_h, fp->k_w, fp->stride_h, fp->stride_w, fp->pool_pad_h, fp->pool_pad_w,
+                                     fp->sub, st);
+                }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::GlobalAvgPool:
+                add_step("global_avgpool " + name, [=](cudaStream_t st) { return k::global_avgpool(x, y, N, is.h * is.w, icp, st); }, 0, io_bytes);
+                break;
+            case FilterKind::Upsample: {
+                const Filter* fp = &f;
+                add_step("upsample " + name, [=](cudaStream_t st) {
+                    return k::upsample2d(x, y, N, is.h, is.w, icp, fp->scale_h, fp->scale_w, fp->sub, fp->align_corners, st);
+                }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::Concat: {
+                int c_off = 0;
+                for (int v : f.in) {
+                    const ImageShape s = values_[size_t(v)].shape;
+                    const __half* src = ptr_of(v);
+                    const int scp = round_up(s.c, 8), co = c_off;
+                    add_step("concat " + name, [=](cudaStream_t st) { return k::concat_channels(src, y, size_t(N) * s.h * s.w, s.c, scp, ocp, co, st); }, 0,
+                             double(N) * s.h * s.w * s.c * 4);
+                    c_off += s.c;
+                }
+                if (ocp != osz.c) {
+                    // padded channels of the destination stay uninitialised otherwise: clear once per encode
+                    // (cheap; only when the concatenated channel count is not a multiple of 8)
+                    const size_t bytes = bytes_of(f.out);
+                    Step clear;
+                    clear.desc = "memset " + name;
+                    clear.run = [=](cudaStream_t st) { return cudaMemsetAsync(y, 0, bytes, st); };
+                    plan->steps.insert(plan->steps.end() - long(f.in.size()), std::move(clear));
+                }
+                break;
+            }
+            case FilterKind::Reshape: {
+                if (scratch[fi].off == size_t(-1)) {
+                    // [N,C,1,1] -> [N,C',1,1] with C == C': same bytes.  Copy keeps the planner simple when the
+                    // value could not be aliased (pitches equal because both are round_up(c, 8)).
+                    const size_t bytes = bytes_of(f.out);
+                    add_step("reshape(copy) " + name, [=](cudaStream_t st) { return cudaMemcpyAsync(y, x, bytes, cudaMemcpyDeviceToDevice, st); }, 0, 2.0 * bytes);
+                } else {
+                    __half* staging = reinterpret_cast<__half*>(abase + scratch[fi].off);
+                    add_step("reshape(nhwc->nchw) " + name, [=](cudaStream_t st) { return k::nhwc_to_nchw(x, staging, N, is.c, is.h, is.w, icp, long(is.c) * is.h * is.w, st); }, 0, io_bytes);
+                    add_step("reshape(nchw->nhwc) " + name, [=](cudaStream_t st) { return k::nchw_to_nhwc(staging, y, N, osz.c, osz.h, osz.w, ocp, 0, 0, 0, 0, st); }, 0, io_bytes);
+                }
+                break;
+            }
+            case FilterKind::Softmax: {
+                const int lg = f.sub;
+                add_step("softmax " + name, [=](cudaStream_t st) { return k::softmax_rows(x, y, size_t(N) * is.h * is.w, is.c, icp, lg, st); }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::Pad: {
+                const Filter* fp = &f;
+                add_step("pad " + name, [=](cudaStream_t st) {
+                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st);
+                }, 0, io_bytes);
+                break;
+            }
+            case FilterKind::Alias:
+                break;
+        }
+    }
+    // boundary: result as NCHW
+    plan->result.ctx = ctx_;
+    plan->result.n = N; plan->result.c = os.c; plan->result.h = os.h; plan->result.w = os.w;
+    plan->result.owned = false;
+    if (result_is_view) {
+        plan->result.ptr = ptr_of(output_value_);
+    } else {
+        __half* dst = reinterpret_cast<__half*>(abase + result_off);
+        const __half* src = ptr_of(output_value_);
+        const int cp = round_up(os.c, 8);
+        const ImageShape o2 = os;
+        add_step("nhwc_to_nchw " + values_[size_t(output_value_)].name,
+                 [=](cudaStream_t st) { return k::nhwc_to_nchw(src, dst, N, o2.c, o2.h, o2.w, cp, long(o2.c) * o2.h * o2.w, st); }, 0,
+                 double(N) * o2.h * o2.w * (o2.c + cp) * 2);
+        plan->result.ptr = dst;
+    }
+    *out = plan.get();
+    plans_[batch] = std::move(plan);
+    return SMELTER_OK;
+}
+
+int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_sources, const Tensor** result) {
+    if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "encode before build");
+    if (!sources || n_sources != int(input_values_.size()))
+        return fail(SMELTER_ERR_INSUFFICIENT_INPUTS, "graph expects " + std::to_string(input_values_.size()) + " source image(s)");
+    for (int i = 0; i < n_sources; ++i)
+        if (!sources[i] || !sources[i]->ptr) return fail(SMELTER_ERR_INVALID_ARGUMENT, "null source");
+    const int batch = sources[0]->n;
+    if (batch <= 0) return fail(SMELTER_ERR_INVALID_ARGUMENT, "empty batch");
+    Plan* plan = nullptr;
+    int rc = plan_for(batch, &plan);
+    if (rc) return rc;
+    for (int i = 0; i < n_sources; ++i) {
+        const ImageShape& s = plan->src_shapes[size_t(i)];
+        const Tensor* t = sources[i];
+        if (t->n != batch || t->c != s.c || t->h != s.h || t->w != s.w)
+            return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "source " + std::to_string(i) + " is [" + std::to_string(t->n) + "," + std::to_string(t->c) + "," +
+                                                           std::to_string(t->h) + "," + std::to_string(t->w) + "], graph input is [N," + std::to_string(s.c) + "," +
+                                                           std::to_string(s.h) + "," + std::to_string(s.w) + "]");
+        *plan->src_slots[size_t(i)] = t->ptr;
+    }
+    if (!stream) stream = ctx_->stream;
+    SM_CUDA(cudaSetDevice(ctx_->device));
+    if (cfg_.use_cuda_graph) {
+        bool same = plan->exec != nullptr && plan->captured_src.size() == size_t(n_sources);
+        for (int i = 0; same && i < n_sources; ++i) same = plan->captured_src[size_t(i)] == sources[i]->ptr;
+        if (!same) {
+            if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+            cudaGraph_t graph = nullptr;
+            SM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
+            cudaError_t e = cudaSuccess;
+            std::string where;
+            for (auto& st : plan->steps) {
+                e = st.run(stream);
+                if (e != cudaSuccess) { where = st.desc; break; }
+            }
+            cudaError_t e2 = cudaStreamEndCapture(stream, &graph);
+            if (e != cudaSuccess || e2 != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                return fail(SMELTER_ERR_CUDA, "capture failed at '" + where + "': " + cudaGetErrorString(e != cudaSuccess ? e : e2));
+            }
+            e = cudaGraphInstantiate(&plan->exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
+            plan->captured_src.clear();
+            for (int i = 0; i < n_sources; ++i) plan->captured_src.push_back(sources[i]->ptr);
+        }
+        SM_CUDA(cudaGraphLaunch(plan->exec, stream));
+    } else {
+        for (auto& st : plan->steps) {
+            cudaError_t e = st.run(stream);
+            if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
+        }
+    }
+    *result = &plan->result;
+    return SMELTER_OK;
+}
+
+int ONNXGraph::num_launches(int batch, int* n) {
+    Plan* plan = nullptr;
+    int rc = plan_for(batch, &plan);
+    if (rc) return rc;
+    int count = 0;
+    for (auto& st : plan->steps) {
+        count += 1;
+        if (st.desc.rfind("instance_norm", 0) == 0) count += 1;  // two kernels
+    }
+    *n = count;
+    return SMELTER_OK;
+}
+
+int ONNXGraph::plan_dump(int batch, std::string* out) {
+    Plan* plan = nullptr;
+    int rc = plan_for(batch, &plan);
+    if (rc) return rc;
+    char line[512];
+    snprintf(line, sizeof line, "# batch %d, %zu steps, activation arena %.1f MiB, weight arena %.1f MiB\n", batch, plan->steps.size(),
+             plan->arena_bytes / 1048576.0, weight_bytes_ / 1048576.0);
+    *out = line;
+    for (auto& st : plan->steps) {
+        snprintf(line, sizeof line, "%-90s flops=%.4g bytes=%.4g\n", st.desc.c_str(), st.flops, st.bytes);
+        *out += line;
+    }
+    return SMELTER_OK;
+}
+
+int ONNXGraph::broadcast_weights(int root) {
+    if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
+    return nccl_broadcast(ctx_, weight_arena_, weight_bytes_, root, ctx_->stream);
+}
+
+int ONNXGraph::weight_checksum(uint64_t* sum, uint64_t* bytes) {
+    if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
+    SM_CUDA(cudaSetDevice(ctx_->device));
+    unsigned long long* d = nullptr;
+    SM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    cudaError_t e = k::checksum64(weight_arena_, weight_bytes_, d, ctx_->stream);
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof h, cudaMemcpyDeviceToHost, ctx_->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx_->stream);
+    cudaFree(d);
+    if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, cudaGetErrorString(e));
+    *sum = h;
+    *bytes = weight_bytes_;
+    return SMELTER_OK;
+}
+
+}  // namespace smelter

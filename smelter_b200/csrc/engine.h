@@ -1,0 +1,190 @@
+// Host side of the engine: the ONNXGraph mirror (symbol tables + converter registry), the filter list it
+// builds, the fusion pass, the per-batch execution plan and the executor.
+//
+// Reference map (Sources/Smelter/):
+//   ONNXGraph            ONNXGraph.swift:3-286      -> class ONNXGraph below (same tables, same five-call converter surface)
+//   NodeConverter        NodeConverter.swift:3-5    -> ConverterFn
+//   MPSNNFilterNode list ONNXGraph.swift:65,263-273 -> std::vector<Filter> filters
+//   MPSNNGraph           ONNXGraph.swift:185-190    -> Plan (compiled per batch size) + encode()
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/smelter_b200.h"
+#include "kernels/kernels.h"
+#include "onnx_wire.h"
+
+namespace smelter {
+
+void set_last_error(const std::string& msg);
+int fail(int code, const std::string& msg);  // sets the thread-local message and returns code
+#define SM_CUDA(expr)                                                                                          \
+    do {                                                                                                       \
+        cudaError_t _e = (expr);                                                                               \
+        if (_e != cudaSuccess) return ::smelter::fail(SMELTER_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+inline int round_up(int v, int m) { return (v + m - 1) / m * m; }
+
+struct Context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    int num_sms = 148;
+    // NCCL (loaded lazily with dlopen; see nccl_shim.cc)
+    void* nccl_comm = nullptr;
+    int rank = 0, world = 1;
+};
+
+struct Tensor {
+    Context* ctx = nullptr;
+    __half* ptr = nullptr;
+    int n = 0, c = 0, h = 0, w = 0;
+    bool owned = false;
+    size_t count() const { return size_t(n) * c * h * w; }
+};
+
+struct ImageShape {
+    int c = 0, h = 0, w = 0;
+    bool operator==(const ImageShape& o) const { return c == o.c && h == o.h && w == o.w; }
+};
+
+enum class FilterKind {
+    Conv, BatchNorm, InstanceNorm, Unary, Binary, Pool, GlobalAvgPool, Upsample, Concat, Reshape, Softmax, Pad, Alias
+};
+
+struct Filter {
+    FilterKind kind;
+    std::string op_type;           // ONNX op that created it (for the plan dump)
+    std::vector<int> in;           // value ids
+    int out = -1;                  // value id
+    bool removed = false;          // fused away
+
+    // Conv / Gemm
+    int c_out = 0, c_in_g = 0, k_h = 1, k_w = 1, stride_h = 1, stride_w = 1, dil_h = 1, dil_w = 1, groups = 1;
+    int pads[4] = {0, 0, 0, 0};    // top, left, bottom, right
+    std::vector<float> w;          // OHWI fp32 [c_out][k_h][k_w][c_in_g]
+    std::vector<float> bias;       // [c_out]
+    bool is_gemm = false;
+    // fused epilogue (also used by BatchNorm / InstanceNorm / Binary for a trailing ReLU)
+    int act = k::ACT_NONE;
+    float clip_lo = 0.f, clip_hi = 0.f;
+    int residual = -1;             // value id added before the activation
+
+    // BatchNorm: scale/shift (folded from gamma,beta,mean,var,eps).  InstanceNorm: gamma/beta + eps.
+    std::vector<float> p0, p1;
+    float eps = 1e-5f;
+    // Unary / Binary / Softmax / Upsample / Pad / Pool
+    int sub = 0;                   // unary kind, binary kind, log-softmax flag, upsample mode, pad mode, is_max
+    float alpha = 0.f, beta = 0.f; // unary params, pad value in alpha
+    int scale_h = 1, scale_w = 1, align_corners = 1;
+    int pool_pad_h = 0, pool_pad_w = 0;
+
+    // device-side constants (offsets into the weight arena), filled by build()
+    size_t w_off = 0, bias_off = 0, p0_off = 0, p1_off = 0;
+    int conv_mode = 0;             // k::ConvMode, or 4 = depthwise
+};
+
+struct Value {
+    std::string name;
+    ImageShape shape;
+    int alias_of = -1;  // view of another value's buffer (Flatten/Reshape views, Dropout)
+    bool is_input = false;
+};
+
+struct Plan;  // per-batch compiled executor state
+
+class ONNXGraph;
+using ConverterFn = std::function<int(ONNXGraph&, int node_index)>;
+
+class ONNXGraph {
+   public:
+    ONNXGraph(Context* ctx) : ctx_(ctx) {}
+    ~ONNXGraph();
+
+    // ONNXGraph.init(data:configuration:)  ONNXGraph.swift:95-156
+    int init(const uint8_t* data, size_t len, const smelter_config& cfg);
+    // ONNXGraph.metalGraph(device:)        ONNXGraph.swift:169-193
+    int build();
+    int encode(cudaStream_t stream, const Tensor* const* sources, int n_sources, const Tensor** result);
+
+    // ---- the converter-facing surface (ONNXGraph.swift:259-285) ----
+    int output(const std::string& name) const;                       // output(name:)  -> value id or -1
+    const ImageShape* shape(const std::string& name) const;          // shape(output:)
+    const onnx::TensorProto* tensor(const std::string& name) const;  // tensor(name:)
+    void initTensor(const std::string& name, const onnx::TensorProto* t) { tensors_[name] = t; }
+    // addFilter: registers `f` and creates the named output image node(s) with `shape`
+    int addFilter(Filter&& f, const ImageShape& shape, const std::vector<std::string>& outputs);
+    int addAlias(int value, const ImageShape& shape, const std::vector<std::string>& outputs);
+    void registerConverter(const std::string& name, ConverterFn fn) { converters_[name] = std::move(fn); }  // register(name:converter:)
+
+    const onnx::NodeProto& node(int i) const { return model_.graph.node[size_t(i)]; }
+    int num_nodes() const { return int(model_.graph.node.size()); }
+    const onnx::ModelProto& model() const { return model_; }
+    const smelter_config& config() const { return cfg_; }
+    smelter_format format() const { return format_; }
+    bool has_converter(const std::string& op) const { return converters_.count(op) != 0; }
+    bool built() const { return built_; }
+    Context* ctx() const { return ctx_; }
+    const std::vector<Value>& values() const { return values_; }
+
+    int plan_for(int batch, Plan** out);
+    int num_launches(int batch, int* n);
+    int plan_dump(int batch, std::string* out);
+    int broadcast_weights(int root);
+    int weight_checksum(uint64_t* sum, uint64_t* bytes);
+
+   private:
+    int initOutputs();  // ONNXGraph.swift:197-251
+    void registerBuiltins();
+    void fuse();
+    int upload_weights();
+    int consumers_of(int value) const;
+
+    Context* ctx_;
+    smelter_config cfg_{};
+    smelter_format format_ = SMELTER_FORMAT_ONNX;
+    std::vector<uint8_t> bytes_;     // owned copy of the model (raw_data views point in here)
+    onnx::ModelProto model_;
+    std::map<std::string, ConverterFn> converters_;
+    std::map<std::string, const onnx::TensorProto*> tensors_;
+    std::map<std::string, int> outputs_;   // name -> value id   (the MPSNNImageNode table)
+    std::vector<Value> values_;            // per value: name + shape (the nodeShapes table)
+    std::vector<Filter> filters_;
+    std::vector<int> input_values_;        // graph inputs that are not initializers, in file order
+    int output_value_ = -1;
+    bool built_ = false;
+
+    void* weight_arena_ = nullptr;
+    size_t weight_bytes_ = 0;
+    std::map<int, std::shared_ptr<Plan>> plans_;
+};
+
+// ---- shared host helpers (also exported through the C ABI) -------------------------------------------------
+// Array.reformatingConvolutionWeight  Extensions/Foundation/Array+Extensions.swift:52-93
+void reformat_conv_weight(const void* src, void* dst, int elem_size, int c_out, int c_in, int k_h, int k_w, bool is_transpose);
+// ONNX_ConvolutionPadding.paddedSize  Padding/ONNXConvolutionPadding.swift:91-113 (+ dilation)
+int conv_output_size(int in, int k, int stride, int dil, int pad_lo, int pad_hi, int out_pad, bool is_transpose);
+// PyTorchPoolPadding.paddedSize       Padding/PyTorchPoolPadding.swift:94-103
+int pool_output_size(int in, int k, int stride, int pad);
+
+// Weight packers for the conv kernels (w is OHWI fp32 [c_out][k_h][k_w][c_in]).
+void pack_weights_ohwi(const float* w, int c_out, int c_in, int k_h, int k_w, int c_in_pitch, uint16_t* dst);  // [c_out][k_h*k_w][pitch]
+void pack_weights_rows(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst);                   // [c_out][k_h][k_w*8]
+void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch, uint16_t* dst);               // [k_h*k_w][pitch]
+int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride_h, int stride_w, int dil_w, const int pads[4]);
+
+// NCCL shim (dlopen'd so the library loads on machines without NCCL / GPUs).
+int nccl_unique_id(uint8_t id[128]);
+int nccl_init(Context* ctx, const uint8_t id[128], int rank, int world);
+int nccl_broadcast(Context* ctx, void* buf, size_t bytes, int root, cudaStream_t stream);
+void nccl_destroy(Context* ctx);
+
+}  // namespace smelter

@@ -1,0 +1,67 @@
+// Host interface of the tcgen05 implicit-GEMM convolution (see conv_igemm.cu).
+#pragma once
+#include <cuda.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include <string>
+
+namespace smelter {
+namespace k {
+
+enum Act : int { ACT_NONE = 0, ACT_RELU = 1, ACT_CLIP = 2, ACT_SIGMOID = 3 };
+
+enum ConvMode : int {
+    CONV_MODE_TILED = 1,       // 1x1, stride 1, no padding: A is the activation matrix [M, Cin_pad]
+    CONV_MODE_IM2COL = 2,      // general: TMA im2col over NHWC
+    CONV_MODE_PACKED_ROW = 3,  // Cin pitch 8: one K block = one filter row (S taps x 8 channels), padding materialised
+};
+
+struct ConvKernelParams {
+    int M;                 // output pixels N*P*Q
+    int out_pitch;         // elements per output pixel (Cout rounded up to 8)
+    int num_m_tiles, num_n_tiles;
+    int num_taps, taps_w, kblocks_per_tap;
+    int P, Q, PQ;
+    int stride_h, stride_w, dil_h, dil_w;
+    int corner_h, corner_w;  // im2col lower corner (= -pad)
+    int mode;
+    const float* bias;       // fp32, zero padded to a multiple of 256 entries
+    const __half* residual;  // optional NHWC tensor with the output's shape, added before the activation
+    __half* out;
+    int act;
+    float clip_lo, clip_hi;
+};
+
+struct ConvTcProblem {
+    int mode;
+    int n, h, w;            // input (for PACKED_ROW: the physically padded input)
+    int c_in;               // logical input channels (flop accounting only)
+    int c_in_pitch;         // elements per input pixel (multiple of 8)
+    int c_out, c_out_pitch;
+    int k_h, k_w, stride_h, stride_w, dil_h, dil_w;
+    int pad_t, pad_l, pad_b, pad_r;
+    const __half* x;        // NHWC
+    const __half* w_packed; // [Cout][taps][kc]
+    const float* bias;
+    const __half* residual;
+    __half* y;              // NHWC, pitch c_out_pitch
+    int act;
+    float clip_lo, clip_hi;
+    int block_n;            // 0 = auto
+};
+
+struct ConvTcLaunch {
+    CUtensorMap tm_a, tm_b;
+    ConvKernelParams p;
+    int block_n;
+    int grid;
+    double flops;  // algorithmic: 2*M*Cout*Cin*R*S
+};
+
+int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms);
+bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
+cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
+
+}  // namespace k
+}  // namespace smelter

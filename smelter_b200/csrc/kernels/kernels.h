@@ -1,0 +1,58 @@
+// Launchers of the non-GEMM kernels.  All activations are NHWC fp16 with the channel pitch `cp` a multiple
+// of 8 (one 128-bit vector = 8 channels); padded channels carry zeros / don't-care values.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <stdint.h>
+
+#include "conv_igemm.h"
+
+namespace smelter {
+namespace k {
+
+enum UnaryKind : int {
+    UN_RELU = 0, UN_SIGMOID = 1, UN_CLIP = 2, UN_TANH = 3, UN_ABS = 4, UN_EXP = 5, UN_LOG = 6, UN_ELU = 7,
+    UN_LEAKY_RELU = 8, UN_HARD_SIGMOID = 9, UN_SOFTPLUS = 10, UN_SOFTSIGN = 11, UN_IDENTITY = 12
+};
+enum BinaryKind : int { BIN_ADD = 0, BIN_SUB = 1, BIN_MUL = 2, BIN_DIV = 3 };
+enum PadMode : int { PAD_CONSTANT = 0, PAD_REFLECT = 1, PAD_EDGE = 2 };
+enum UpsampleMode : int { UP_NEAREST = 0, UP_BILINEAR = 1 };
+
+// Boundary layout conversion.  dst is [N, H+pt+pb, W+pl+pr, cp] with zero borders and zero padded channels.
+cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, int w, int cp, int pad_t, int pad_l, int pad_b,
+                         int pad_r, cudaStream_t s);
+// dst[n * dst_image_pitch + (c*H + h)*W + w] = src[n,h,w,c]
+cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s);
+
+cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s);
+cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s);
+// y = act(x * scale[c] + shift[c])  (un-fused BatchNormalization)
+cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act,
+                        cudaStream_t s);
+cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int p, int q, int kh, int kw, int sh, int sw, int ph,
+                   int pw, int is_max, cudaStream_t s);
+cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cudaStream_t s);
+cudaError_t softmax_rows(const __half* x, __half* y, size_t rows, int c, int cp, int log_softmax, cudaStream_t s);
+cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
+                       cudaStream_t s);
+cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
+                  cudaStream_t s);
+// Instance normalisation: deterministic two-kernel scheme.  `partials` holds n * splits * cp * 2 floats.
+int instance_norm_splits(int hw, int cp);
+cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
+                          int act, float* partials, cudaStream_t s);
+// copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
+cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
+                            cudaStream_t s);
+// Depthwise convolution (groups == C, multiplier 1).  w: [kh*kw][cp] fp16, bias fp32 [cp].
+cudaError_t depthwise_conv(const __half* x, const __half* w, const float* bias, __half* y, int n, int h, int wd, int cp, int p, int q,
+                           int kh, int kw, int sh, int sw, int dh, int dw, int pt, int pl, int act, float lo, float hi, cudaStream_t s);
+
+cudaError_t f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s);
+cudaError_t f16_to_f32(const __half* src, float* dst, size_t n, cudaStream_t s);
+// 64-bit order-independent checksum (sum of 32-bit words with a position-mixing multiplier), result on device.
+cudaError_t checksum64(const void* p, size_t bytes, unsigned long long* out_dev, cudaStream_t s);
+
+}  // namespace k
+}  // namespace smelter

@@ -1,0 +1,342 @@
+// Window / reduction kernels on NHWC fp16: pooling, global average pool, channel softmax, instance norm,
+// depthwise convolution.  Replaces (Sources/Smelter/Converters.swift):
+//   pool2d          MPSCNNPooling{Max,Average}Node + PyTorchPoolPadding     :607-695, Padding/PyTorchPoolPadding.swift
+//   global_avgpool  MPSCNNPoolingAverageNode + GlobalPoolPadding            :578-605
+//   softmax_rows    MPSCNN{SoftMax,LogSoftMax}Node                          :697-714, :1213-1231
+//   instance_norm   MPSCNNInstanceNormalizationNode                         :992-1054
+//   depthwise_conv  MPSCNNConvolutionNode with MPSCNNDepthWiseConvolutionDescriptor  :57-66
+// All HBM-bound; fp32 math, fp16 storage; warp-shuffle reductions.
+#include <cfloat>
+
+#include "kernels.h"
+
+namespace smelter {
+namespace k {
+
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kSMs = 148;
+
+inline int grid_for(size_t work_items, int per_block = kThreads) {
+    size_t blocks = (work_items + per_block - 1) / per_block;
+    size_t cap = size_t(kSMs) * 16;
+    if (blocks > cap) blocks = cap;
+    if (blocks < 1) blocks = 1;
+    return int(blocks);
+}
+
+struct alignas(16) Half8 {
+    __half2 v[4];
+};
+__device__ __forceinline__ Half8 ld8(const __half* p) {
+    Half8 r;
+    *reinterpret_cast<uint4*>(&r) = __ldg(reinterpret_cast<const uint4*>(p));
+    return r;
+}
+__device__ __forceinline__ void st8(__half* p, const Half8& v) { *reinterpret_cast<uint4*>(p) = *reinterpret_cast<const uint4*>(&v); }
+__device__ __forceinline__ void unpack(const Half8& h, float (&f)[8]) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        float2 t = __half22float2(h.v[i]);
+        f[2 * i] = t.x;
+        f[2 * i + 1] = t.y;
+    }
+}
+__device__ __forceinline__ Half8 pack(const float (&f)[8]) {
+    Half8 h;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) h.v[i] = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+    return h;
+}
+__device__ __forceinline__ float act_op(float v, int act, float lo, float hi) {
+    if (act == ACT_RELU) return fmaxf(v, 0.f);
+    if (act == ACT_CLIP) return fminf(fmaxf(v, lo), hi);
+    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+    return v;
+}
+
+// ---- pooling: one thread per (output pixel, 8 channels); floor mode; average divides by the full window
+//      (count_include_pad=1, the MPS/PyTorch default the reference relies on, Converters.swift:609-616).
+__global__ void __launch_bounds__(kThreads) pool2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
+                                                         int p, int q, int kh, int kw, int sh, int sw, int ph, int pw, int is_max) {
+    const size_t total = size_t(n) * p * q * cp8;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(i % cp8);
+        size_t pix = i / cp8;
+        const int oq = int(pix % q);
+        const int op = int((pix / q) % p);
+        const int img = int(pix / (size_t(q) * p));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = is_max ? -FLT_MAX : 0.f;
+        for (int r = 0; r < kh; ++r) {
+            const int iy = op * sh - ph + r;
+            if (iy < 0 || iy >= h) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int ix = oq * sw - pw + s;
+                if (ix < 0 || ix >= w) continue;
+                float f[8];
+                unpack(ld8(x + (((size_t(img) * h + iy) * w + ix) * cp8 + g) * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = is_max ? fmaxf(acc[j], f[j]) : acc[j] + f[j];
+            }
+        }
+        if (!is_max) {
+            const float inv = 1.f / float(kh * kw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        }
+        st8(y + i * 8, pack(acc));
+    }
+}
+
+// ---- global average pool: block = (n, 8-channel group chunk); threads split the pixels, shuffle + smem reduce.
+// grid = (cp8 groups, n); 256 threads over pixels.
+__global__ void __launch_bounds__(kThreads) global_avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int hw, int cp8) {
+    const int g = blockIdx.x;
+    const int img = blockIdx.y;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const __half* base = x + size_t(img) * hw * cp8 * 8 + g * 8;
+    for (int pix = threadIdx.x; pix < hw; pix += blockDim.x) {
+        float f[8];
+        unpack(ld8(base + size_t(pix) * cp8 * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+    }
+    __shared__ float red[kThreads / 32][8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], o);
+    }
+    if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[threadIdx.x >> 5][j] = acc[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        float s = 0.f;
+        for (int wv = 0; wv < blockDim.x / 32; ++wv) s += red[wv][threadIdx.x];
+        y[size_t(img) * cp8 * 8 + g * 8 + threadIdx.x] = __float2half_rn(s / float(hw));
+    }
+}
+// Many-channel / few-pixel variant (e.g. 7x7x2048): one thread per (image, 8 channels), loops over the pixels.
+__global__ void __launch_bounds__(kThreads) global_avgpool_small_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int hw,
+                                                                       int cp8) {
+    const size_t total = size_t(n) * cp8;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(i % cp8);
+        const int img = int(i / cp8);
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const __half* base = x + size_t(img) * hw * cp8 * 8 + g * 8;
+        for (int pix = 0; pix < hw; ++pix) {
+            float f[8];
+            unpack(ld8(base + size_t(pix) * cp8 * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += f[j];
+        }
+        const float inv = 1.f / float(hw);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] *= inv;
+        st8(y + i * 8, pack(acc));
+    }
+}
+
+// ---- softmax over the channel axis of each pixel: one warp per row.
+__global__ void __launch_bounds__(kThreads) softmax_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int c, int cp,
+                                                          int log_softmax) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    for (size_t row = warp; row < rows; row += nwarps) {
+        const __half* xr = x + row * cp;
+        __half* yr = y + row * cp;
+        float mx = -FLT_MAX;
+        for (int i = lane; i < c; i += 32) mx = fmaxf(mx, __half2float(xr[i]));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+        for (int i = lane; i < c; i += 32) sum += __expf(__half2float(xr[i]) - mx);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        const float lse = mx + __logf(sum);
+        for (int i = lane; i < cp; i += 32) {
+            float v = 0.f;
+            if (i < c) {
+                const float xv = __half2float(xr[i]);
+                v = log_softmax ? xv - lse : __expf(xv - mx) * inv;
+            }
+            yr[i] = __float2half_rn(v);
+        }
+    }
+}
+
+// ---- instance norm, pass 1: partial (sum, sumsq) per (image, split, channel).  Block = (split, image);
+//      thread t owns channel group t % cp8 and pixel lane t / cp8.  Deterministic: fixed reduction order.
+__global__ void __launch_bounds__(kThreads) inorm_stats_kernel(const __half* __restrict__ x, float* __restrict__ partials, int hw, int cp8,
+                                                              int splits) {
+    extern __shared__ float sm[];  // [lanes][cp8*8][2]
+    const int split = blockIdx.x, img = blockIdx.y;
+    const int lanes = blockDim.x / cp8;  // host guarantees cp8 <= blockDim.x
+    const int g = threadIdx.x % cp8;
+    const int pl = threadIdx.x / cp8;
+    const int per = (hw + splits - 1) / splits;
+    const int p0 = split * per, p1 = min(hw, p0 + per);
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (pl < lanes) {
+        const __half* base = x + size_t(img) * hw * cp8 * 8 + g * 8;
+        for (int pix = p0 + pl; pix < p1; pix += lanes) {
+            float f[8];
+            unpack(ld8(base + size_t(pix) * cp8 * 8), f);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sm[(pl * cp8 * 8 + g * 8 + j) * 2] = s1[j];
+            sm[(pl * cp8 * 8 + g * 8 + j) * 2 + 1] = s2[j];
+        }
+    }
+    __syncthreads();
+    const int cp = cp8 * 8;
+    for (int ch = threadIdx.x; ch < cp; ch += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int l = 0; l < lanes; ++l) { a += sm[(l * cp + ch) * 2]; b += sm[(l * cp + ch) * 2 + 1]; }
+        float* o = partials + ((size_t(img) * splits + split) * cp + ch) * 2;
+        o[0] = a; o[1] = b;
+    }
+}
+// pass 2: y = act((x - mean) * rstd * gamma + beta); block (chunk, image) recomputes the tiny reduction into smem.
+__global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
+                                                              const float* __restrict__ partials, const float* __restrict__ gamma,
+                                                              const float* __restrict__ beta, int hw, int cp8, int splits, float eps, int act) {
+    extern __shared__ float sm[];  // [cp][2] scale, shift
+    const int img = blockIdx.y;
+    const int cp = cp8 * 8;
+    for (int ch = threadIdx.x; ch < cp; ch += blockDim.x) {
+        double a = 0.0, b = 0.0;
+        for (int sp = 0; sp < splits; ++sp) {
+            const float* o = partials + ((size_t(img) * splits + sp) * cp + ch) * 2;
+            a += o[0]; b += o[1];
+        }
+        const double mean = a / hw;
+        double var = b / hw - mean * mean;
+        if (var < 0.0) var = 0.0;
+        const float rstd = float(1.0 / sqrt(var + double(eps)));
+        const float sc = rstd * gamma[ch];
+        sm[ch * 2] = sc;
+        sm[ch * 2 + 1] = beta[ch] - float(mean) * sc;
+    }
+    __syncthreads();
+    const size_t n8 = size_t(hw) * cp8;
+    const __half* xb = x + size_t(img) * n8 * 8;
+    __half* yb = y + size_t(img) * n8 * 8;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+        const int c0 = int(i % cp8) * 8;
+        float f[8];
+        unpack(ld8(xb + i * 8), f);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float r = f[j] * sm[(c0 + j) * 2] + sm[(c0 + j) * 2 + 1];
+            f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
+        }
+        st8(yb + i * 8, pack(f));
+    }
+}
+
+// ---- depthwise conv: one thread per (output pixel, 8 channels); weights [kh*kw][cp].
+__global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
+                                                            const float* __restrict__ bias, __half* __restrict__ y, int n, int h, int w,
+                                                            int cp8, int p, int q, int kh, int kw, int sh, int sw, int dh, int dw, int pt,
+                                                            int pl, int act, float lo, float hi) {
+    const size_t total = size_t(n) * p * q * cp8;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(i % cp8);
+        size_t pix = i / cp8;
+        const int oq = int(pix % q);
+        const int op = int((pix / q) % p);
+        const int img = int(pix / (size_t(q) * p));
+        float acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + g * 8 + j);
+        for (int r = 0; r < kh; ++r) {
+            const int iy = op * sh - pt + r * dh;
+            if (iy < 0 || iy >= h) continue;
+            for (int s = 0; s < kw; ++s) {
+                const int ix = oq * sw - pl + s * dw;
+                if (ix < 0 || ix >= w) continue;
+                float f[8], wv[8];
+                unpack(ld8(x + (((size_t(img) * h + iy) * w + ix) * cp8 + g) * 8), f);
+                unpack(ld8(wt + (size_t(r * kw + s) * cp8 + g) * 8), wv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wv[j], acc[j]);
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = act_op(acc[j], act, lo, hi);
+        st8(y + i * 8, pack(acc));
+    }
+}
+
+}  // namespace
+
+cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int p, int q, int kh, int kw, int sh, int sw, int ph, int pw,
+                   int is_max, cudaStream_t s) {
+    pool2d_kernel<<<grid_for(size_t(n) * p * q * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
+    return cudaGetLastError();
+}
+
+cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cudaStream_t s) {
+    if (hw <= 64 || size_t(n) * (cp / 8) >= size_t(kSMs) * 64) {
+        global_avgpool_small_kernel<<<grid_for(size_t(n) * (cp / 8), 64), 64, 0, s>>>(x, y, n, hw, cp / 8);
+    } else {
+        dim3 grid(cp / 8, n);
+        global_avgpool_kernel<<<grid, kThreads, 0, s>>>(x, y, hw, cp / 8);
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t softmax_rows(const __half* x, __half* y, size_t rows, int c, int cp, int log_softmax, cudaStream_t s) {
+    softmax_kernel<<<grid_for(rows * 32), kThreads, 0, s>>>(x, y, rows, c, cp, log_softmax);
+    return cudaGetLastError();
+}
+
+int instance_norm_splits(int hw, int cp) {
+    (void)cp;
+    int splits = (hw + 1023) / 1024;
+    if (splits > 256) splits = 256;
+    if (splits < 1) splits = 1;
+    return splits;
+}
+
+cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
+                          float* partials, cudaStream_t s) {
+    const int cp8 = cp / 8;
+    if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
+    const int splits = instance_norm_splits(hw, cp);
+    const int lanes = kThreads / cp8;
+    const size_t smem1 = size_t(lanes) * cp * 2 * sizeof(float);
+    // lanes * cp <= 2048 floats x 2 => at most 16 KB: no opt-in needed
+    inorm_stats_kernel<<<dim3(splits, n), kThreads, smem1, s>>>(x, partials, hw, cp8, splits);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    const size_t n8 = size_t(hw) * cp8;
+    int chunks = int((n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
+    const int cap = (kSMs * 8 + n - 1) / n;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    inorm_apply_kernel<<<dim3(chunks, n), kThreads, size_t(cp) * 2 * sizeof(float), s>>>(x, y, partials, gamma, beta, hw, cp8, splits, eps, act);
+    return cudaGetLastError();
+}
+
+cudaError_t depthwise_conv(const __half* x, const __half* w, const float* bias, __half* y, int n, int h, int wd, int cp, int p, int q, int kh,
+                           int kw, int sh, int sw, int dh, int dw, int pt, int pl, int act, float lo, float hi, cudaStream_t s) {
+    depthwise_kernel<<<grid_for(size_t(n) * p * q * (cp / 8)), kThreads, 0, s>>>(x, w, bias, y, n, h, wd, cp / 8, p, q, kh, kw, sh, sw, dh, dw,
+                                                                                pt, pl, act, lo, hi);
+    return cudaGetLastError();
+}
+
+}  // namespace k
+}  // namespace smelter

@@ -138,6 +138,9 @@ int32_t smelter_graph_encode(smelter_graph* g, void* cuda_stream, const smelter_
  * 64-bit checksum of the arena (computed on the device) to prove replicas are identical. */
 int32_t smelter_graph_broadcast_weights(smelter_graph* g, int32_t root);
 int32_t smelter_graph_weight_checksum(smelter_graph* g, uint64_t* checksum, uint64_t* bytes);
+/* The packed weight arena itself (device pointer + size), so a host that already owns a communicator
+ * (e.g. torch.distributed under torchrun) can broadcast it instead of smelter_graph_broadcast_weights. */
+int32_t smelter_graph_weight_arena(smelter_graph* g, void** device_ptr, uint64_t* bytes);
 
 /* ---- fine-grained builder (what a Swift NodeConverter would call) ----------------------------------------
  * Mirrors the five-call surface converters use on ONNXGraph (ONNXGraph.swift:259-285): output(name:),
@@ -238,6 +241,35 @@ typedef struct smelter_conv_problem {
  * CUDA-event time of `iters` back-to-back launches of the conv kernel alone, divided by iters. */
 int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, const void* x, const void* w, const float* bias,
                          const void* residual, void* y, int32_t iters, float* kernel_ms);
+
+
+/* Single non-GEMM kernels (everything that is HBM-bound on the path).  x / x2 / y are NCHW fp16 DEVICE buffers,
+ * p0 / p1 are fp32 HOST arrays of length c (scale/shift for SCALE_SHIFT, gamma/beta for INSTANCE_NORM).  The
+ * driver converts to the engine's NHWC layout, launches the kernel `iters` times between two CUDA events on the
+ * context's stream, and converts the last result back.  *kernel_ms = event time / iters (kernel only). */
+typedef enum smelter_ew_op {
+    SMELTER_EW_UNARY = 0,          /* sub = smelter_unary, alpha/beta = parameters           Converters.swift:342-476, 1056-1175 */
+    SMELTER_EW_BINARY = 1,         /* sub = smelter_binary, act = fused ReLU                 :430-464, 1177-1211 */
+    SMELTER_EW_SCALE_SHIFT = 2,    /* un-fused BatchNormalization, act = fused ReLU          :797-827 */
+    SMELTER_EW_POOL = 3,           /* sub = is_max; k/stride/pad_h/pad_w                     :607-695 */
+    SMELTER_EW_GLOBAL_AVGPOOL = 4, /*                                                        :578-605 */
+    SMELTER_EW_SOFTMAX = 5,        /* sub = log-softmax flag; channel axis                   :697-714, 1213-1231 */
+    SMELTER_EW_UPSAMPLE = 6,       /* sub = smelter_upsample_mode; scale_h/w; align_corners  :478-552 */
+    SMELTER_EW_PAD = 7,            /* sub = smelter_pad_mode; pad_h=top pad_w=left pad_b pad_r; alpha = value  :942-989 */
+    SMELTER_EW_CONCAT = 8,         /* x (c channels) ++ x2 (c2 channels)                     :554-574 */
+    SMELTER_EW_INSTANCE_NORM = 9,  /* alpha = epsilon, act = fused ReLU                      :992-1054 */
+    SMELTER_EW_LAYOUT_ROUNDTRIP = 10 /* NCHW -> NHWC -> NCHW boundary conversion only        MPSImage+Extensions.swift:26-59 */
+} smelter_ew_op;
+typedef struct smelter_ew_problem {
+    int32_t op, n, c, h, w, c2, sub, act;
+    int32_t k_h, k_w, stride_h, stride_w, pad_h, pad_w, pad_b, pad_r;
+    int32_t scale_h, scale_w, align_corners;
+    float alpha, beta;
+} smelter_ew_problem;
+int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* p, const void* x, const void* x2, const float* p0,
+                                const float* p1, void* y, int32_t iters, float* kernel_ms);
+/* Overwrite a buffer larger than L2 (126 MB) on the context's stream: benchmarks call it between timed iterations. */
+int32_t smelter_l2_flush(smelter_context* ctx);
 
 #ifdef __cplusplus
 }

@@ -66,6 +66,7 @@ int32_t smelter_context_create(int32_t device, void* cuda_stream, smelter_contex
 int32_t smelter_context_destroy(smelter_context* ctx) {
     if (!ctx) return SMELTER_OK;
     nccl_destroy(&ctx->c);
+    if (ctx->c.flush_buf) cudaFree(ctx->c.flush_buf);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
     return SMELTER_OK;
@@ -259,6 +260,14 @@ int32_t smelter_graph_broadcast_weights(smelter_graph* g, int32_t root) { ARG(g)
 int32_t smelter_graph_weight_checksum(smelter_graph* g, uint64_t* checksum, uint64_t* bytes) {
     ARG(g && checksum && bytes);
     return g->g->weight_checksum(checksum, bytes);
+}
+
+int32_t smelter_graph_weight_arena(smelter_graph* g, void** device_ptr, uint64_t* bytes) {
+    ARG(g && device_ptr && bytes);
+    if (!g->g->built()) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
+    *device_ptr = g->g->weight_arena();
+    *bytes = g->g->weight_bytes();
+    return SMELTER_OK;
 }
 
 // ---- symbol tables + builder ---------------------------------------------------------------------------------------
@@ -670,6 +679,113 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
         SM_CUDA(cudaEventRecord(B.e1, s));
     }
     SM_CUDA(k::nhwc_to_nchw(static_cast<const __half*>(B.yo), static_cast<__half*>(y), p->n, p->c_out, P, Q, ocp, long(p->c_out) * P * Q, s));
+    SM_CUDA(cudaStreamSynchronize(s));
+    if (kernel_ms) {
+        float ms = 0.f;
+        SM_CUDA(cudaEventElapsedTime(&ms, B.e0, B.e1));
+        *kernel_ms = ms / float(iters);
+    }
+    return SMELTER_OK;
+}
+
+int32_t smelter_l2_flush(smelter_context* ctx) {
+    ARG(ctx);
+    SM_CUDA(cudaSetDevice(ctx->c.device));
+    if (!ctx->c.flush_buf) {
+        ctx->c.flush_bytes = size_t(256) << 20;  // 2x the 126 MB L2
+        SM_CUDA(cudaMalloc(&ctx->c.flush_buf, ctx->c.flush_bytes));
+    }
+    SM_CUDA(cudaMemsetAsync(ctx->c.flush_buf, 0, ctx->c.flush_bytes, ctx->c.stream));
+    return SMELTER_OK;
+}
+
+int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* p, const void* x, const void* x2, const float* p0,
+                                const float* p1, void* y, int32_t iters, float* kernel_ms) {
+    ARG(ctx && p && x && y);
+    ARG(p->n > 0 && p->c > 0 && p->h > 0 && p->w > 0);
+    ARG(p->op >= SMELTER_EW_UNARY && p->op <= SMELTER_EW_LAYOUT_ROUNDTRIP);
+    SM_CUDA(cudaSetDevice(ctx->c.device));
+    cudaStream_t s = ctx->c.stream;
+    const int N = p->n, Cc = p->c, H = p->h, W = p->w;
+    const int cp = round_up(Cc, 8);
+    int oc = Cc, oh = H, ow = W;
+    switch (p->op) {
+        case SMELTER_EW_BINARY: ARG(x2); break;
+        case SMELTER_EW_SCALE_SHIFT: case SMELTER_EW_INSTANCE_NORM: ARG(p0 && p1); break;
+        case SMELTER_EW_POOL:
+            ARG(p->k_h > 0 && p->k_w > 0 && p->stride_h > 0 && p->stride_w > 0);
+            oh = pool_output_size(H, p->k_h, p->stride_h, p->pad_h);
+            ow = pool_output_size(W, p->k_w, p->stride_w, p->pad_w);
+            break;
+        case SMELTER_EW_GLOBAL_AVGPOOL: oh = ow = 1; break;
+        case SMELTER_EW_UPSAMPLE: ARG(p->scale_h >= 1 && p->scale_w >= 1); oh = H * p->scale_h; ow = W * p->scale_w; break;
+        case SMELTER_EW_PAD: oh = H + p->pad_h + p->pad_b; ow = W + p->pad_w + p->pad_r; break;
+        case SMELTER_EW_CONCAT: ARG(x2 && p->c2 > 0); oc = Cc + p->c2; break;
+        default: break;
+    }
+    if (oh <= 0 || ow <= 0) return fail(SMELTER_ERR_INCONSISTENT_STATE, "empty output");
+    const int ocp = round_up(oc, 8);
+    struct Bufs {
+        void *xi = nullptr, *x2i = nullptr, *yo = nullptr, *q0 = nullptr, *q1 = nullptr, *scratch = nullptr;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+        ~Bufs() { cudaFree(xi); cudaFree(x2i); cudaFree(yo); cudaFree(q0); cudaFree(q1); cudaFree(scratch); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+    } B;
+    const size_t in_elems = size_t(N) * H * W * cp, out_elems = size_t(N) * oh * ow * ocp;
+    SM_CUDA(cudaMalloc(&B.xi, in_elems * 2));
+    SM_CUDA(cudaMalloc(&B.yo, out_elems * 2));
+    SM_CUDA(cudaMemsetAsync(B.yo, 0xff, out_elems * 2, s));
+    SM_CUDA(k::nchw_to_nhwc(static_cast<const __half*>(x), static_cast<__half*>(B.xi), N, Cc, H, W, cp, 0, 0, 0, 0, s));
+    int c2p = 0;
+    if (x2) {
+        const int c2 = p->op == SMELTER_EW_CONCAT ? p->c2 : Cc;
+        c2p = round_up(c2, 8);
+        SM_CUDA(cudaMalloc(&B.x2i, size_t(N) * H * W * c2p * 2));
+        SM_CUDA(k::nchw_to_nhwc(static_cast<const __half*>(x2), static_cast<__half*>(B.x2i), N, c2, H, W, c2p, 0, 0, 0, 0, s));
+    }
+    if (p0 && p1) {
+        std::vector<float> a(size_t(cp), 0.f), b(size_t(cp), 0.f);
+        memcpy(a.data(), p0, size_t(Cc) * 4);
+        memcpy(b.data(), p1, size_t(Cc) * 4);
+        SM_CUDA(cudaMalloc(&B.q0, size_t(cp) * 4));
+        SM_CUDA(cudaMalloc(&B.q1, size_t(cp) * 4));
+        SM_CUDA(cudaMemcpy(B.q0, a.data(), size_t(cp) * 4, cudaMemcpyHostToDevice));
+        SM_CUDA(cudaMemcpy(B.q1, b.data(), size_t(cp) * 4, cudaMemcpyHostToDevice));
+    }
+    if (p->op == SMELTER_EW_INSTANCE_NORM)
+        SM_CUDA(cudaMalloc(&B.scratch, size_t(N) * k::instance_norm_splits(H * W, cp) * cp * 2 * sizeof(float)));
+    if (p->op == SMELTER_EW_CONCAT && ocp != oc) SM_CUDA(cudaMemsetAsync(B.yo, 0, out_elems * 2, s));
+    const __half* xi = static_cast<const __half*>(B.xi);
+    const __half* x2i = static_cast<const __half*>(B.x2i);
+    __half* yo = static_cast<__half*>(B.yo);
+    auto launch = [&]() -> cudaError_t {
+        switch (p->op) {
+            case SMELTER_EW_UNARY: return k::unary(xi, yo, in_elems, p->sub, p->alpha, p->beta, s);
+            case SMELTER_EW_BINARY: return k::binary(xi, x2i, yo, in_elems, p->sub, p->act, s);
+            case SMELTER_EW_SCALE_SHIFT:
+                return k::scale_shift(xi, yo, size_t(N) * H * W, cp, static_cast<const float*>(B.q0), static_cast<const float*>(B.q1), p->act, s);
+            case SMELTER_EW_POOL: return k::pool2d(xi, yo, N, H, W, cp, oh, ow, p->k_h, p->k_w, p->stride_h, p->stride_w, p->pad_h, p->pad_w, p->sub, s);
+            case SMELTER_EW_GLOBAL_AVGPOOL: return k::global_avgpool(xi, yo, N, H * W, cp, s);
+            case SMELTER_EW_SOFTMAX: return k::softmax_rows(xi, yo, size_t(N) * H * W, Cc, cp, p->sub, s);
+            case SMELTER_EW_UPSAMPLE: return k::upsample2d(xi, yo, N, H, W, cp, p->scale_h, p->scale_w, p->sub, p->align_corners, s);
+            case SMELTER_EW_PAD: return k::pad2d(xi, yo, N, H, W, cp, p->pad_h, p->pad_w, p->pad_b, p->pad_r, p->sub, p->alpha, s);
+            case SMELTER_EW_CONCAT: {
+                cudaError_t e = k::concat_channels(xi, yo, size_t(N) * H * W, Cc, cp, ocp, 0, s);
+                if (e != cudaSuccess) return e;
+                return k::concat_channels(x2i, yo, size_t(N) * H * W, p->c2, c2p, ocp, Cc, s);
+            }
+            case SMELTER_EW_INSTANCE_NORM:
+                return k::instance_norm(xi, yo, N, H * W, cp, static_cast<const float*>(B.q0), static_cast<const float*>(B.q1), p->alpha, p->act,
+                                        static_cast<float*>(B.scratch), s);
+            default: return cudaMemcpyAsync(yo, xi, in_elems * 2, cudaMemcpyDeviceToDevice, s);
+        }
+    };
+    SM_CUDA(cudaEventCreate(&B.e0));
+    SM_CUDA(cudaEventCreate(&B.e1));
+    if (iters < 1) iters = 1;
+    SM_CUDA(cudaEventRecord(B.e0, s));
+    for (int it = 0; it < iters; ++it) SM_CUDA(launch());
+    SM_CUDA(cudaEventRecord(B.e1, s));
+    SM_CUDA(k::nhwc_to_nchw(yo, static_cast<__half*>(y), N, oc, oh, ow, ocp, long(oc) * oh * ow, s));
     SM_CUDA(cudaStreamSynchronize(s));
     if (kernel_ms) {
         float ms = 0.f;

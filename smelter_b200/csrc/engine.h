@@ -41,6 +41,9 @@ struct Context {
     // NCCL (loaded lazily with dlopen; see nccl_shim.cc)
     void* nccl_comm = nullptr;
     int rank = 0, world = 1;
+    // benchmark helper: scratch larger than L2, written by smelter_l2_flush
+    void* flush_buf = nullptr;
+    size_t flush_bytes = 0;
 };
 
 struct Tensor {
@@ -140,6 +143,8 @@ class ONNXGraph {
     int plan_dump(int batch, std::string* out);
     int broadcast_weights(int root);
     int weight_checksum(uint64_t* sum, uint64_t* bytes);
+    void* weight_arena() const { return weight_arena_; }
+    size_t weight_bytes() const { return weight_bytes_; }
 
    private:
     int initOutputs();  // ONNXGraph.swift:197-251

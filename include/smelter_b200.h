@@ -59,6 +59,8 @@ typedef struct smelter_config {
     /* engine options (no reference counterpart) */
     int32_t enable_fusion;           /* 1 (default): fold BN, fuse bias/activation/residual into Conv epilogues */
     int32_t use_cuda_graph;          /* 1 (default): replay encode() from a captured CUDA graph */
+    int32_t defer_weights;           /* 1: build() leaves the device weight arena zero-filled; the caller must fill it with
+                                        smelter_graph_broadcast_weights (non-root ranks of a multi-GPU job). default 0 */
 } smelter_config;
 
 /* Shape (Sources/Smelter/TypeDefinitions.swift:1-33) */
@@ -127,6 +129,13 @@ int32_t smelter_graph_has_converter(const smelter_graph* g, const char* op_type,
  * and a human-readable plan dump (one line per launched kernel). */
 int32_t smelter_graph_num_launches(smelter_graph* g, int32_t batch, int32_t* n);
 int32_t smelter_graph_plan_dump(smelter_graph* g, int32_t batch, char* buf, size_t cap);
+/* Per-kernel timing of one encode: runs the plan for sources' batch WITHOUT the CUDA graph, every kernel launch
+ * bracketed by a CUDA-event pair on `cuda_stream`, `iters` passes; ms[i] = mean duration of plan step i,
+ * flops[i] / bytes[i] = its algorithmic work (conv: 2*M*N*K; others: 2 B x elements read + written), is_tensor[i] = 1
+ * for the tcgen05 conv/gemm kernel.  *n_steps receives the step count (call with cap = 0 to size the arrays). */
+int32_t smelter_graph_profile(smelter_graph* g, void* cuda_stream, const smelter_tensor* const* sources, int32_t n_sources,
+                              int32_t iters, float* ms, double* flops, double* bytes, int32_t* is_tensor, int32_t cap,
+                              int32_t* n_steps);
 
 /* ---- inference ------------------------------------------------------------------------------------------
  * MPSNNGraph.encode(to:sourceImages:) (README.md:43-44): enqueue only, no synchronisation.  `*result` is

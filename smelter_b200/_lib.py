@@ -20,7 +20,7 @@ P = C.POINTER
 
 class smelter_config(C.Structure):
     _fields_ = [("input_constraint", i32), ("bilinear_align_corners", i32), ("n_dims", i32), ("dims_axis", i32 * 8),
-                ("dims_value", i64 * 8), ("enable_fusion", i32), ("use_cuda_graph", i32)]
+                ("dims_value", i64 * 8), ("enable_fusion", i32), ("use_cuda_graph", i32), ("defer_weights", i32)]
 
 
 class smelter_shape(C.Structure):
@@ -77,6 +77,7 @@ SIGNATURES = {
     "smelter_graph_has_converter": (i32, [vp, cp, P(i32)]),
     "smelter_graph_num_launches": (i32, [vp, i32, P(i32)]),
     "smelter_graph_plan_dump": (i32, [vp, i32, C.c_char_p, sz]),
+    "smelter_graph_profile": (i32, [vp, vp, P(vp), i32, i32, P(f32), P(C.c_double), P(C.c_double), P(i32), i32, P(i32)]),
     "smelter_graph_encode": (i32, [vp, vp, P(vp), i32, P(vp)]),
     "smelter_graph_broadcast_weights": (i32, [vp, i32]),
     "smelter_graph_weight_checksum": (i32, [vp, P(u64), P(u64)]),

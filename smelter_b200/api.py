@@ -67,6 +67,7 @@ class Configuration:
     # engine options (no reference counterpart)
     enableFusion: bool = True
     useCudaGraph: bool = True
+    deferWeights: bool = False
 
     def _c(self) -> L.smelter_config:
         c = L.smelter_config()
@@ -81,6 +82,7 @@ class Configuration:
             c.dims_value[i] = value
         c.enable_fusion = int(self.enableFusion)
         c.use_cuda_graph = int(self.useCudaGraph)
+        c.defer_weights = int(self.deferWeights)
         return c
 
 
@@ -172,6 +174,11 @@ class Image:
             _check(L.lib().smelter_tensor_from_float(self._h, st, a.ctypes.data_as(C.c_void_p), a.size))
         self._keepalive = a
 
+    def copyFromPointer(self, host_ptr: int, count: int, stream: Optional[int] = None, half: bool = True) -> None:
+        """Asynchronous host->device copy from a raw (ideally pinned) host pointer holding `count` fp16 (or fp32) values."""
+        fn = L.lib().smelter_tensor_from_half if half else L.lib().smelter_tensor_from_float
+        _check(fn(self._h, C.c_void_p(stream) if stream else None, C.c_void_p(host_ptr), count))
+
     @property
     def devicePointer(self) -> int:
         p = C.c_void_p()
@@ -218,6 +225,23 @@ class NNGraph:
         dims = (C.c_int32 * 4)()
         _check(L.lib().smelter_tensor_dims(res, dims))
         return Image(self._owner.context, *dims, _handle=res, _owned=False)
+
+    def profile(self, sourceImages: Sequence[Image], iters: int = 3, stream: Optional[int] = None):
+        """Per-kernel CUDA-event timing of one encode (no CUDA graph).  Returns a list of dicts, one per launched step:
+        {desc, ms, flops, bytes, tensor}."""
+        lib = L.lib()
+        arr = (C.c_void_p * len(sourceImages))(*[img._h for img in sourceImages])
+        n = C.c_int32()
+        st = C.c_void_p(stream) if stream else None
+        cap = 4096
+        ms = (C.c_float * cap)()
+        fl = (C.c_double * cap)()
+        by = (C.c_double * cap)()
+        tc = (C.c_int32 * cap)()
+        _check(lib.smelter_graph_profile(self._owner._h, st, arr, len(sourceImages), iters, ms, fl, by, tc, cap, C.byref(n)))
+        descs = [l.split(" flops=")[0].rstrip() for l in self.planDump(sourceImages[0].shape[0]).splitlines()[1:]]
+        return [{"desc": descs[i] if i < len(descs) else "", "ms": ms[i], "flops": fl[i], "bytes": by[i], "tensor": bool(tc[i])}
+                for i in range(n.value)]
 
     def numLaunches(self, batch: int) -> int:
         n = C.c_int32()

@@ -33,6 +33,7 @@ void smelter_config_default(smelter_config* cfg) {
     cfg->n_dims = 0;                              // ONNXGraph.swift:30
     cfg->enable_fusion = 1;
     cfg->use_cuda_graph = 1;
+    cfg->defer_weights = 0;
 }
 
 // ---- context ----------------------------------------------------------------------------------------------
@@ -254,6 +255,25 @@ int32_t smelter_graph_encode(smelter_graph* g, void* cuda_stream, const smelter_
     if (rc) return rc;
     // smelter_tensor is a standard-layout wrapper whose only member is the Tensor
     *result = reinterpret_cast<const smelter_tensor*>(res);
+    return SMELTER_OK;
+}
+int32_t smelter_graph_profile(smelter_graph* g, void* cuda_stream, const smelter_tensor* const* sources, int32_t n_sources, int32_t iters,
+                              float* ms, double* flops, double* bytes, int32_t* is_tensor, int32_t cap, int32_t* n_steps) {
+    ARG(g && sources && n_steps && n_sources > 0 && n_sources <= 16 && cap >= 0);
+    const Tensor* src[16];
+    for (int i = 0; i < n_sources; ++i) { ARG(sources[i]); src[i] = &sources[i]->t; }
+    std::vector<float> v_ms;
+    std::vector<double> v_fl, v_by;
+    std::vector<int> v_tc;
+    int rc = g->g->profile(static_cast<cudaStream_t>(cuda_stream), src, n_sources, iters, &v_ms, &v_fl, &v_by, &v_tc);
+    if (rc) return rc;
+    *n_steps = int32_t(v_ms.size());
+    for (int i = 0; i < cap && size_t(i) < v_ms.size(); ++i) {
+        if (ms) ms[i] = v_ms[size_t(i)];
+        if (flops) flops[i] = v_fl[size_t(i)];
+        if (bytes) bytes[i] = v_by[size_t(i)];
+        if (is_tensor) is_tensor[i] = v_tc[size_t(i)];
+    }
     return SMELTER_OK;
 }
 int32_t smelter_graph_broadcast_weights(smelter_graph* g, int32_t root) { ARG(g); return g->g->broadcast_weights(root); }

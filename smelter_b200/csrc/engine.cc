@@ -94,6 +94,10 @@ struct Step {
     std::function<cudaError_t(cudaStream_t)> run;
     std::string desc;
     double flops = 0, bytes = 0;
+    int launches = 1;      // device kernels (or memset/memcpy nodes) this step enqueues
+    bool tensor = false;   // the tcgen05 implicit-GEMM kernel
+    bool boundary = false; // reads a caller-owned source image: launched eagerly ahead of the captured CUDA graph,
+                           // so the graph never bakes in a caller pointer and is captured once per batch size
 };
 
 struct Plan {
@@ -102,7 +106,6 @@ struct Plan {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     std::vector<__half**> src_slots;          // where each graph input's current NCHW device pointer is read from
-    std::vector<const __half*> captured_src;  // pointers baked into the captured CUDA graph
     std::vector<std::unique_ptr<__half*>> src_ptr_storage;
     std::vector<ImageShape> src_shapes;
     Tensor result;
@@ -348,7 +351,8 @@ int ONNXGraph::upload_weights() {
         }
     }
     SM_CUDA(cudaMalloc(&weight_arena_, weight_bytes_));
-    SM_CUDA(cudaMemcpy(weight_arena_, host.data(), weight_bytes_, cudaMemcpyHostToDevice));
+    if (cfg_.defer_weights) SM_CUDA(cudaMemset(weight_arena_, 0, weight_bytes_));  // filled by broadcast_weights()
+    else SM_CUDA(cudaMemcpy(weight_arena_, host.data(), weight_bytes_, cudaMemcpyHostToDevice));
     return SMELTER_OK;
 }
 
@@ -497,6 +501,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         const int cp = pitch_of(v);
         add_step("nchw_to_nhwc " + values_[size_t(v)].name, [=](cudaStream_t st) { return k::nchw_to_nhwc(*slot, dst, N, s.c, s.h, s.w, cp, 0, 0, 0, 0, st); },
                  0, double(N) * s.h * s.w * (s.c + cp) * 2);
+        plan->steps.back().boundary = true;
     }
 
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
@@ -554,6 +559,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,
                          io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0));
+                plan->steps.back().tensor = true;
                 break;
             }
             case FilterKind::BatchNorm: {
@@ -571,6 +577,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 const float eps = f.eps;
                 add_step("instance_norm " + name, [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st); }, 0,
                          io_bytes + double(N) * is.h * is.w * icp * 2);
+                plan->steps.back().launches = 2;
                 break;
             }
             case FilterKind::Unary: {
@@ -698,15 +705,18 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     if (!stream) stream = ctx_->stream;
     SM_CUDA(cudaSetDevice(ctx_->device));
     if (cfg_.use_cuda_graph) {
-        bool same = plan->exec != nullptr && plan->captured_src.size() == size_t(n_sources);
-        for (int i = 0; same && i < n_sources; ++i) same = plan->captured_src[size_t(i)] == sources[i]->ptr;
-        if (!same) {
-            if (plan->exec) { cudaGraphExecDestroy(plan->exec); plan->exec = nullptr; }
+        for (auto& st : plan->steps) {  // source-image conversions run eagerly: their pointers change per call
+            if (!st.boundary) continue;
+            cudaError_t e = st.run(stream);
+            if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
+        }
+        if (!plan->exec) {
             cudaGraph_t graph = nullptr;
             SM_CUDA(cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal));
             cudaError_t e = cudaSuccess;
             std::string where;
             for (auto& st : plan->steps) {
+                if (st.boundary) continue;
                 e = st.run(stream);
                 if (e != cudaSuccess) { where = st.desc; break; }
             }
@@ -718,8 +728,6 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
             e = cudaGraphInstantiate(&plan->exec, graph, 0);
             cudaGraphDestroy(graph);
             if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e));
-            plan->captured_src.clear();
-            for (int i = 0; i < n_sources; ++i) plan->captured_src.push_back(sources[i]->ptr);
         }
         SM_CUDA(cudaGraphLaunch(plan->exec, stream));
     } else {
@@ -737,11 +745,57 @@ int ONNXGraph::num_launches(int batch, int* n) {
     int rc = plan_for(batch, &plan);
     if (rc) return rc;
     int count = 0;
-    for (auto& st : plan->steps) {
-        count += 1;
-        if (st.desc.rfind("instance_norm", 0) == 0) count += 1;  // two kernels
-    }
+    for (auto& st : plan->steps) count += st.launches;
     *n = count;
+    return SMELTER_OK;
+}
+
+int ONNXGraph::profile(cudaStream_t stream, const Tensor* const* sources, int n_sources, int iters, std::vector<float>* ms,
+                       std::vector<double>* flops, std::vector<double>* bytes, std::vector<int>* is_tensor) {
+    if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "profile before build");
+    if (!sources || n_sources != int(input_values_.size())) return fail(SMELTER_ERR_INSUFFICIENT_INPUTS, "wrong number of sources");
+    Plan* plan = nullptr;
+    int rc = plan_for(sources[0]->n, &plan);
+    if (rc) return rc;
+    for (int i = 0; i < n_sources; ++i) {
+        const ImageShape& s = plan->src_shapes[size_t(i)];
+        const Tensor* t = sources[i];
+        if (!t || !t->ptr || t->n != plan->batch || t->c != s.c || t->h != s.h || t->w != s.w) return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "source shape mismatch");
+        *plan->src_slots[size_t(i)] = t->ptr;
+    }
+    if (!stream) stream = ctx_->stream;
+    SM_CUDA(cudaSetDevice(ctx_->device));
+    const size_t n = plan->steps.size();
+    std::vector<cudaEvent_t> ev(2 * n, nullptr);
+    auto cleanup = [&]() { for (auto e : ev) if (e) cudaEventDestroy(e); };
+    for (auto& e : ev) {
+        cudaError_t ce = cudaEventCreate(&e);
+        if (ce != cudaSuccess) { cleanup(); return fail(SMELTER_ERR_CUDA, cudaGetErrorString(ce)); }
+    }
+    ms->assign(n, 0.f);
+    flops->resize(n); bytes->resize(n); is_tensor->resize(n);
+    if (iters < 1) iters = 1;
+    for (int it = 0; it < iters; ++it) {
+        for (size_t i = 0; i < n; ++i) {
+            cudaEventRecord(ev[2 * i], stream);
+            cudaError_t ce = plan->steps[i].run(stream);
+            cudaEventRecord(ev[2 * i + 1], stream);
+            if (ce != cudaSuccess) { cleanup(); return fail(SMELTER_ERR_CUDA, "launch failed at '" + plan->steps[i].desc + "': " + cudaGetErrorString(ce)); }
+        }
+        cudaError_t ce = cudaStreamSynchronize(stream);
+        if (ce != cudaSuccess) { cleanup(); return fail(SMELTER_ERR_CUDA, cudaGetErrorString(ce)); }
+        for (size_t i = 0; i < n; ++i) {
+            float t = 0.f;
+            cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
+            (*ms)[i] += t / float(iters);
+        }
+    }
+    for (size_t i = 0; i < n; ++i) {
+        (*flops)[i] = plan->steps[i].flops;
+        (*bytes)[i] = plan->steps[i].bytes;
+        (*is_tensor)[i] = plan->steps[i].tensor ? 1 : 0;
+    }
+    cleanup();
     return SMELTER_OK;
 }
 

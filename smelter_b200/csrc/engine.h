@@ -140,6 +140,8 @@ class ONNXGraph {
 
     int plan_for(int batch, Plan** out);
     int num_launches(int batch, int* n);
+    int profile(cudaStream_t stream, const Tensor* const* sources, int n_sources, int iters, std::vector<float>* ms,
+                std::vector<double>* flops, std::vector<double>* bytes, std::vector<int>* is_tensor);
     int plan_dump(int batch, std::string* out);
     int broadcast_weights(int root);
     int weight_checksum(uint64_t* sum, uint64_t* bytes);

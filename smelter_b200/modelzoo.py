@@ -187,13 +187,15 @@ def resnet50(seed: int = 0, fold_bn: bool = True, batch: int = 1, num_classes: i
     return g.model()
 
 
-def mobilenet_v2(seed: int = 0, fold_bn: bool = True, batch: int = 1, num_classes: int = 1000, hw: int = 224) -> op.Model:
-    """torchvision MobileNetV2: 52 Conv (17 depthwise) + 35 Clip + 10 Add + GAP + Flatten + Gemm."""
+def mobilenet_v2(seed: int = 0, fold_bn: bool = True, batch: int = 1, num_classes: int = 1000, hw: int = 224, width_div: int = 1) -> op.Model:
+    """torchvision MobileNetV2: 52 Conv (17 depthwise) + 35 Clip + 10 Add + GAP + Flatten + Gemm.
+    width_div > 1 shrinks every channel count (test fixtures only)."""
     g = GraphBuilder(seed, fold_bn=fold_bn, name="mobilenet_v2")
     x = g.input("input", [batch, 3, hw, hw])
-    y = g.clip(g.conv_bn(x, 32, 3, 2, 1))
-    cfg = [(1, 16, 1, 1), (6, 24, 2, 2), (6, 32, 3, 2), (6, 64, 4, 2), (6, 96, 3, 1), (6, 160, 3, 2), (6, 320, 1, 1)]
-    c_in = 32
+    d = width_div
+    y = g.clip(g.conv_bn(x, 32 // d, 3, 2, 1))
+    cfg = [(1, 16 // d, 1, 1), (6, 24 // d, 2, 2), (6, 32 // d, 3, 2), (6, 64 // d, 4, 2), (6, 96 // d, 3, 1), (6, 160 // d, 3, 2), (6, 320 // d, 1, 1)]
+    c_in = 32 // d
     for t, c, n, s in cfg:
         for i in range(n):
             stride = s if i == 0 else 1
@@ -205,30 +207,32 @@ def mobilenet_v2(seed: int = 0, fold_bn: bool = True, batch: int = 1, num_classe
             z = g.conv_bn(z, c, 1, gain=1.0, gamma_scale=0.7)
             y = g.add(y, z) if (stride == 1 and c_in == c) else z
             c_in = c
-    y = g.clip(g.conv_bn(y, 1280, 1))
+    y = g.clip(g.conv_bn(y, 1280 // d, 1))
     y = g.flatten(g.gap(y))
     y = g.gemm(y, num_classes)
     g.output(y, [batch, num_classes])
     return g.model()
 
 
-def transformer_net(seed: int = 0, batch: int = 1, hw: int = 512) -> op.Model:
-    """pytorch/examples fast_neural_style TransformerNet: 16 Pad + 16 Conv + 15 InstanceNorm + 10 Relu + 5 Add + 2 Upsample."""
+def transformer_net(seed: int = 0, batch: int = 1, hw: int = 512, width_div: int = 1) -> op.Model:
+    """pytorch/examples fast_neural_style TransformerNet: 16 Pad + 16 Conv + 15 InstanceNorm + 10 Relu + 5 Add + 2 Upsample.
+    width_div > 1 shrinks every channel count (test fixtures only)."""
     g = GraphBuilder(seed, name="transformer_net")
     x = g.input("input", [batch, 3, hw, hw])
+    c32, c64, c128 = 32 // width_div, 64 // width_div, 128 // width_div
 
     def conv_layer(v, c, k, s, gain=2.0):
         return g.conv(g.pad(v, k // 2), c, k, s, 0, gain=gain)
 
-    y = g.relu(g.instancenorm(conv_layer(x, 32, 9, 1)))
-    y = g.relu(g.instancenorm(conv_layer(y, 64, 3, 2)))
-    y = g.relu(g.instancenorm(conv_layer(y, 128, 3, 2)))
+    y = g.relu(g.instancenorm(conv_layer(x, c32, 9, 1)))
+    y = g.relu(g.instancenorm(conv_layer(y, c64, 3, 2)))
+    y = g.relu(g.instancenorm(conv_layer(y, c128, 3, 2)))
     for _ in range(5):
-        z = g.relu(g.instancenorm(conv_layer(y, 128, 3, 1)))
-        z = g.instancenorm(conv_layer(z, 128, 3, 1, gain=1.0))
+        z = g.relu(g.instancenorm(conv_layer(y, c128, 3, 1)))
+        z = g.instancenorm(conv_layer(z, c128, 3, 1, gain=1.0))
         y = g.add(z, y)
-    y = g.relu(g.instancenorm(conv_layer(g.upsample(y, 2), 64, 3, 1)))
-    y = g.relu(g.instancenorm(conv_layer(g.upsample(y, 2), 32, 3, 1)))
+    y = g.relu(g.instancenorm(conv_layer(g.upsample(y, 2), c64, 3, 1)))
+    y = g.relu(g.instancenorm(conv_layer(g.upsample(y, 2), c32, 3, 1)))
     y = conv_layer(y, 3, 9, 1, gain=1.0)
     g.output(y, [batch, 3, hw, hw])
     return g.model()

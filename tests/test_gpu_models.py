@@ -1,0 +1,244 @@
+"""End-to-end parity of ONNXGraph(data:) -> metalGraph -> encode -> toFloatArray on the B200 against the fp32 oracle:
+golden fixtures, the four BASELINE.json model families, both model flavours, fusion on/off, CUDA graph on/off, batch
+sharding, and the reference's error behaviour.  Tolerance: 1e-2 max-abs (BASELINE.json north_star), outputs O(1)."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLDEN = sorted(glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")))
+TOL = 1e-2
+
+
+def _run(ctx, model: bytes, x: np.ndarray, **cfg):
+    from smelter_b200.api import Configuration, Image, ONNXGraph
+
+    g = ONNXGraph(model, Configuration(**cfg), context=ctx)
+    nn = g.metalGraph()
+    out = nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
+    launches = nn.numLaunches(x.shape[0])
+    g.close()
+    return out, launches
+
+
+def _oracle(model: bytes, x: np.ndarray, **kw):
+    from oracle.onnx_interp import Interpreter
+
+    return Interpreter(model, **kw).run(torch.from_numpy(x.astype(np.float32))).numpy()
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_golden_fixture(ctx, path):
+    z = np.load(path)
+    model, x, y = z["model"].tobytes(), z["x"], z["y"]
+    out, _ = _run(ctx, model, x)
+    assert np.isfinite(out).all()
+    assert np.abs(out.reshape(y.shape) - y).max() <= TOL
+
+
+@pytest.mark.parametrize("fusion", [True, False])
+@pytest.mark.parametrize("graph", [True, False])
+def test_fusion_and_cuda_graph_do_not_change_results(ctx, fusion, graph):
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "resnet_tiny.npz"))
+    out, launches = _run(ctx, z["model"].tobytes(), z["x"], enableFusion=fusion, useCudaGraph=graph)
+    assert np.abs(out - z["y"]).max() <= TOL
+    # un-fused: 53-ish extra BN/ReLU/Add launches; fused: one launch per conv + pool/gap/fc/boundary
+    assert (launches < 30) == fusion
+
+
+def test_config1_pipeline_conv_bn_relu(ctx):
+    """BASELINE.json configs[0] on the device: raw model == ONNX2MPS fp32 == ONNX2MPS --half within tolerance."""
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Format, ONNXGraph
+
+    raw = modelzoo.conv_bn_relu(seed=0).serialize()
+    x = np.random.default_rng(0).random((1, 3, 16, 16), dtype=np.float32).astype(np.float16)
+    want = _oracle(raw, x)
+    for model, fmt in ((raw, Format.onnx), (onnx2mps.convert_bytes(raw, half=False), Format.mpsFlavor), (onnx2mps.convert_bytes(raw, half=True), Format.mpsFlavor)):
+        g = ONNXGraph(model, context=ctx)
+        assert g.modelFormat == fmt
+        g.close()
+        out, launches = _run(ctx, model, x)
+        assert launches == 3  # nchw->nhwc, conv(+bn)+relu, nhwc->nchw
+        assert np.abs(out - want).max() <= 5e-3
+
+
+def test_resnet50_batch4_matches_oracle(ctx):
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    x = np.random.default_rng(1).random((4, 3, 224, 224), dtype=np.float32).astype(np.float16)
+    out, launches = _run(ctx, model, x)
+    want = _oracle(model, x)
+    assert out.shape == (4, 1000)
+    assert np.abs(out - want).max() <= TOL
+    assert (out.argmax(1) == want.argmax(1)).all()
+    assert launches == 1 + 53 + 1 + 1 + 1  # boundary + conv (all ReLU/Add fused) + maxpool + gap + fc (logits are a view)
+
+
+def test_resnet50_batch32_properties(ctx):
+    """BASELINE size (batch 32): every image's logits equal the logits of the same image run alone (images never interact,
+    SURVEY.md §8e) — bit for bit, since per-image arithmetic order does not depend on the batch."""
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Image, ONNXGraph
+
+    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    x = np.random.default_rng(2).random((32, 3, 224, 224), dtype=np.float32).astype(np.float16)
+    g = ONNXGraph(model, context=ctx)
+    nn = g.metalGraph()
+    full = nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().copy()
+    again = nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().copy()
+    assert np.array_equal(full.view(np.uint16), again.view(np.uint16))  # replay determinism
+    lo = nn.encode(sourceImages=[Image.fromArray(ctx, x[:16])]).toHalfArray().copy()
+    hi = nn.encode(sourceImages=[Image.fromArray(ctx, x[16:])]).toHalfArray().copy()
+    assert np.array_equal(np.concatenate([lo, hi]).view(np.uint16), full.view(np.uint16))  # shard == whole
+    want = _oracle(model, x[:2])
+    assert np.abs(full[:2].astype(np.float32) - want).max() <= TOL
+    g.close()
+
+
+def test_mobilenet_v2_batch1(ctx):
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = onnx2mps.convert_bytes(modelzoo.mobilenet_v2(seed=0, fold_bn=False).serialize(), half=True)
+    x = np.random.default_rng(1).random((1, 3, 224, 224), dtype=np.float32).astype(np.float16)
+    out, launches = _run(ctx, model, x)
+    want = _oracle(model, x)
+    assert np.abs(out - want).max() <= TOL
+    assert launches == 1 + 52 + 10 + 1 + 1  # boundary + conv (Clip fused) + residual Adds (linear bottleneck: not fusable into a ReLU-less conv? see DESIGN) + gap + fc
+
+
+def test_transformer_net_256(ctx):
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=256).serialize(), half=True)
+    x = np.random.default_rng(1).random((1, 3, 256, 256), dtype=np.float32).astype(np.float16)
+    out, _ = _run(ctx, model, x)
+    want = _oracle(model, x)
+    assert out.shape == (1, 3, 256, 256)
+    # InstanceNorm re-normalises every layer, so fp16 storage error does not grow; output magnitudes are O(1)
+    assert np.abs(out - want).max() <= 2e-2
+    assert np.abs(out - want).mean() <= 2e-3
+
+
+def test_batch_override_through_configuration_dims(ctx):
+    """Configuration.dims overrides input dims by axis (ONNXGraph.swift:200-202); spatial override re-plans shapes."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Configuration, Image, ONNXGraph
+
+    model = modelzoo.transformer_net(seed=5, hw=32, width_div=8).serialize()
+    x = np.random.default_rng(3).random((1, 3, 48, 40), dtype=np.float32).astype(np.float16)
+    g = ONNXGraph(model, Configuration(dims={2: 48, 3: 40}), context=ctx)
+    out = g.metalGraph().encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
+    assert out.shape == (1, 3, 48, 40)
+    assert np.abs(out - _oracle(model, x)).max() <= 2e-2
+    g.close()
+
+
+def test_bilinear_upsample_honours_align_corners(ctx):
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import BillinearUpsampling, Configuration, Image, ONNXGraph
+
+    b = modelzoo.GraphBuilder(seed=1)
+    xin = b.input("input", [1, 8, 6, 5])
+    y = b.upsample(b.conv(xin, 8, 3, 1, 1), 2, mode="linear")
+    b.output(y, [1, 8, 12, 10])
+    model = b.model().serialize()
+    x = np.random.default_rng(4).random((1, 8, 6, 5), dtype=np.float32).astype(np.float16)
+    for align in (True, False):
+        g = ONNXGraph(model, Configuration(billinearUpsamplingConfiguration=BillinearUpsampling(alignCorners=align)), context=ctx)
+        out = g.metalGraph().encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
+        assert np.abs(out - _oracle(model, x, align_corners=align)).max() <= 5e-3
+        g.close()
+
+
+def test_error_behaviour_mirrors_the_reference(ctx):
+    from smelter_b200 import modelzoo, onnx_proto as op
+    from smelter_b200.api import Errors, Image, ONNXGraph
+
+    m = modelzoo.conv_bn_relu(seed=0)
+    m.graph.node[2].op_type = "Gelu"                       # not in the registry -> unknownNodeOpType(opType:) (ONNXGraph.swift:173-174)
+    with pytest.raises(Errors) as e:
+        ONNXGraph(m.serialize(), context=ctx).metalGraph()
+    assert e.value.case == "unknownNodeOpType" and e.value.opType == "Gelu"
+
+    m = modelzoo.conv_bn_relu(seed=0)
+    m.graph.output.append(op.ValueInfo(name=m.graph.node[0].output[0], elem_type=op.FLOAT, dims=[1, 8, 16, 16]))
+    with pytest.raises(Errors) as e:                       # exactly one output (ONNXGraph.swift:178-180)
+        ONNXGraph(m.serialize(), context=ctx).metalGraph()
+    assert e.value.case == "unsupportedOutput"
+
+    m = modelzoo.conv_bn_relu(seed=0)
+    m.graph.node[0].attribute = [a for a in m.graph.node[0].attribute if a.name != "kernel_shape"]
+    with pytest.raises(Errors) as e:                       # Converters.swift:234-237
+        ONNXGraph(m.serialize(), context=ctx).metalGraph()
+    assert e.value.case == "notEnoughAttributes"
+
+    m = modelzoo.conv_bn_relu(seed=0)
+    m.graph.node[1].input[0] = "nowhere"
+    with pytest.raises(Errors) as e:
+        ONNXGraph(m.serialize(), context=ctx).metalGraph()
+    assert e.value.case == "noSuchOutput"
+
+    with pytest.raises(Errors) as e:
+        ONNXGraph(b"\x0a\x7f\x01", context=ctx)
+    assert e.value.case == "parse"
+
+    g = ONNXGraph(modelzoo.conv_bn_relu(seed=0).serialize(), context=ctx)
+    nn = g.metalGraph()
+    with pytest.raises(Errors) as e:                       # wrong source shape
+        nn.encode(sourceImages=[Image.fromArray(ctx, np.zeros((1, 3, 8, 8), np.float16))])
+    assert e.value.case == "unsupportedInput"
+    with pytest.raises(Errors) as e:
+        nn.encode(sourceImages=[])
+    assert e.value.code in (6, 100)
+    g.close()
+
+
+def test_host_language_converter_plugin(ctx):
+    """NodeConverter protocol through the C ABI (NodeConverter.swift:3-5): a Python converter for a custom op."""
+    import ctypes as C
+
+    from smelter_b200 import _lib as L, modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    m = modelzoo.conv_bn_relu(seed=0)
+    m.graph.node[2].op_type = "MyRelu6"
+    g = ONNXGraph(m.serialize(), context=ctx)
+    lib = L.lib()
+
+    def convert(handle, node):
+        name_in, name_out = C.c_char_p(), C.c_char_p()
+        assert lib.smelter_node_input(handle, node, 0, C.byref(name_in)) == 0
+        assert lib.smelter_node_output(handle, node, 0, C.byref(name_out)) == 0
+        return lib.smelter_add_unary(handle, name_in.value, 2, 0.0, 6.0, name_out.value)  # Clip(0, 6)
+
+    assert not g.hasConverter("MyRelu6")
+    g.register("MyRelu6", convert)
+    assert g.hasConverter("MyRelu6")
+    x = (np.random.default_rng(0).random((1, 3, 16, 16), dtype=np.float32) * 8).astype(np.float16)
+    out = g.metalGraph().encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
+    m.graph.node[2].op_type = "Relu"
+    want = np.minimum(_oracle(m.serialize(), x), 6.0)
+    assert np.abs(out - want).max() <= 1e-2
+    g.close()
+
+
+def test_weight_arena_checksum_and_deferred_weights(ctx):
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Configuration, ONNXGraph
+
+    model = modelzoo.conv_bn_relu(seed=0).serialize()
+    a = ONNXGraph(model, context=ctx)
+    b = ONNXGraph(model, context=ctx)
+    c = ONNXGraph(model, Configuration(deferWeights=True), context=ctx)
+    ca, cb, cc = a.metalGraph().weightChecksum(), b.metalGraph().weightChecksum(), c.metalGraph().weightChecksum()
+    assert ca == cb and ca[1] > 0
+    assert cc[0] == 0 and cc[1] == ca[1]  # zero-filled arena waiting for the broadcast
+    ptr, nbytes = a.metalGraph().weightArena()
+    assert ptr != 0 and nbytes == ca[1]
+    for g in (a, b, c):
+        g.close()

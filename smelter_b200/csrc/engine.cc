@@ -364,6 +364,7 @@ struct ArenaAlloc {
     struct Block { size_t off, size; };
     std::vector<Block> free_list;
     size_t top = 0;
+    size_t peak = 0;  // high-water mark: `top` shrinks again when trailing blocks are released
     static size_t align(size_t v) { return (v + 1023) & ~size_t(1023); }
     size_t alloc(size_t bytes) {
         bytes = align(std::max<size_t>(bytes, 16));
@@ -378,6 +379,7 @@ struct ArenaAlloc {
         }
         const size_t off = top;
         top += bytes;
+        if (top > peak) peak = top;
         return off;
     }
     void release(size_t off, size_t bytes) {
@@ -434,13 +436,35 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     std::vector<Scratch> scratch(filters_.size(), Scratch{size_t(-1), 0});   // per-filter temporary (padded input copy, IN partials, NCHW staging)
     std::vector<Scratch> scratch2(filters_.size(), Scratch{size_t(-1), 0});
 
+    // A graph input whose only reader is a packed-row (stem) convolution is converted straight into the zero-padded
+    // NHWC image that kernel wants: the boundary conversion materialises the padding, no separate pad pass.
+    std::vector<const Filter*> stem_of(values_.size(), nullptr);
+    for (int v : input_values_) {
+        const Filter* only = nullptr;
+        int readers = 0;
+        for (const Filter& f : filters_) {
+            if (f.removed) continue;
+            for (int i : f.in) if (root_of(i) == v) { ++readers; only = &f; }
+            if (f.residual >= 0 && root_of(f.residual) == v) ++readers;
+        }
+        if (readers == 1 && v != out_root && only->kind == FilterKind::Conv && only->conv_mode == k::CONV_MODE_PACKED_ROW && only->in[0] == v &&
+            (only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
+            stem_of[size_t(v)] = only;
+    }
+    auto input_bytes = [&](int v) {
+        const Filter* f = stem_of[size_t(v)];
+        if (!f) return bytes_of(v);
+        const ImageShape& s = values_[size_t(v)].shape;
+        return size_t(N) * (s.h + f->pads[0] + f->pads[2]) * (s.w + f->pads[1] + f->pads[3]) * round_up(s.c, 8) * 2;
+    };
     // graph inputs: NHWC copies produced by the boundary conversion
-    for (int v : input_values_) off[size_t(v)] = arena.alloc(bytes_of(v));
+    for (int v : input_values_) off[size_t(v)] = arena.alloc(input_bytes(v));
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
         if (f.removed) continue;
         // temporaries first (live only during this filter)
-        if (f.kind == FilterKind::Conv && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3])) {
+        if (f.kind == FilterKind::Conv && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) &&
+            stem_of[size_t(root_of(f.in[0]))] != &f) {
             const ImageShape& s = values_[size_t(f.in[0])].shape;
             scratch[fi].bytes = size_t(N) * (s.h + f.pads[0] + f.pads[2]) * (s.w + f.pads[1] + f.pads[3]) * 8 * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
@@ -468,7 +492,8 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
-            if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1)) arena.release(off[size_t(r)], bytes_of(r));
+            if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1))
+                arena.release(off[size_t(r)], values_[size_t(r)].is_input ? input_bytes(r) : bytes_of(r));
     }
     // result tensor (NCHW) unless the output value is already NCHW-compatible
     const ImageShape& os = values_[size_t(output_value_)].shape;
@@ -476,7 +501,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     size_t result_off = size_t(-1);
     if (!result_is_view) result_off = arena.alloc(size_t(N) * os.c * os.h * os.w * 2);
 
-    plan->arena_bytes = std::max<size_t>(arena.top, 1024);
+    plan->arena_bytes = std::max<size_t>(arena.peak, 1024);
     SM_CUDA(cudaMalloc(&plan->arena, plan->arena_bytes));
     char* abase = static_cast<char*>(plan->arena);
     auto ptr_of = [&](int v) { return reinterpret_cast<__half*>(abase + off[size_t(root_of(v))]); };
@@ -499,8 +524,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         plan->src_shapes.push_back(s);
         __half* dst = ptr_of(v);
         const int cp = pitch_of(v);
-        add_step("nchw_to_nhwc " + values_[size_t(v)].name, [=](cudaStream_t st) { return k::nchw_to_nhwc(*slot, dst, N, s.c, s.h, s.w, cp, 0, 0, 0, 0, st); },
-                 0, double(N) * s.h * s.w * (s.c + cp) * 2);
+        int pt = 0, pl = 0, pb = 0, pr = 0;
+        if (const Filter* sf = stem_of[size_t(v)]) { pt = sf->pads[0]; pl = sf->pads[1]; pb = sf->pads[2]; pr = sf->pads[3]; }
+        add_step(std::string(pt || pl || pb || pr ? "nchw_to_nhwc+pad0 " : "nchw_to_nhwc ") + values_[size_t(v)].name,
+                 [=](cudaStream_t st) { return k::nchw_to_nhwc(*slot, dst, N, s.c, s.h, s.w, cp, pt, pl, pb, pr, st); }, 0,
+                 double(N) * (double(s.h) * s.w * s.c + double(s.h + pt + pb) * (s.w + pl + pr) * cp) * 2);
         plan->steps.back().boundary = true;
     }
 
@@ -540,7 +568,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
                 q.x = x; q.w_packed = w; q.bias = bias; q.residual = res; q.y = y;
                 q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
-                if (f.conv_mode == k::CONV_MODE_PACKED_ROW && scratch[fi].off != size_t(-1)) {
+                if (f.conv_mode == k::CONV_MODE_PACKED_ROW && stem_of[size_t(root_of(f.in[0]))] == &f) {
+                    q.h = is.h + f.pads[0] + f.pads[2];  // the boundary conversion already wrote the padded image
+                    q.w = is.w + f.pads[1] + f.pads[3];
+                    q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+                } else if (f.conv_mode == k::CONV_MODE_PACKED_ROW && scratch[fi].off != size_t(-1)) {
                     // materialise the zero padding so one K block can span a whole filter row
                     __half* padded = reinterpret_cast<__half*>(abase + scratch[fi].off);
                     const Filter* fp = &f;
@@ -775,21 +807,47 @@ int ONNXGraph::profile(cudaStream_t stream, const Tensor* const* sources, int n_
     ms->assign(n, 0.f);
     flops->resize(n); bytes->resize(n); is_tensor->resize(n);
     if (iters < 1) iters = 1;
-    for (int it = 0; it < iters; ++it) {
-        for (size_t i = 0; i < n; ++i) {
-            cudaEventRecord(ev[2 * i], stream);
-            cudaError_t ce = plan->steps[i].run(stream);
-            cudaEventRecord(ev[2 * i + 1], stream);
-            if (ce != cudaSuccess) { cleanup(); return fail(SMELTER_ERR_CUDA, "launch failed at '" + plan->steps[i].desc + "': " + cudaGetErrorString(ce)); }
+    // In-situ timing: the whole plan is captured into one CUDA graph with an external event-record node before and
+    // after every kernel, so each duration is measured under graph replay (no host launch gaps between kernels).
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    {
+        cudaError_t ce = cudaStreamBeginCapture(stream, cudaStreamCaptureModeThreadLocal);
+        std::string where;
+        for (size_t i = 0; i < n && ce == cudaSuccess; ++i) {
+            if (plan->steps[i].boundary) continue;
+            ce = cudaEventRecordWithFlags(ev[2 * i], stream, cudaEventRecordExternal);
+            if (ce == cudaSuccess) ce = plan->steps[i].run(stream);
+            if (ce == cudaSuccess) ce = cudaEventRecordWithFlags(ev[2 * i + 1], stream, cudaEventRecordExternal);
+            if (ce != cudaSuccess) where = plan->steps[i].desc;
         }
-        cudaError_t ce = cudaStreamSynchronize(stream);
-        if (ce != cudaSuccess) { cleanup(); return fail(SMELTER_ERR_CUDA, cudaGetErrorString(ce)); }
+        cudaError_t ce2 = cudaStreamEndCapture(stream, &graph);
+        if (ce == cudaSuccess) ce = ce2;
+        if (ce == cudaSuccess) ce = cudaGraphInstantiate(&exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (ce != cudaSuccess) {
+            cleanup();
+            return fail(SMELTER_ERR_CUDA, "profile capture failed" + (where.empty() ? std::string() : " at '" + where + "'") + ": " + cudaGetErrorString(ce));
+        }
+    }
+    for (int it = 0; it < iters; ++it) {
+        cudaError_t ce = cudaSuccess;
+        for (size_t i = 0; i < n && ce == cudaSuccess; ++i) {
+            if (!plan->steps[i].boundary) continue;
+            cudaEventRecord(ev[2 * i], stream);
+            ce = plan->steps[i].run(stream);
+            cudaEventRecord(ev[2 * i + 1], stream);
+        }
+        if (ce == cudaSuccess) ce = cudaGraphLaunch(exec, stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(stream);
+        if (ce != cudaSuccess) { cudaGraphExecDestroy(exec); cleanup(); return fail(SMELTER_ERR_CUDA, std::string("profile run failed: ") + cudaGetErrorString(ce)); }
         for (size_t i = 0; i < n; ++i) {
             float t = 0.f;
             cudaEventElapsedTime(&t, ev[2 * i], ev[2 * i + 1]);
             (*ms)[i] += t / float(iters);
         }
     }
+    cudaGraphExecDestroy(exec);
     for (size_t i = 0; i < n; ++i) {
         (*flops)[i] = plan->steps[i].flops;
         (*bytes)[i] = plan->steps[i].bytes;

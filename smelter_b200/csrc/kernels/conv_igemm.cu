@@ -18,6 +18,7 @@
 #include "conv_igemm.h"
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "ptx.cuh"
@@ -32,50 +33,60 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;        // 12 warps: TMA producer, MMA issuer, TMEM allocator, (idle), 2 x 4 epilogue warps
 constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarps = 8;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+constexpr int kChunkN = 64;                           // epilogue column chunk = one 128-byte row of fp16
+constexpr uint32_t kEpiBufBytes = 32 * kChunkN * 2;   // one warp's [32 rows x 64 cols] staging tile
+constexpr uint32_t kBiasSlotBytes = kChunkN * 4;     // one warp's bias values for the current chunk (fp32)
+constexpr uint32_t kEpiBytes = kEpilogueWarps * (2 /*double buffered*/ * kEpiBufBytes + kBiasSlotBytes);
+constexpr uint32_t kSmemLimit = 227 * 1024;
 
 template <int BLOCK_N>
 struct Cfg {
     static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    // leave 2 KB for barriers + alignment slack out of 227 KB
-    static constexpr int kStages = (BLOCK_N >= 256) ? 4 : (BLOCK_N >= 128 ? 6 : 8);
+    static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - 1024 /*align*/ - 512 /*barriers*/) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
-    static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kChunks = BLOCK_N >= kChunkN ? BLOCK_N / kChunkN : 1;
+    static constexpr int kChunkCols = BLOCK_N >= kChunkN ? kChunkN : BLOCK_N;  // columns of a chunk that carry data
+    static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + 1024 + 512;
 };
 
-__device__ __forceinline__ float apply_act(float v, int act, float lo, float hi) {
-    if (act == ACT_RELU) return fmaxf(v, 0.f);
-    if (act == ACT_CLIP) return fminf(fmaxf(v, lo), hi);
-    if (act == ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-    return v;
-}
+// Sigmoid is rare on this path (no BASELINE model fuses it): keep it out of line so the hot epilogue stays small.
+__device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
 
-template <int BLOCK_N>
+template <int BLOCK_N, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ConvKernelParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res, const ConvKernelParams p) {
     using C = Cfg<BLOCK_N>;
     extern __shared__ uint8_t smem_raw[];
     // SWIZZLE_128B tiles need 1024-byte alignment.
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    const uint32_t bar_base = smem_base + C::kStages * C::kStageBytes;
+    const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
+    const uint32_t bar_base = epi_base + kEpiBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 4);
+    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };  // w in [0, 8)
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 20);
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int num_kb = p.num_taps * p.kblocks_per_tap;
+    const int my_tiles = int(blockIdx.x) < num_tiles ? (num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a);
         prefetch_tensormap(&tm_b);
+        prefetch_tensormap(&tm_out);
+        if (HAS_RES) prefetch_tensormap(&tm_res);
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
@@ -86,6 +97,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             mbar_init(tmem_full_bar(a), 1);
             mbar_init(tmem_empty_bar(a), 128);
         }
+        for (int w = 0; w < kEpilogueWarps; ++w)
+            for (int b = 0; b < 2; ++b) mbar_init(res_bar(w, b), 1);
         fence_barrier_init();
     }
     if (warp == 2) {
@@ -96,6 +109,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may overlap
+    // the previous kernel's tail; from here on we read its output (and overwrite buffers it may still be reading).
+    if (p.use_pdl) {
+        grid_dep_launch_dependents();
+        grid_dep_wait();
+    }
 
     if (warp == 0) {
         // ================= TMA producer =================
@@ -142,10 +161,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
             int stage = 0;
             uint32_t phase = 0;
-            int acc = 0;
-            uint32_t acc_phase = 0;
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-                mbar_wait(tmem_empty_bar(acc), acc_phase ^ 1);
+            for (int t = 0; t < my_tiles; ++t) {
+                const int acc = t & 1;                       // accumulator buffer == epilogue group
+                mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
                 for (int kb = 0; kb < num_kb; ++kb) {
@@ -162,72 +180,141 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
             }
         }
     } else if (warp >= kEpilogueWarp0) {
         // ================= epilogue =================
-        const int ew = warp - kEpilogueWarp0;  // == warp % 4: the TMEM lane quarter this warp may read
-        int acc = 0;
-        uint32_t acc_phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        // Two groups of four warps; group g drains accumulator buffer g, i.e. this CTA's tiles g, g+2, g+4, ... so the
+        // two groups interleave on the four SM sub-partitions and hide each other's latencies.  Within a group each warp
+        // owns 32 accumulator rows (its TMEM lane quarter) and streams them out in 64-column chunks:
+        //   TMEM -> registers -> +bias (+residual) in fp32 -> fp16 -> activation clamp (packed half2) ->
+        //   128B-swizzled smem staging -> TMA store.
+        // The residual chunk is fetched by TMA into the same staging buffer ahead of time and the result overwrites it
+        // in place (every thread reads and writes only its own 16-byte pieces), so all global traffic is whole 128-byte
+        // lines issued by the TMA unit.
+        const int ewarp = warp - kEpilogueWarp0;  // 0..7
+        const int group = ewarp >> 2;
+        const int ew = ewarp & 3;                 // == warp % 4: the TMEM lane quarter this warp may read
+        const uint32_t buf0 = epi_base + uint32_t(ewarp) * 2u * kEpiBufBytes;
+        const uint32_t bias_slot = epi_base + kEpilogueWarps * 2u * kEpiBufBytes + uint32_t(ewarp) * kBiasSlotBytes;
+        const uint32_t row_off = uint32_t(lane) * 128u;
+        const uint32_t sw = uint32_t(lane & 7);
+        const bool is_sigmoid = p.act == ACT_SIGMOID;
+        const __half2 lo2 = __float2half2_rn(p.act == ACT_RELU ? 0.f : (p.act == ACT_CLIP ? p.clip_lo : -INFINITY));
+        const __half2 hi2 = __float2half2_rn(p.act == ACT_CLIP ? p.clip_hi : INFINITY);
+        const int group_tiles = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
+        const int n_items = group_tiles * C::kChunks;  // (tile, chunk) stream of this warp
+        auto item_coords = [&](int item, int* m_row0, int* col0) {
+            const int gt = item / C::kChunks;           // kChunks is a power of two: shifts
+            const int c = item - gt * C::kChunks;
+            const int tile = int(blockIdx.x) + (2 * gt + group) * int(gridDim.x);
             const int m_tile = tile / p.num_n_tiles;
             const int n_tile = tile - m_tile * p.num_n_tiles;
-            const int m = m_tile * kBlockM + ew * 32 + lane;
-            const int n0 = n_tile * BLOCK_N;
-            mbar_wait(tmem_full_bar(acc), acc_phase);
+            *m_row0 = m_tile * kBlockM + ew * 32;
+            *col0 = n_tile * BLOCK_N + c * kChunkN;
+        };
+        auto prefetch_res = [&](int item) {  // lane 0 only; the target buffer must no longer be read by a TMA store
+            int m_row0, col0;
+            item_coords(item, &m_row0, &col0);
+            const int b = item & 1;
+            fence_proxy_async_smem();
+            mbar_expect_tx(res_bar(ewarp, b), kEpiBufBytes);
+            tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0);
+        };
+        if (HAS_RES && n_items > 0 && lane == 0) prefetch_res(0);
+        // bias of the next chunk, two columns per lane, fetched one chunk ahead (weights: no dependency on the previous kernel)
+        float2 bias_next = make_float2(0.f, 0.f);
+        if (n_items > 0) {
+            int m_row0, col0;
+            item_coords(0, &m_row0, &col0);
+            bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
+        }
+        uint32_t res_phase = 0;  // bit b = parity of res_bar(ewarp, b)
+        uint32_t acc_phase = 0;
+        int item = 0;
+        for (int gt = 0; gt < group_tiles; ++gt) {
+            mbar_wait(tmem_full_bar(group), acc_phase);
+            acc_phase ^= 1u;
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
-            const bool row_ok = m < p.M;
-            __half* out_row = p.out + size_t(row_ok ? m : 0) * p.out_pitch;
-            const __half* res_row = p.residual ? p.residual + size_t(row_ok ? m : 0) * p.out_pitch : nullptr;
+            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(group * BLOCK_N);
+            int m_row0, col0;
+            item_coords(item, &m_row0, &col0);
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 16) {
-                uint32_t v[16];
-                tmem_ld_16(taddr + uint32_t(c0), v);
-                tmem_ld_wait();
-                const int col = n0 + c0;
-                if (row_ok && col < p.out_pitch) {
-                    float f[16];
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-                    const float4* b4 = reinterpret_cast<const float4*>(p.bias + col);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) {
-                        const float4 b = __ldg(b4 + i);
-                        f[4 * i + 0] += b.x; f[4 * i + 1] += b.y; f[4 * i + 2] += b.z; f[4 * i + 3] += b.w;
-                    }
-#pragma unroll
-                    for (int h8 = 0; h8 < 2; ++h8) {
-                        if (col + 8 * h8 < p.out_pitch) {
-                            if (res_row) {
-                                const uint4 rv = *reinterpret_cast<const uint4*>(res_row + col + 8 * h8);
-                                const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                                for (int i = 0; i < 4; ++i) {
-                                    const float2 r2 = __half22float2(rh[i]);
-                                    f[8 * h8 + 2 * i] += r2.x;
-                                    f[8 * h8 + 2 * i + 1] += r2.y;
-                                }
-                            }
-                            uint4 ov;
-                            __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                            for (int i = 0; i < 4; ++i) {
-                                const float a = apply_act(f[8 * h8 + 2 * i], p.act, p.clip_lo, p.clip_hi);
-                                const float b = apply_act(f[8 * h8 + 2 * i + 1], p.act, p.clip_lo, p.clip_hi);
-                                oh[i] = __floats2half2_rn(a, b);
-                            }
-                            *reinterpret_cast<uint4*>(out_row + col + 8 * h8) = ov;
+            for (int c = 0; c < C::kChunks; ++c, ++item, col0 += kChunkN) {
+                const int b = item & 1;
+                const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
+                if (lane == 0) {
+                    if (HAS_RES) {
+                        if (item + 1 < n_items) {
+                            tma_store_wait_read<0>();  // the store of item-1 has finished reading buffer b^1
+                            prefetch_res(item + 1);
                         }
+                    } else {
+                        tma_store_wait_read<1>();      // the store of item-2 has finished reading buffer b
                     }
                 }
+                // publish this chunk's bias to the warp through smem, then start fetching the next chunk's
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
+                if (item + 1 < n_items) {
+                    int nm, ncol;
+                    item_coords(item + 1, &nm, &ncol);
+                    bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + ncol) + lane);
+                }
+                uint32_t v[C::kChunkCols];
+                tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
+                if (C::kChunkCols > 32) tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + (C::kChunkCols > 32 ? 32 : 0));
+                tmem_ld_wait();
+                if (c == C::kChunks - 1) {  // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    mbar_arrive(tmem_empty_bar(group));
+                }
+                if (HAS_RES) {
+                    mbar_wait(res_bar(ewarp, b), (res_phase >> b) & 1u);
+                    res_phase ^= 1u << b;
+                }
+                __syncwarp();  // lane 0's wait_group.read above covers the whole warp's upcoming smem writes
+#pragma unroll
+                for (int g = 0; g < C::kChunkCols / 8; ++g) {
+                    float f[8];
+                    const uint4 bq0 = ld_shared_v4(bias_slot + uint32_t(g) * 32u);        // same address in every lane: broadcast
+                    const uint4 bq1 = ld_shared_v4(bias_slot + uint32_t(g) * 32u + 16u);
+                    const float4 b0 = make_float4(__uint_as_float(bq0.x), __uint_as_float(bq0.y), __uint_as_float(bq0.z), __uint_as_float(bq0.w));
+                    const float4 b1 = make_float4(__uint_as_float(bq1.x), __uint_as_float(bq1.y), __uint_as_float(bq1.z), __uint_as_float(bq1.w));
+                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
+                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
+                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
+                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
+                    const uint32_t addr = buf + row_off + ((uint32_t(g) ^ sw) << 4);
+                    if (HAS_RES) {
+                        const uint4 rv = ld_shared_v4(addr);
+                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const float2 r2 = __half22float2(rh[i]);
+                            f[2 * i] += r2.x;
+                            f[2 * i + 1] += r2.y;
+                        }
+                    }
+                    if (is_sigmoid) {
+#pragma unroll 1
+                        for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
+                    }
+                    uint4 ov;
+                    __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
+                    st_shared_v4(addr, ov);
+                }
+                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, buf, col0, m_row0);  // rows >= M and columns >= out_pitch are clipped by the map
+                    tma_store_commit();
+                }
             }
-            tc_fence_before();
-            mbar_arrive(tmem_empty_bar(acc));
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
+        if (lane == 0) tma_store_wait<0>();
     }
 
     tc_fence_before();
@@ -273,7 +360,9 @@ bool load_driver_entry_points(std::string* err) {
 template <int BLOCK_N>
 cudaError_t set_attr_t() {
     // per device; cheap, and done at prepare time so that launches are legal inside stream capture
-    return cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N>::kSmemBytes));
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N>::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N>::kSmemBytes));
 }
 cudaError_t set_attr(int block_n) {
     switch (block_n) {
@@ -287,8 +376,18 @@ cudaError_t set_attr(int block_n) {
 
 template <int BLOCK_N>
 cudaError_t launch_t(const ConvTcLaunch& L, cudaStream_t stream) {
-    conv_igemm_kernel<BLOCK_N><<<L.grid, kThreads, Cfg<BLOCK_N>::kSmemBytes, stream>>>(L.tm_a, L.tm_b, L.p);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(L.grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = Cfg<BLOCK_N>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = L.use_pdl ? 1 : 0;
+    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, true>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_igemm_kernel<BLOCK_N, false>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
 }
 
 }  // namespace
@@ -351,6 +450,8 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
 
     const int block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), num_sms);
     L->block_n = block_n;
+    L->use_pdl = getenv("SMELTER_NO_PDL") ? 0 : 1;
+    p.use_pdl = L->use_pdl;
     {
         cudaError_t e = set_attr(block_n);
         if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
@@ -369,7 +470,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     p.corner_h = -q.pad_t;
     p.corner_w = -q.pad_l;
     p.mode = mode;
-    p.bias = q.bias; p.residual = q.residual; p.out = q.y;
+    p.bias = q.bias; p.has_residual = q.residual ? 1 : 0;
     p.act = q.act; p.clip_lo = q.clip_lo; p.clip_hi = q.clip_hi;
     L->grid = int(std::min<long>(long(p.num_m_tiles) * p.num_n_tiles, num_sms));
     L->flops = 2.0 * double(M) * q.c_out * double(q.c_in) * R * S;
@@ -385,6 +486,21 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             if (err) *err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r));
+            return false;
+        }
+    }
+    // ---- D (and the residual, same geometry): [M, out_pitch] fp16, stored / loaded as [32 rows x 64 cols] swizzled boxes ----
+    for (int which = 0; which < 2; ++which) {
+        const __half* base = which == 0 ? q.y : (q.residual ? q.residual : q.y);
+        cuuint64_t dims[2] = {cuuint64_t(q.c_out_pitch), cuuint64_t(M)};
+        cuuint64_t strides[1] = {cuuint64_t(q.c_out_pitch) * 2};
+        cuuint32_t box[2] = {cuuint32_t(kChunkN), 32};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(which == 0 ? &L->tm_out : &L->tm_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
+                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled(output) failed: " + std::to_string(int(r));
             return false;
         }
     }

@@ -27,10 +27,10 @@ struct ConvKernelParams {
     int corner_h, corner_w;  // im2col lower corner (= -pad)
     int mode;
     const float* bias;       // fp32, zero padded to a multiple of 256 entries
-    const __half* residual;  // optional NHWC tensor with the output's shape, added before the activation
-    __half* out;
+    int has_residual;        // an NHWC tensor with the output's shape (tm_res) is added before the activation
     int act;
     float clip_lo, clip_hi;
+    int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
 };
 
 struct ConvTcProblem {
@@ -52,10 +52,11 @@ struct ConvTcProblem {
 };
 
 struct ConvTcLaunch {
-    CUtensorMap tm_a, tm_b;
+    CUtensorMap tm_a, tm_b, tm_out, tm_res;
     ConvKernelParams p;
     int block_n;
     int grid;
+    int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
 };
 

@@ -240,6 +240,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(group * BLOCK_N);
             int m_row0, col0;
             item_coords(item, &m_row0, &col0);
+            int next_tile_col0 = 0;
+            if (gt + 1 < group_tiles) {
+                int nm;
+                item_coords(item + C::kChunks, &nm, &next_tile_col0);
+            }
 #pragma unroll 1
             for (int c = 0; c < C::kChunks; ++c, ++item, col0 += kChunkN) {
                 const int b = item & 1;
@@ -256,11 +261,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
                 // publish this chunk's bias to the warp through smem, then start fetching the next chunk's
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
-                if (item + 1 < n_items) {
-                    int nm, ncol;
-                    item_coords(item + 1, &nm, &ncol);
-                    bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + ncol) + lane);
-                }
+                if (c + 1 < C::kChunks) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + kChunkN) + lane);
+                else if (item + 1 < n_items) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + next_tile_col0) + lane);
                 uint32_t v[C::kChunkCols];
                 tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
                 if (C::kChunkCols > 32) tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + (C::kChunkCols > 32 ? 32 : 0));
@@ -274,20 +276,27 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     res_phase ^= 1u << b;
                 }
                 __syncwarp();  // lane 0's wait_group.read above covers the whole warp's upcoming smem writes
+                // software-pipelined over the eight 8-column groups: the bias (and residual) of group g+1 are fetched
+                // from shared memory while group g is computed, so no LDS latency sits on the dependency chain
+                constexpr int kGroups = C::kChunkCols / 8;
+                const uint32_t rowbuf = buf + row_off;
+                uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
+                uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
+                if (HAS_RES) nrv = ld_shared_v4(rowbuf + (sw << 4));
 #pragma unroll
-                for (int g = 0; g < C::kChunkCols / 8; ++g) {
+                for (int g = 0; g < kGroups; ++g) {
+                    const uint4 bq0 = nb0, bq1 = nb1, rv = nrv;
+                    if (g + 1 < kGroups) {
+                        nb0 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u);
+                        nb1 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u + 16u);
+                        if (HAS_RES) nrv = ld_shared_v4(rowbuf + ((uint32_t(g + 1) ^ sw) << 4));
+                    }
                     float f[8];
-                    const uint4 bq0 = ld_shared_v4(bias_slot + uint32_t(g) * 32u);        // same address in every lane: broadcast
-                    const uint4 bq1 = ld_shared_v4(bias_slot + uint32_t(g) * 32u + 16u);
-                    const float4 b0 = make_float4(__uint_as_float(bq0.x), __uint_as_float(bq0.y), __uint_as_float(bq0.z), __uint_as_float(bq0.w));
-                    const float4 b1 = make_float4(__uint_as_float(bq1.x), __uint_as_float(bq1.y), __uint_as_float(bq1.z), __uint_as_float(bq1.w));
-                    f[0] = __uint_as_float(v[g * 8 + 0]) + b0.x; f[1] = __uint_as_float(v[g * 8 + 1]) + b0.y;
-                    f[2] = __uint_as_float(v[g * 8 + 2]) + b0.z; f[3] = __uint_as_float(v[g * 8 + 3]) + b0.w;
-                    f[4] = __uint_as_float(v[g * 8 + 4]) + b1.x; f[5] = __uint_as_float(v[g * 8 + 5]) + b1.y;
-                    f[6] = __uint_as_float(v[g * 8 + 6]) + b1.z; f[7] = __uint_as_float(v[g * 8 + 7]) + b1.w;
-                    const uint32_t addr = buf + row_off + ((uint32_t(g) ^ sw) << 4);
+                    f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(bq0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(bq0.y);
+                    f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(bq0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(bq0.w);
+                    f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(bq1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(bq1.y);
+                    f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(bq1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(bq1.w);
                     if (HAS_RES) {
-                        const uint4 rv = ld_shared_v4(addr);
                         const __half2* rh = reinterpret_cast<const __half2*>(&rv);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
@@ -297,14 +306,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         }
                     }
                     if (is_sigmoid) {
-#pragma unroll 1
+#pragma unroll
                         for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
                     }
                     uint4 ov;
                     __half2* oh = reinterpret_cast<__half2*>(&ov);
 #pragma unroll
                     for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
-                    st_shared_v4(addr, ov);
+                    st_shared_v4(rowbuf + ((uint32_t(g) ^ sw) << 4), ov);
                 }
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();

@@ -277,6 +277,10 @@ typedef struct smelter_ew_problem {
 } smelter_ew_problem;
 int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* p, const void* x, const void* x2, const float* p0,
                                 const float* p1, void* y, int32_t iters, float* kernel_ms);
+/* Benchmark only: sustained TMA load rate of [128 pixel x 64 channel] fp16 boxes from an NHWC tensor [n,h,w,c] (zero-filled
+ * scratch), `stages` loads in flight per CTA, `iters` loads per CTA, `grid` CTAs; mode 0 = 2-D tiled, 1 = im2col (3x3 pad 1). */
+int32_t smelter_tma_probe(smelter_context* ctx, int32_t mode, int32_t c, int32_t w, int32_t h, int32_t n, int32_t stages, int32_t iters,
+                          int32_t grid, int32_t distinct, float* ms);
 /* Overwrite a buffer larger than L2 (126 MB) on the context's stream: benchmarks call it between timed iterations. */
 int32_t smelter_l2_flush(smelter_context* ctx);
 

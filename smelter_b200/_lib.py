@@ -116,6 +116,7 @@ SIGNATURES = {
     "smelter_run_conv": (i32, [vp, P(smelter_conv_problem), vp, vp, vp, vp, vp, i32, P(f32)]),
     "smelter_run_elementwise": (i32, [vp, P(smelter_ew_problem), vp, vp, vp, vp, vp, i32, P(f32)]),
     "smelter_l2_flush": (i32, [vp]),
+    "smelter_tma_probe": (i32, [vp, i32, i32, i32, i32, i32, i32, i32, i32, i32, P(f32)]),
 }
 
 _lib = None

@@ -708,6 +708,28 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
     return SMELTER_OK;
 }
 
+int32_t smelter_tma_probe(smelter_context* ctx, int32_t mode, int32_t c, int32_t w, int32_t h, int32_t n, int32_t stages, int32_t iters, int32_t grid,
+                          int32_t distinct, float* ms) {
+    ARG(ctx && ms && c >= 64 && c % 8 == 0 && w > 0 && h > 0 && n > 0 && stages >= 1 && stages <= 12 && iters > 0 && grid > 0);
+    SM_CUDA(cudaSetDevice(ctx->c.device));
+    void* x = nullptr;
+    const size_t bytes = size_t(n) * h * w * c * 2;
+    SM_CUDA(cudaMalloc(&x, bytes));
+    cudaMemsetAsync(x, 0, bytes, ctx->c.stream);
+    std::string err;
+    int rc;
+    if (mode >= 4) {  // mode 4: distinct = K slabs per instruction; mode 5: distinct = issuing warps
+        rc = k::tma_probe3(mode, c, long(n) * h * w, distinct, stages, iters, grid, static_cast<const __half*>(x), ctx->c.stream, ms, &err);
+    } else if (mode >= 2) {  // mode 2: distinct = box_c * 1000 + box_r (no swizzle); mode 3: distinct = cluster size (multicast)
+        rc = k::tma_probe2(mode, c, long(n) * h * w, mode == 2 ? distinct / 1000 : 64, mode == 2 ? distinct % 1000 : 128, mode == 3 ? distinct : 1, stages, iters,
+                           grid, static_cast<const __half*>(x), ctx->c.stream, ms, &err);
+    } else
+    rc = k::tma_probe(mode, c, w, h, n, stages, iters, grid, distinct, static_cast<const __half*>(x), ctx->c.stream, ms, &err);
+    cudaFree(x);
+    if (rc) return fail(SMELTER_ERR_CUDA, err);
+    return SMELTER_OK;
+}
+
 int32_t smelter_l2_flush(smelter_context* ctx) {
     ARG(ctx);
     SM_CUDA(cudaSetDevice(ctx->c.device));

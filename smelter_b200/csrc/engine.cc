@@ -5,6 +5,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 namespace smelter {
@@ -763,8 +764,10 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
         }
         SM_CUDA(cudaGraphLaunch(plan->exec, stream));
     } else {
+        static const bool debug_sync = getenv("SMELTER_DEBUG_SYNC") != nullptr;  // fault isolation: sync after every kernel
         for (auto& st : plan->steps) {
             cudaError_t e = st.run(stream);
+            if (e == cudaSuccess && debug_sync) e = cudaStreamSynchronize(stream);
             if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
         }
     }

@@ -33,9 +33,15 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-constexpr int kThreads = 384;        // 12 warps: TMA producer, MMA issuer, TMEM allocator, (idle), 2 x 4 epilogue warps
+// 13 warps: 0-3 TMA producers, 4-11 epilogue (two groups of four), 12 MMA issuer + TMEM allocator.
+// Four producers because TMA operations issued by one thread complete strictly one after another (~0.35 us each on
+// B200, whatever the box size — measured with tools/tma_probe.py): a single issuing thread caps an SM at one 16 KiB
+// box per 0.35 us (48 GB/s); independent issuers scale that up to the L2 limit (~125 GB/s per SM with all SMs busy).
+constexpr int kThreads = 416;
+constexpr int kNumProducers = 4;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kEpilogueWarps = 8;
+constexpr int kMmaWarp = 12;
 constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 constexpr int kChunkN = 64;                           // epilogue column chunk = one 128-byte row of fp16
 constexpr uint32_t kEpiBufBytes = 32 * kChunkN * 2;   // one warp's [32 rows x 64 cols] staging tile
@@ -50,6 +56,10 @@ struct Cfg {
     static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - 1024 /*align*/ - 512 /*barriers*/) / kStageBytes);
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
+    // Producers in use: never more than the ring has stages.  A producer only knows (from its own previous wait) that
+    // every k-block up to g - kStages has been consumed; its next k-block g + P needs k-block g + P - kStages consumed and
+    // the parity wait is only unambiguous if k-block g + P - 2*kStages already is, i.e. P <= kStages.
+    static constexpr int kProducers = kStages < kNumProducers ? kStages : kNumProducers;
     static constexpr int kChunks = BLOCK_N >= kChunkN ? BLOCK_N / kChunkN : 1;
     static constexpr int kChunkCols = BLOCK_N >= kChunkN ? kChunkN : BLOCK_N;  // columns of a chunk that carry data
     static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + 1024 + 512;
@@ -101,7 +111,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             for (int b = 0; b < 2; ++b) mbar_init(res_bar(w, b), 1);
         fence_barrier_init();
     }
-    if (warp == 2) {
+    if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, C::kTmemCols);
         tmem_relinquish();
     }
@@ -116,11 +126,13 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         grid_dep_wait();
     }
 
-    if (warp == 0) {
-        // ================= TMA producer =================
-        if (lane == 0) {
+    if (warp < kNumProducers) {
+        // ================= TMA producers =================
+        // All walk the same (tile, k-block) sequence; producer i issues the loads of every kProducers-th k-block.
+        if (lane == 0 && warp < C::kProducers) {
             int stage = 0;
             uint32_t phase = 0;
+            uint32_t turn = 0;  // k-block counter modulo kNumProducers
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
@@ -135,27 +147,30 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     base_h = p.corner_h + op * p.stride_h;
                     base_w = p.corner_w + oq * p.stride_w;
                 }
+                int tap = 0, cblk = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    const int tap = kb / p.kblocks_per_tap;
-                    const int cblk = kb - tap * p.kblocks_per_tap;
-                    mbar_wait(empty_bar(stage), phase ^ 1);
-                    const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                    const uint32_t b_dst = a_dst + kABytes;
-                    mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                    if (p.mode == CONV_MODE_TILED) {
-                        tma_load_2d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, m0);
-                    } else {
-                        const int r = tap / p.taps_w;
-                        const int s = tap - r * p.taps_w;
-                        tma_load_im2col_4d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, base_w, base_h, img,
-                                           uint16_t(s * p.dil_w), uint16_t(r * p.dil_h));
+                    if (turn == uint32_t(warp)) {
+                        mbar_wait(empty_bar(stage), phase ^ 1);
+                        const uint32_t a_dst = smem_base + stage * C::kStageBytes;
+                        const uint32_t b_dst = a_dst + kABytes;
+                        mbar_expect_tx(full_bar(stage), C::kStageBytes);
+                        if (p.mode == CONV_MODE_TILED) {
+                            tma_load_2d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, m0);
+                        } else {
+                            const int r = tap / p.taps_w;
+                            const int s = tap - r * p.taps_w;
+                            tma_load_im2col_4d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, base_w, base_h, img,
+                                               uint16_t(s * p.dil_w), uint16_t(r * p.dil_h));
+                        }
+                        tma_load_3d(&tm_b, full_bar(stage), b_dst, cblk * kBlockK, tap, n0);
                     }
-                    tma_load_3d(&tm_b, full_bar(stage), b_dst, cblk * kBlockK, tap, n0);
+                    if (++cblk == p.kblocks_per_tap) { cblk = 0; ++tap; }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (++turn == uint32_t(C::kProducers)) turn = 0;
                 }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
         if (lane == 0) {
             constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
@@ -183,8 +198,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
             }
         }
-    } else if (warp >= kEpilogueWarp0) {
-        // ================= epilogue =================
+    } else {
+        // ================= epilogue (warps 4..11) =================
         // Two groups of four warps; group g drains accumulator buffer g, i.e. this CTA's tiles g, g+2, g+4, ... so the
         // two groups interleave on the four SM sub-partitions and hide each other's latencies.  Within a group each warp
         // owns 32 accumulator rows (its TMEM lane quarter) and streams them out in 64-column chunks:
@@ -328,7 +343,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 2) {
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::kTmemCols);
     }
@@ -457,7 +472,11 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     }
     if (kc % 8) { if (err) *err = "conv: channel pitch must be a multiple of 8"; return false; }
 
-    const int block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), num_sms);
+    int block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), num_sms);
+    if (const char* force = getenv("SMELTER_FORCE_BN")) {  // tuning experiments only
+        const int v = atoi(force);
+        if (v == 32 || v == 64 || v == 128 || v == 256) block_n = v;
+    }
     L->block_n = block_n;
     L->use_pdl = getenv("SMELTER_NO_PDL") ? 0 : 1;
     p.use_pdl = L->use_pdl;
@@ -569,6 +588,292 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
         }
     }
     return true;
+}
+
+
+// ---- TMA load-rate probe (benchmarks only): one thread per CTA keeps `stages` loads of a [128 pixel x 64 channel]
+//      box in flight from an NHWC tensor and nothing consumes them; reports what the TMA unit can deliver.
+namespace {
+__global__ void __launch_bounds__(128, 1)
+tma_probe_kernel(const __grid_constant__ CUtensorMap tm, int mode, int stages, int iters, int tiles_total, int PQ, int Q, int taps_w, int taps,
+                 int distinct) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + uint32_t(stages) * kABytes;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(bars + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int issued = 0, done = 0;
+        uint32_t phase = 0;
+        int tile = distinct ? int(blockIdx.x) : 0;
+        int tap = 0;
+        while (done < iters) {
+            while (issued < iters && issued - done < stages) {
+                const int s = issued % stages;
+                mbar_expect_tx(bars + 8u * s, kABytes);
+                const int m0 = (tile % tiles_total) * kBlockM;
+                if (mode == 0) {
+                    tma_load_2d(&tm, bars + 8u * s, base + uint32_t(s) * kABytes, 0, m0);
+                } else {
+                    const int img = m0 / PQ, rem = m0 - img * PQ, op = rem / Q, oq = rem - op * Q;
+                    tma_load_im2col_4d(&tm, bars + 8u * s, base + uint32_t(s) * kABytes, 0, oq - 1, op - 1, img, uint16_t(tap % taps_w), uint16_t(tap / taps_w));
+                }
+                if (++tap == taps) { tap = 0; tile += distinct ? int(gridDim.x) : 1; }
+                ++issued;
+            }
+            const int s = done % stages;
+            mbar_wait(bars + 8u * s, phase);
+            if (++done % stages == 0) phase ^= 1;
+        }
+    }
+}
+}  // namespace
+
+int tma_probe(int mode, int c, int w, int h, int n, int stages, int iters, int grid, int distinct, const __half* x, cudaStream_t stream, float* ms,
+              std::string* err) {
+    if (!load_driver_entry_points(err)) return 1;
+    CUtensorMap tm;
+    const long M = long(n) * h * w;
+    if (mode == 0) {
+        cuuint64_t dims[2] = {cuuint64_t(c), cuuint64_t(M)};
+        cuuint64_t strides[1] = {cuuint64_t(c) * 2};
+        cuuint32_t box[2] = {kBlockK, kBlockM};
+        cuuint32_t estr[2] = {1, 1};
+        if (g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            if (err) *err = "encode tiled failed";
+            return 1;
+        }
+    } else {
+        cuuint64_t dims[4] = {cuuint64_t(c), cuuint64_t(w), cuuint64_t(h), cuuint64_t(n)};
+        cuuint64_t strides[3] = {cuuint64_t(c) * 2, cuuint64_t(c) * 2 * w, cuuint64_t(c) * 2 * w * h};
+        int lower[2] = {-1, -1}, upper[2] = {-1, -1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        if (g_encode_im2col(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(x), dims, strides, lower, upper, kBlockK, kBlockM, estr,
+                            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            if (err) *err = "encode im2col failed";
+            return 1;
+        }
+    }
+    const size_t smem = size_t(stages) * kABytes + 1024 + 256;
+    cudaFuncSetAttribute(tma_probe_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int tiles_total = int((M + kBlockM - 1) / kBlockM);
+    const int taps = mode == 0 ? 1 : 9;
+    tma_probe_kernel<<<grid, 128, smem, stream>>>(tm, mode, stages, iters, tiles_total, h * w, w, 3, taps, distinct);  // warm-up
+    cudaEventRecord(e0, stream);
+    tma_probe_kernel<<<grid, 128, smem, stream>>>(tm, mode, stages, iters, tiles_total, h * w, w, 3, taps, distinct);
+    cudaEventRecord(e1, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return 1;
+    }
+    return 0;
+}
+
+
+namespace {
+// mode 2: tiled 2-D box {box_c elems, box_r rows} (16 KiB) without swizzle; mode 3: sw128 {64,128} box fetched by a cluster of
+// `csz` CTAs, each loading 128/csz rows and multicasting them to every CTA of the cluster.
+__global__ void __launch_bounds__(128, 1)
+tma_probe2_kernel(const __grid_constant__ CUtensorMap tm, int mode, int stages, int iters, int tiles_total, int box_c, int box_r, int csz) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t bars = base + uint32_t(stages) * kABytes;
+    uint32_t rank = 0;
+    if (csz > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages; ++s) mbar_init(bars + 8u * s, 1);
+        fence_barrier_init();
+    }
+    if (csz > 1) {
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    } else {
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int issued = 0, done = 0;
+        uint32_t phase = 0;
+        int tile = int(blockIdx.x) / csz;
+        while (done < iters) {
+            while (issued < iters && issued - done < stages) {
+                const int s = issued % stages;
+                mbar_expect_tx(bars + 8u * s, kABytes);
+                const int m0 = (tile % tiles_total) * kBlockM;
+                const uint32_t dst = base + uint32_t(s) * kABytes;
+                if (mode == 2) {
+                    tma_load_2d(&tm, bars + 8u * s, dst, 0, (tile % tiles_total) * box_r);
+                } else {
+                    const int rows = kBlockM / csz;
+                    const uint16_t mask = uint16_t((1u << csz) - 1u);
+                    asm volatile(
+                        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                        ::"r"(dst + rank * uint32_t(rows) * 128u), "l"(reinterpret_cast<uint64_t>(&tm)), "r"(bars + 8u * s), "r"(0), "r"(m0 + int(rank) * rows), "h"(mask)
+                        : "memory");
+                }
+                tile += int(gridDim.x) / csz;
+                ++issued;
+            }
+            const int s = done % stages;
+            mbar_wait(bars + 8u * s, phase);
+            if (++done % stages == 0) phase ^= 1;
+        }
+    }
+    if (csz > 1) {  // nobody may exit while peers still multicast into its shared memory
+        asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+        asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    }
+}
+}  // namespace
+
+int tma_probe2(int mode, int c, long rows_total, int box_c, int box_r, int csz, int stages, int iters, int grid, const __half* x, cudaStream_t stream,
+               float* ms, std::string* err) {
+    if (!load_driver_entry_points(err)) return 1;
+    CUtensorMap tm;
+    cuuint64_t dims[2] = {cuuint64_t(c), cuuint64_t(rows_total)};
+    cuuint64_t strides[1] = {cuuint64_t(c) * 2};
+    cuuint32_t box[2] = {cuuint32_t(mode == 2 ? box_c : kBlockK), cuuint32_t(mode == 2 ? box_r : kBlockM / csz)};
+    cuuint32_t estr[2] = {1, 1};
+    if (g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                       mode == 2 ? CU_TENSOR_MAP_SWIZZLE_NONE : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+        if (err) *err = "encode tiled failed";
+        return 1;
+    }
+    const size_t smem = size_t(stages) * kABytes + 1024 + 256;
+    cudaFuncSetAttribute(tma_probe2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int tiles_total = int(rows_total / (mode == 2 ? box_r : kBlockM));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(128);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = unsigned(csz);
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, tma_probe2_kernel, tm, mode, stages, iters, tiles_total, box_c, box_r, csz);
+    cudaEventRecord(e0, stream);
+    if (e == cudaSuccess) e = cudaLaunchKernelEx(&cfg, tma_probe2_kernel, tm, mode, stages, iters, tiles_total, box_c, box_r, csz);
+    cudaEventRecord(e1, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return 1;
+    }
+    return 0;
+}
+
+
+namespace {
+// mode 4: one issuer thread, 3-D box {64, 128, slabs} (slabs x 16 KiB per instruction) over the tensor viewed as
+// {64, rows, C/64}.  mode 5: `slabs` issuer warps, each streaming its own 16 KiB boxes through its own stage ring.
+__global__ void __launch_bounds__(256, 1)
+tma_probe3_kernel(const __grid_constant__ CUtensorMap tm, int mode, int stages, int iters, int tiles_total, int slabs) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const int warp = threadIdx.x >> 5;
+    const int issuers = mode == 5 ? slabs : 1;
+    const uint32_t box_bytes = mode == 4 ? uint32_t(slabs) * kABytes : kABytes;
+    const uint32_t ring_bytes = uint32_t(stages) * box_bytes;
+    const uint32_t bars = base + uint32_t(issuers) * ring_bytes;
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < stages * issuers; ++s) mbar_init(bars + 8u * s, 1);
+        fence_barrier_init();
+    }
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && warp < issuers) {
+        const uint32_t my_base = base + uint32_t(warp) * ring_bytes;
+        const uint32_t my_bars = bars + 8u * uint32_t(warp * stages);
+        int issued = 0, done = 0;
+        uint32_t phase = 0;
+        int tile = int(blockIdx.x) * issuers + warp;
+        while (done < iters) {
+            while (issued < iters && issued - done < stages) {
+                const int s = issued % stages;
+                mbar_expect_tx(my_bars + 8u * s, box_bytes);
+                const int m0 = (tile % tiles_total) * kBlockM;
+                if (mode == 4) tma_load_3d(&tm, my_bars + 8u * s, my_base + uint32_t(s) * box_bytes, 0, m0, 0);
+                else tma_load_2d(&tm, my_bars + 8u * s, my_base + uint32_t(s) * box_bytes, 0, m0);
+                tile += int(gridDim.x) * issuers;
+                ++issued;
+            }
+            const int s = done % stages;
+            mbar_wait(my_bars + 8u * s, phase);
+            if (++done % stages == 0) phase ^= 1;
+        }
+    }
+}
+}  // namespace
+
+int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
+               std::string* err) {
+    if (!load_driver_entry_points(err)) return 1;
+    CUtensorMap tm;
+    CUresult r;
+    if (mode == 4) {
+        cuuint64_t dims[3] = {64, cuuint64_t(rows_total), cuuint64_t(c / 64)};
+        cuuint64_t strides[2] = {cuuint64_t(c) * 2, 128};
+        cuuint32_t box[3] = {64, kBlockM, cuuint32_t(slabs)};
+        cuuint32_t estr[3] = {1, 1, 1};
+        r = g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else {
+        cuuint64_t dims[2] = {cuuint64_t(c), cuuint64_t(rows_total)};
+        cuuint64_t strides[1] = {cuuint64_t(c) * 2};
+        cuuint32_t box[2] = {kBlockK, kBlockM};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encode_tiled(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    }
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "encode failed " + std::to_string(int(r));
+        return 1;
+    }
+    const int issuers = mode == 5 ? slabs : 1;
+    const size_t smem = size_t(stages) * issuers * (mode == 4 ? slabs : 1) * kABytes + 1024 + 512;
+    if (smem > kSmemLimit) {
+        if (err) *err = "too much shared memory";
+        return 1;
+    }
+    cudaFuncSetAttribute(tma_probe3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int tiles_total = int(rows_total / kBlockM);
+    tma_probe3_kernel<<<grid, 256, smem, stream>>>(tm, mode, stages, iters, tiles_total, slabs);
+    cudaEventRecord(e0, stream);
+    tma_probe3_kernel<<<grid, 256, smem, stream>>>(tm, mode, stages, iters, tiles_total, slabs);
+    cudaEventRecord(e1, stream);
+    cudaError_t e = cudaStreamSynchronize(stream);
+    if (e == cudaSuccess) cudaEventElapsedTime(ms, e0, e1);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    if (e != cudaSuccess) {
+        if (err) *err = cudaGetErrorString(e);
+        return 1;
+    }
+    return 0;
 }
 
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream) {

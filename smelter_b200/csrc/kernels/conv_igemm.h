@@ -63,6 +63,13 @@ struct ConvTcLaunch {
 int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms);
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
+// benchmark only: TMA load rate of [128 x 64] fp16 boxes; mode 0 = 2-D tiled over [N*H*W, C], 1 = im2col (3x3, pad 1)
+int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
+               std::string* err);
+int tma_probe2(int mode, int c, long rows_total, int box_c, int box_r, int csz, int stages, int iters, int grid, const __half* x, cudaStream_t stream,
+               float* ms, std::string* err);
+int tma_probe(int mode, int c, int w, int h, int n, int stages, int iters, int grid, int distinct, const __half* x, cudaStream_t stream, float* ms,
+              std::string* err);
 
 }  // namespace k
 }  // namespace smelter

@@ -33,12 +33,15 @@ namespace {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
 constexpr int kUmmaK = 16;
-// 13 warps: 0-3 TMA producers, 4-11 epilogue (two groups of four), 12 MMA issuer + TMEM allocator.
-// Four producers because TMA operations issued by one thread complete strictly one after another (~0.35 us each on
+// 16 warps (512 threads x 128 registers = the whole register file): 0-3 TMA producers of the A (activation) operand,
+// 4-11 epilogue (two groups of four), 12 MMA issuer + TMEM allocator, 13-15 TMA producers of the B (weight) operand.
+// Several producers because TMA operations issued by one thread complete strictly one after another (~0.35 us each on
 // B200, whatever the box size — measured with tools/tma_probe.py): a single issuing thread caps an SM at one 16 KiB
 // box per 0.35 us (48 GB/s); independent issuers scale that up to the L2 limit (~125 GB/s per SM with all SMs busy).
-constexpr int kThreads = 416;
-constexpr int kNumProducers = 4;
+constexpr int kThreads = 512;
+constexpr int kNumProducers = 4;      // A operand (im2col boxes are the slower ones to issue)
+constexpr int kNumBProducers = 3;     // B operand
+constexpr int kBProducerWarp0 = 13;
 constexpr int kEpilogueWarp0 = 4;
 constexpr int kEpilogueWarps = 8;
 constexpr int kMmaWarp = 12;
@@ -60,6 +63,7 @@ struct Cfg {
     // every k-block up to g - kStages has been consumed; its next k-block g + P needs k-block g + P - kStages consumed and
     // the parity wait is only unambiguous if k-block g + P - 2*kStages already is, i.e. P <= kStages.
     static constexpr int kProducers = kStages < kNumProducers ? kStages : kNumProducers;
+    static constexpr int kBProducers = kStages < kNumBProducers ? kStages : kNumBProducers;
     static constexpr int kChunks = BLOCK_N >= kChunkN ? BLOCK_N / kChunkN : 1;
     static constexpr int kChunkCols = BLOCK_N >= kChunkN ? kChunkN : BLOCK_N;  // columns of a chunk that carry data
     static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + 1024 + 512;
@@ -100,7 +104,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(full_bar(s), 1);
+            mbar_init(full_bar(s), 2);   // one arrive.expect_tx from the A producer, one from the B producer
             mbar_init(empty_bar(s), 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -126,20 +130,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         grid_dep_wait();
     }
 
-    if (warp < kNumProducers) {
+    if (warp < kNumProducers || warp >= kBProducerWarp0) {
         // ================= TMA producers =================
-        // All walk the same (tile, k-block) sequence; producer i issues the loads of every kProducers-th k-block.
-        if (lane == 0 && warp < C::kProducers) {
+        // All walk the same (tile, k-block) sequence; producer i of an operand issues the loads of every kProducers-th
+        // k-block of that operand.  Both operands of a k-block land in the same stage and complete the same full barrier.
+        const bool is_a = warp < kNumProducers;
+        const int me = is_a ? warp : warp - kBProducerWarp0;
+        const int n_prod = is_a ? C::kProducers : C::kBProducers;
+        const bool leader = elect_one();  // whole warp runs the loop (uniform waits); the elected lane issues the TMA
+        if (me < n_prod && !(p.debug_flags & 32)) {
             int stage = 0;
             uint32_t phase = 0;
-            uint32_t turn = 0;  // k-block counter modulo kNumProducers
+            uint32_t turn = 0;  // k-block counter modulo the number of producers of this operand
             for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
                 const int m0 = m_tile * kBlockM;
                 const int n0 = n_tile * BLOCK_N;
                 int img = 0, base_h = 0, base_w = 0;
-                if (p.mode != CONV_MODE_TILED) {
+                if (is_a && p.mode != CONV_MODE_TILED) {
                     img = m0 / p.PQ;
                     const int rem = m0 - img * p.PQ;
                     const int op = rem / p.Q;
@@ -149,54 +158,72 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
                 int tap = 0, cblk = 0;
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (turn == uint32_t(warp)) {
+                    if (turn == uint32_t(me)) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                        const uint32_t b_dst = a_dst + kABytes;
-                        mbar_expect_tx(full_bar(stage), C::kStageBytes);
-                        if (p.mode == CONV_MODE_TILED) {
-                            tma_load_2d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, m0);
+                        if (!leader) {
+                        } else if (p.debug_flags & 16) {
+                            mbar_arrive(full_bar(stage));
+                        } else if (is_a) {
+                            mbar_expect_tx(full_bar(stage), kABytes);
+                            if (p.mode == CONV_MODE_TILED) {
+                                tma_load_2d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, m0);
+                            } else {
+                                const int r = tap / p.taps_w;
+                                const int s = tap - r * p.taps_w;
+                                tma_load_im2col_4d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, base_w, base_h, img,
+                                                   uint16_t(s * p.dil_w), uint16_t(r * p.dil_h));
+                            }
                         } else {
-                            const int r = tap / p.taps_w;
-                            const int s = tap - r * p.taps_w;
-                            tma_load_im2col_4d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, base_w, base_h, img,
-                                               uint16_t(s * p.dil_w), uint16_t(r * p.dil_h));
+                            mbar_expect_tx(full_bar(stage), C::kBBytes);
+                            tma_load_3d(&tm_b, full_bar(stage), a_dst + kABytes, cblk * kBlockK, tap, n0);
                         }
-                        tma_load_3d(&tm_b, full_bar(stage), b_dst, cblk * kBlockK, tap, n0);
                     }
                     if (++cblk == p.kblocks_per_tap) { cblk = 0; ++tap; }
                     if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-                    if (++turn == uint32_t(C::kProducers)) turn = 0;
+                    if (++turn == uint32_t(n_prod)) turn = 0;
                 }
             }
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
-        if (lane == 0) {
-            constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const int acc = t & 1;                       // accumulator buffer == epilogue group
-                mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
+        // The whole warp runs the loop (barrier waits are warp-uniform); one elected lane issues the tcgen05 instructions.
+        // This single instruction stream feeds the tensor core, so it is kept minimal: the shared-memory descriptors are
+        // (constant high word, low word = stage base >> 4) and the k-advance is an immediate add.
+        constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
+        constexpr uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);  // SBO, version, SWIZZLE_128B
+        constexpr uint32_t desc_lbo = 1u << 16;
+        const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | desc_lbo;
+        constexpr uint32_t kStage16 = C::kStageBytes >> 4;
+        constexpr uint32_t kB16 = kABytes >> 4;
+        const bool leader = elect_one();
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int t = 0; t < my_tiles; ++t) {
+            const int acc = t & 1;                       // accumulator buffer == epilogue group
+            mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+            uint32_t accumulate = 0;
+            for (int kb = 0; kb < num_kb; ++kb) {
+                if (!(p.debug_flags & 32)) mbar_wait(full_bar(stage), phase);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    mbar_wait(full_bar(stage), phase);
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_base + stage * C::kStageBytes;
-                    const uint64_t a_desc = make_sw128_kmajor_desc(a_addr);
-                    const uint64_t b_desc = make_sw128_kmajor_desc(a_addr + kABytes);
-#pragma unroll
-                    for (int k = 0; k < kBlockK / kUmmaK; ++k) {
-                        // advance K inside the swizzle atom: +32 bytes -> +2 in the (>>4) address field
-                        umma_f16(tmem_d, a_desc + uint64_t(2 * k), b_desc + uint64_t(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+                if (leader) {
+                    const uint64_t a_desc = desc_hi | uint64_t(a_lo0 + uint32_t(stage) * kStage16);
+                    const uint64_t b_desc = a_desc + kB16;
+                    if (!(p.debug_flags & 64)) {
+                        umma_f16(tmem_d, a_desc, b_desc, idesc, accumulate);
+                        umma_f16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);   // +32 bytes along K inside the swizzle atom
+                        umma_f16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
+                        umma_f16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
                     }
-                    umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (!(p.debug_flags & 32)) umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
                 }
-                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
+                accumulate = 1u;
+                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
             }
+            if (leader) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
+            __syncwarp();
         }
     } else {
         // ================= epilogue (warps 4..11) =================
@@ -480,6 +507,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     L->block_n = block_n;
     L->use_pdl = getenv("SMELTER_NO_PDL") ? 0 : 1;
     p.use_pdl = L->use_pdl;
+    { const char* dbg = getenv("SMELTER_CONV_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
     {
         cudaError_t e = set_attr(block_n);
         if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
@@ -793,7 +821,7 @@ tma_probe3_kernel(const __grid_constant__ CUtensorMap tm, int mode, int stages, 
     extern __shared__ uint8_t smem_raw[];
     const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const int warp = threadIdx.x >> 5;
-    const int issuers = mode == 5 ? slabs : 1;
+    const int issuers = mode >= 5 ? slabs : 1;
     const uint32_t box_bytes = mode == 4 ? uint32_t(slabs) * kABytes : kABytes;
     const uint32_t ring_bytes = uint32_t(stages) * box_bytes;
     const uint32_t bars = base + uint32_t(issuers) * ring_bytes;
@@ -802,12 +830,13 @@ tma_probe3_kernel(const __grid_constant__ CUtensorMap tm, int mode, int stages, 
         fence_barrier_init();
     }
     __syncthreads();
-    if ((threadIdx.x & 31) == 0 && warp < issuers) {
-        const uint32_t my_base = base + uint32_t(warp) * ring_bytes;
-        const uint32_t my_bars = bars + 8u * uint32_t(warp * stages);
+    const int me = mode == 6 ? int(threadIdx.x) : warp;  // mode 6: the issuers are lanes of warp 0
+    if ((mode == 6 ? (warp == 0 && me < issuers) : ((threadIdx.x & 31) == 0 && warp < issuers))) {
+        const uint32_t my_base = base + uint32_t(me) * ring_bytes;
+        const uint32_t my_bars = bars + 8u * uint32_t(me * stages);
         int issued = 0, done = 0;
         uint32_t phase = 0;
-        int tile = int(blockIdx.x) * issuers + warp;
+        int tile = int(blockIdx.x) * issuers + me;
         while (done < iters) {
             while (issued < iters && issued - done < stages) {
                 const int s = issued % stages;
@@ -850,7 +879,7 @@ int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iter
         if (err) *err = "encode failed " + std::to_string(int(r));
         return 1;
     }
-    const int issuers = mode == 5 ? slabs : 1;
+    const int issuers = mode >= 5 ? slabs : 1;
     const size_t smem = size_t(stages) * issuers * (mode == 4 ? slabs : 1) * kABytes + 1024 + 512;
     if (smem > kSmemLimit) {
         if (err) *err = "too much shared memory";

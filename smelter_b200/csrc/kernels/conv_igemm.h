@@ -30,6 +30,7 @@ struct ConvKernelParams {
     int has_residual;        // an NHWC tensor with the output's shape (tm_res) is added before the activation
     int act;
     float clip_lo, clip_hi;
+    int debug_flags;         // perf experiments only (env SMELTER_CONV_DEBUG): 16 = producers skip the TMA loads (results wrong)
     int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
 };
 

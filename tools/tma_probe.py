@@ -9,11 +9,8 @@ def run(label, mode, c, stages, iters, grid, extra, kib_per_iter):
     _check(lib.smelter_tma_probe(ctx._h, mode, c, 56, 56, 32, stages, iters, grid, extra, C.byref(ms)))
     gb = grid * iters * kib_per_iter * 1024 / (ms.value * 1e-3) / 1e9
     print(f"{label:40s} stages={stages} grid={grid:3d}: {ms.value*1e3/iters:7.3f} us/iter  {gb/grid:6.1f} GB/s/SM delivered  {gb/1e3:6.2f} TB/s total", flush=True)
-run("1 issuer, 16KiB box", 0, 256, 4, 400, 148, 1, 16)
-for slabs in (1, 2, 4):
-    run(f"1 issuer, 3-D box {slabs}x16KiB per instr", 4, 256, 2, 400, 148, slabs, 16 * slabs)
-    run(f"1 issuer, 3-D box {slabs}x16KiB per instr", 4, 256, 2, 400, 1, slabs, 16 * slabs)
-for warps in (1, 2, 4, 8):
-    st = 2 if warps == 8 else 3
-    run(f"{warps} issuer warps x 16KiB boxes", 5, 256, st, 400, 148, warps, 16 * warps)
-    run(f"{warps} issuer warps x 16KiB boxes", 5, 256, st, 400, 1, warps, 16 * warps)
+for n in (1, 2, 4, 6):
+    run(f"{n} issuer LANES of one warp x 16KiB", 6, 256, 2, 400, 148, n, 16 * n)
+    run(f"{n} issuer LANES of one warp x 16KiB", 6, 256, 2, 400, 1, n, 16 * n)
+for n in (2, 4, 6):
+    run(f"{n} issuer warps x 16KiB", 5, 256, 2, 400, 148, n, 16 * n)

@@ -247,18 +247,27 @@ def run_native(args) -> int:
     clocks = sampler.stop(lo, hi)
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with CUDA events --------------------
+    # Every kernel of one encode is bracketed by CUDA-event record nodes inside a captured graph (smelter_graph_profile), which
+    # gives each kernel's duration in situ.  The event nodes themselves cost a few us per kernel and defeat PDL overlap, so the
+    # per-kernel numbers are used for the conv kernels' SHARE of the step; the absolute duration is pinned to the event-timed
+    # step above: conv_ms = ms_per_step x share.  Both the raw and the pinned figures are reported.
     prof = nn.profile([images[0]], iters=5, stream=stream.cuda_stream)
     conv = [p for p in prof if p["tensor"]]
-    conv_ms = sum(p["ms"] for p in conv)
+    conv_ms_raw = sum(p["ms"] for p in conv)
     conv_flops = sum(p["flops"] for p in conv)
-    total_ms = sum(p["ms"] for p in prof)
+    total_ms_raw = sum(p["ms"] for p in prof)
+    share = conv_ms_raw / total_ms_raw if total_ms_raw else 0.0
+    step_ms = elapsed_ms / K
+    conv_ms = step_ms * share
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": None, "kernel": "conv_igemm_kernel<BLOCK_N> (53 conv + 1 gemm launches per step, aggregated)",
-                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": conv_ms / total_ms if total_ms else None,
-                "launch_ms_sum": conv_ms, "flops_per_step": conv_flops,
-                "e2e_frac_of_conv_roofline": value / world / (pk["tflops_sustained"] * 1e12 / FLOPS_PER_IMAGE)}
+                "traffic": None, "kernel": "conv_igemm_kernel<BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
+                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": share,
+                "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
+                "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,
+                "how": "algorithmic FLOPs (2*M*N*K, SURVEY 8d) / (event-timed step x conv share from in-graph per-kernel events)",
+                "step_frac_of_conv_roofline": value / world / (pk["tflops_sustained"] * 1e12 / FLOPS_PER_IMAGE)}
     if rank == 0:
         outdir = os.path.join(ROOT, "gpurun_out")
         try:

@@ -102,17 +102,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         prefetch_tensormap(&tm_out);
         if (HAS_RES) prefetch_tensormap(&tm_res);
     }
-    if (warp == 1 && lane == 0) {
-        for (int s = 0; s < C::kStages; ++s) {
-            mbar_init(full_bar(s), 2);   // one arrive.expect_tx from the A producer, one from the B producer
-            mbar_init(empty_bar(s), 1);
+    if (warp == 1) {  // one barrier per lane, all initialised in parallel
+        if (lane < C::kStages) {
+            mbar_init(full_bar(lane), 2);   // one arrive.expect_tx from the A producer, one from the B producer
+            mbar_init(empty_bar(lane), 1);
+        } else if (lane < C::kStages + 2) {
+            mbar_init(tmem_full_bar(lane - C::kStages), 1);
+            mbar_init(tmem_empty_bar(lane - C::kStages), 128);
+        } else if (lane >= 16) {
+            mbar_init(res_bar((lane - 16) >> 1, lane & 1), 1);
         }
-        for (int a = 0; a < 2; ++a) {
-            mbar_init(tmem_full_bar(a), 1);
-            mbar_init(tmem_empty_bar(a), 128);
-        }
-        for (int w = 0; w < kEpilogueWarps; ++w)
-            for (int b = 0; b < 2; ++b) mbar_init(res_bar(w, b), 1);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) {
@@ -365,7 +364,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
             }
         }
-        if (lane == 0) tma_store_wait<0>();
+        if (lane == 0) tma_store_wait_read<0>();  // smem must stay valid until read; global visibility comes with grid completion
     }
 
     tc_fence_before();

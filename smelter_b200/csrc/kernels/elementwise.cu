@@ -21,7 +21,7 @@ constexpr int kSMs = 148;
 
 inline int grid_for(size_t work_items, int per_block = kThreads) {
     size_t blocks = (work_items + per_block - 1) / per_block;
-    size_t cap = size_t(kSMs) * 16;
+    size_t cap = size_t(kSMs) * 64;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return int(blocks);

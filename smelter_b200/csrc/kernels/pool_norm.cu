@@ -20,7 +20,7 @@ constexpr int kSMs = 148;
 
 inline int grid_for(size_t work_items, int per_block = kThreads) {
     size_t blocks = (work_items + per_block - 1) / per_block;
-    size_t cap = size_t(kSMs) * 16;
+    size_t cap = size_t(kSMs) * 64;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return int(blocks);
@@ -288,9 +288,44 @@ cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int 
     return cudaGetLastError();
 }
 
+// Few-pixel variant with more parallelism (e.g. 7x7x2048 x 32 images): 8 lanes share one (image, 8-channel group), each
+// summing every 8th pixel, then a 3-step shuffle reduction.  Consecutive 8-lane teams read consecutive 16-byte vectors.
+__global__ void __launch_bounds__(kThreads) global_avgpool_team_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int hw,
+                                                                      int cp8) {
+    const size_t total = size_t(n) * cp8;
+    const int sub = threadIdx.x & 7;
+    for (size_t i = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 3; i < ((total + 31) & ~size_t(31)); i += (size_t(gridDim.x) * blockDim.x) >> 3) {
+        const bool live = i < total;
+        const int g = live ? int(i % cp8) : 0;
+        const int img = live ? int(i / cp8) : 0;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const __half* base = x + size_t(img) * hw * cp8 * 8 + g * 8;
+        if (live)
+            for (int pix = sub; pix < hw; pix += 8) {
+                float f[8];
+                unpack(ld8(base + size_t(pix) * cp8 * 8), f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+            }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 1);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 2);
+            acc[j] += __shfl_xor_sync(0xffffffffu, acc[j], 4);
+        }
+        if (live && sub == 0) {
+            const float inv = 1.f / float(hw);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] *= inv;
+            st8(y + i * 8, pack(acc));
+        }
+    }
+}
+
 cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cudaStream_t s) {
     if (hw <= 64 || size_t(n) * (cp / 8) >= size_t(kSMs) * 64) {
-        global_avgpool_small_kernel<<<grid_for(size_t(n) * (cp / 8), 64), 64, 0, s>>>(x, y, n, hw, cp / 8);
+        const size_t teams = size_t(n) * (cp / 8);
+        global_avgpool_team_kernel<<<grid_for(teams * 8), kThreads, 0, s>>>(x, y, n, hw, cp / 8);
     } else {
         dim3 grid(cp / 8, n);
         global_avgpool_kernel<<<grid, kThreads, 0, s>>>(x, y, hw, cp / 8);

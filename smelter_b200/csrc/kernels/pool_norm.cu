@@ -60,16 +60,36 @@ __device__ __forceinline__ float act_op(float v, int act, float lo, float hi) {
 //      (count_include_pad=1, the MPS/PyTorch default the reference relies on, Converters.swift:609-616).
 __global__ void __launch_bounds__(kThreads) pool2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
                                                          int p, int q, int kh, int kw, int sh, int sw, int ph, int pw, int is_max) {
-    const size_t total = size_t(n) * p * q * cp8;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-        const int g = int(i % cp8);
-        size_t pix = i / cp8;
-        const int oq = int(pix % q);
-        const int op = int((pix / q) % p);
-        const int img = int(pix / (size_t(q) * p));
+    // grid.y walks output rows (image, op); threads walk (oq, channel group) of that row
+    const int op = blockIdx.y % p;
+    const int img = blockIdx.y / p;
+    const int row_items = q * cp8;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < row_items; it += gridDim.x * blockDim.x) {
+        const int g = it % cp8;
+        const int oq = it / cp8;
+        const size_t i = (size_t(blockIdx.y) * q + oq) * cp8 + g;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = is_max ? -FLT_MAX : 0.f;
+        if (kh == 3 && kw == 3) {
+            // the common 3x3 window: issue all nine 128-bit loads before the first use (clamped address + validity flag)
+            Half8 v[9];
+            bool ok[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int iy = op * sh - ph + t / 3, ix = oq * sw - pw + t % 3;
+                ok[t] = iy >= 0 && iy < h && ix >= 0 && ix < w;
+                v[t] = ld8(x + (((size_t(img) * h + (ok[t] ? iy : 0)) * w + (ok[t] ? ix : 0)) * cp8 + g) * 8);
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                if (!ok[t]) continue;
+                float f[8];
+                unpack(v[t], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc[j] = is_max ? fmaxf(acc[j], f[j]) : acc[j] + f[j];
+            }
+        } else
         for (int r = 0; r < kh; ++r) {
             const int iy = op * sh - ph + r;
             if (iy < 0 || iy >= h) continue;
@@ -143,7 +163,62 @@ __global__ void __launch_bounds__(kThreads) global_avgpool_small_kernel(const __
     }
 }
 
-// ---- softmax over the channel axis of each pixel: one warp per row.
+// ---- softmax over the channel axis of each pixel: one warp per row; rows of up to 1024 channels are read ONCE as
+//      128-bit vectors (up to four per lane, kept in registers across the max / sum / normalise passes).
+__global__ void __launch_bounds__(kThreads) softmax_vec_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int c, int cp,
+                                                              int log_softmax) {
+    const int lane = threadIdx.x & 31;
+    const size_t warp = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
+    const size_t nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
+    const int nvec = cp / 8;
+    for (size_t row = warp; row < rows; row += nwarps) {
+        const __half* xr = x + row * cp;
+        __half* yr = y + row * cp;
+        float f[4][8];
+        float mx = -FLT_MAX;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = lane + 32 * u;
+            if (v < nvec) {
+                unpack(ld8(xr + v * 8), f[u]);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (v * 8 + j >= c) f[u][j] = -FLT_MAX;   // padded lanes do not take part
+                    mx = fmaxf(mx, f[u][j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+        float sum = 0.f;
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lane + 32 * u < nvec) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float e = f[u][j] > -FLT_MAX ? __expf(f[u][j] - mx) : 0.f;
+                    sum += e;
+                    if (!log_softmax) f[u][j] = e;
+                }
+            }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float inv = 1.f / sum;
+        const float lse = mx + __logf(sum);
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int v = lane + 32 * u;
+            if (v < nvec) {
+                float o8[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o8[j] = v * 8 + j < c ? (log_softmax ? f[u][j] - lse : f[u][j] * inv) : 0.f;
+                st8(yr + v * 8, pack(o8));
+            }
+        }
+    }
+}
+
+// ---- general fallback (rows longer than 1024 channels): one warp per row, three passes.
 __global__ void __launch_bounds__(kThreads) softmax_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int c, int cp,
                                                           int log_softmax) {
     const int lane = threadIdx.x & 31;
@@ -251,13 +326,14 @@ __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __res
                                                             const float* __restrict__ bias, __half* __restrict__ y, int n, int h, int w,
                                                             int cp8, int p, int q, int kh, int kw, int sh, int sw, int dh, int dw, int pt,
                                                             int pl, int act, float lo, float hi) {
-    const size_t total = size_t(n) * p * q * cp8;
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
-        const int g = int(i % cp8);
-        size_t pix = i / cp8;
-        const int oq = int(pix % q);
-        const int op = int((pix / q) % p);
-        const int img = int(pix / (size_t(q) * p));
+    // grid.y walks output rows (image, op); threads walk (oq, channel group) of that row
+    const int op = blockIdx.y % p;
+    const int img = blockIdx.y / p;
+    const int row_items = q * cp8;
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < row_items; it += gridDim.x * blockDim.x) {
+        const int g = it % cp8;
+        const int oq = it / cp8;
+        const size_t i = (size_t(blockIdx.y) * q + oq) * cp8 + g;
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + g * 8 + j);
@@ -284,7 +360,10 @@ __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __res
 
 cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int p, int q, int kh, int kw, int sh, int sw, int ph, int pw,
                    int is_max, cudaStream_t s) {
-    pool2d_kernel<<<grid_for(size_t(n) * p * q * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
+    if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
+    const int row_items = q * (cp / 8);
+    dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
+    pool2d_kernel<<<grid, kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
     return cudaGetLastError();
 }
 
@@ -301,11 +380,19 @@ __global__ void __launch_bounds__(kThreads) global_avgpool_team_kernel(const __h
         float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         const __half* base = x + size_t(img) * hw * cp8 * 8 + g * 8;
         if (live)
-            for (int pix = sub; pix < hw; pix += 8) {
-                float f[8];
-                unpack(ld8(base + size_t(pix) * cp8 * 8), f);
+            for (int pix = sub; pix < hw; pix += 32) {  // four independent loads in flight per lane
+                Half8 v[4];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                for (int u = 0; u < 4; ++u)
+                    if (pix + 8 * u < hw) v[u] = ld8(base + size_t(pix + 8 * u) * cp8 * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (pix + 8 * u < hw) {
+                        float f[8];
+                        unpack(v[u], f);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) acc[j] += f[j];
+                    }
             }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
@@ -334,6 +421,8 @@ cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cu
 }
 
 cudaError_t softmax_rows(const __half* x, __half* y, size_t rows, int c, int cp, int log_softmax, cudaStream_t s) {
+    if (cp <= 1024) softmax_vec_kernel<<<grid_for(rows * 32), kThreads, 0, s>>>(x, y, rows, c, cp, log_softmax);
+    else
     softmax_kernel<<<grid_for(rows * 32), kThreads, 0, s>>>(x, y, rows, c, cp, log_softmax);
     return cudaGetLastError();
 }
@@ -368,8 +457,10 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
 
 cudaError_t depthwise_conv(const __half* x, const __half* w, const float* bias, __half* y, int n, int h, int wd, int cp, int p, int q, int kh,
                            int kw, int sh, int sw, int dh, int dw, int pt, int pl, int act, float lo, float hi, cudaStream_t s) {
-    depthwise_kernel<<<grid_for(size_t(n) * p * q * (cp / 8)), kThreads, 0, s>>>(x, w, bias, y, n, h, wd, cp / 8, p, q, kh, kw, sh, sw, dh, dw,
-                                                                                pt, pl, act, lo, hi);
+    if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
+    const int row_items = q * (cp / 8);
+    dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
+    depthwise_kernel<<<grid, kThreads, 0, s>>>(x, w, bias, y, n, h, wd, cp / 8, p, q, kh, kw, sh, sw, dh, dw, pt, pl, act, lo, hi);
     return cudaGetLastError();
 }
 

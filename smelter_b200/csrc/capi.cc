@@ -654,9 +654,9 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
     const int hp = materialise ? p->h + p->pad_t + p->pad_b : p->h;
     const int wp = materialise ? p->w + p->pad_l + p->pad_r : p->w;
     struct Bufs {
-        void *w = nullptr, *b = nullptr, *xi = nullptr, *yo = nullptr, *res = nullptr;
+        void *w = nullptr, *b = nullptr, *xi = nullptr, *yo = nullptr, *res = nullptr, *ws = nullptr, *cnt = nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        ~Bufs() { cudaFree(w); cudaFree(b); cudaFree(xi); cudaFree(yo); cudaFree(res); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+        ~Bufs() { cudaFree(w); cudaFree(b); cudaFree(xi); cudaFree(yo); cudaFree(res); cudaFree(ws); cudaFree(cnt); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
     } B;
     SM_CUDA(cudaMalloc(&B.w, packed.size() * 2));
     SM_CUDA(cudaMalloc(&B.b, bias_pad.size() * 4));
@@ -691,12 +691,22 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
         q.x = static_cast<const __half*>(B.xi); q.w_packed = static_cast<const __half*>(B.w); q.bias = static_cast<const float*>(B.b);
         q.residual = static_cast<const __half*>(B.res); q.y = static_cast<__half*>(B.yo);
         q.act = p->act; q.clip_lo = p->clip_lo; q.clip_hi = p->clip_hi;
+        const k::ConvTcPlanInfo info = k::conv_tc_plan(q, ctx->c.num_sms);
+        if (info.splits > 1) {
+            SM_CUDA(cudaMalloc(&B.ws, info.ws_bytes));
+            SM_CUDA(cudaMalloc(&B.cnt, info.counter_bytes));
+            SM_CUDA(cudaMemsetAsync(B.cnt, 0, info.counter_bytes, s));
+            q.split_ws = static_cast<float*>(B.ws);
+            q.split_counters = static_cast<unsigned int*>(B.cnt);
+        }
         k::ConvTcLaunch L;
         std::string cerr;
         if (!k::conv_tc_prepare(&L, q, ctx->c.num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, cerr);
         SM_CUDA(cudaEventRecord(B.e0, s));
         for (int it = 0; it < iters; ++it) SM_CUDA(k::conv_tc_launch(L, s));
         SM_CUDA(cudaEventRecord(B.e1, s));
+        SM_CUDA(cudaStreamSynchronize(s));
+        k::conv_tc_dump_timeline(L);
     }
     SM_CUDA(k::nhwc_to_nchw(static_cast<const __half*>(B.yo), static_cast<__half*>(y), p->n, p->c_out, P, Q, ocp, long(p->c_out) * P * Q, s));
     SM_CUDA(cudaStreamSynchronize(s));

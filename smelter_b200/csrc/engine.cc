@@ -111,9 +111,11 @@ struct Plan {
     std::vector<ImageShape> src_shapes;
     Tensor result;
     cudaGraphExec_t exec = nullptr;
+    void* counters = nullptr;  // split-K arrival counters of every conv in the plan (zero between launches)
     ~Plan() {
         if (exec) cudaGraphExecDestroy(exec);
         if (arena) cudaFree(arena);
+        if (counters) cudaFree(counters);
     }
 };
 
@@ -430,12 +432,35 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     const int out_root = root_of(output_value_);
     last_use[size_t(out_root)] = int(filters_.size()) + 1;
 
+    // shape part of the tensor-core conv problem of filter f (pointers are bound later)
+    auto conv_problem = [&](const Filter& f, const std::vector<const Filter*>& stem_map) {
+        const ImageShape is = values_[size_t(f.in[0])].shape;
+        const ImageShape osz = values_[size_t(f.out)].shape;
+        k::ConvTcProblem q{};
+        q.mode = f.conv_mode;
+        q.n = N; q.h = is.h; q.w = is.w;
+        q.c_in = f.c_in_g; q.c_in_pitch = round_up(is.c, 8);
+        if (f.is_gemm) { q.h = q.w = 1; q.c_in_pitch = round_up(is.c * is.h * is.w, 8); }
+        q.c_out = f.c_out; q.c_out_pitch = round_up(osz.c, 8);
+        q.k_h = f.k_h; q.k_w = f.k_w; q.stride_h = f.stride_h; q.stride_w = f.stride_w; q.dil_h = f.dil_h; q.dil_w = f.dil_w;
+        q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
+        q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
+        if (f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3])) {
+            q.h = is.h + f.pads[0] + f.pads[2];  // packed-row convolutions read a materialised zero-padded image
+            q.w = is.w + f.pads[1] + f.pads[3];
+            q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        }
+        (void)stem_map;
+        return q;
+    };
     // ---- offsets (two passes: first compute offsets, then allocate, then bind pointers) ----
     ArenaAlloc arena;
     std::vector<size_t> off(values_.size(), size_t(-1));
     struct Scratch { size_t off, bytes; };
     std::vector<Scratch> scratch(filters_.size(), Scratch{size_t(-1), 0});   // per-filter temporary (padded input copy, IN partials, NCHW staging)
-    std::vector<Scratch> scratch2(filters_.size(), Scratch{size_t(-1), 0});
+    std::vector<Scratch> scratch2(filters_.size(), Scratch{size_t(-1), 0});   // split-K fp32 workspace
+    std::vector<size_t> counter_off(filters_.size(), size_t(-1));
+    size_t counter_total = 0;
 
     // A graph input whose only reader is a packed-row (stem) convolution is converted straight into the zero-padded
     // NHWC image that kernel wants: the boundary conversion materialises the padding, no separate pad pass.
@@ -470,6 +495,15 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             scratch[fi].bytes = size_t(N) * (s.h + f.pads[0] + f.pads[2]) * (s.w + f.pads[1] + f.pads[3]) * 8 * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
+        if (f.kind == FilterKind::Conv && f.conv_mode != 4) {
+            const k::ConvTcPlanInfo info = k::conv_tc_plan(conv_problem(f, stem_of), num_sms);
+            if (info.splits > 1) {
+                scratch2[fi].bytes = info.ws_bytes;
+                scratch2[fi].off = arena.alloc(scratch2[fi].bytes);
+                counter_off[fi] = counter_total;
+                counter_total += (info.counter_bytes + 255) & ~size_t(255);
+            }
+        }
         if (f.kind == FilterKind::InstanceNorm) {
             const ImageShape& s = values_[size_t(f.in[0])].shape;
             scratch[fi].bytes = size_t(N) * k::instance_norm_splits(s.h * s.w, round_up(s.c, 8)) * round_up(s.c, 8) * 2 * sizeof(float);
@@ -486,6 +520,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         }
         off[size_t(f.out)] = arena.alloc(bytes_of(f.out));
         if (scratch[fi].off != size_t(-1)) arena.release(scratch[fi].off, scratch[fi].bytes);
+        if (scratch2[fi].off != size_t(-1)) arena.release(scratch2[fi].off, scratch2[fi].bytes);
         // release inputs whose last use is this filter
         std::vector<int> roots;
         for (int i : f.in) roots.push_back(root_of(i));
@@ -504,6 +539,10 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
 
     plan->arena_bytes = std::max<size_t>(arena.peak, 1024);
     SM_CUDA(cudaMalloc(&plan->arena, plan->arena_bytes));
+    if (counter_total) {
+        SM_CUDA(cudaMalloc(&plan->counters, counter_total));
+        SM_CUDA(cudaMemset(plan->counters, 0, counter_total));
+    }
     char* abase = static_cast<char*>(plan->arena);
     auto ptr_of = [&](int v) { return reinterpret_cast<__half*>(abase + off[size_t(root_of(v))]); };
 
@@ -559,20 +598,14 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                     }, flops, io_bytes);
                     break;
                 }
-                k::ConvTcProblem q{};
-                q.mode = f.conv_mode;
-                q.n = N; q.h = is.h; q.w = is.w;
-                q.c_in = f.c_in_g; q.c_in_pitch = icp;
-                if (f.is_gemm) { q.h = q.w = 1; q.c_in_pitch = round_up(is.c * is.h * is.w, 8); }
-                q.c_out = f.c_out; q.c_out_pitch = ocp;
-                q.k_h = f.k_h; q.k_w = f.k_w; q.stride_h = f.stride_h; q.stride_w = f.stride_w; q.dil_h = f.dil_h; q.dil_w = f.dil_w;
-                q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
+                k::ConvTcProblem q = conv_problem(f, stem_of);
                 q.x = x; q.w_packed = w; q.bias = bias; q.residual = res; q.y = y;
-                q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
+                if (scratch2[fi].off != size_t(-1)) {
+                    q.split_ws = reinterpret_cast<float*>(abase + scratch2[fi].off);
+                    q.split_counters = reinterpret_cast<unsigned int*>(static_cast<char*>(plan->counters) + counter_off[fi]);
+                }
                 if (f.conv_mode == k::CONV_MODE_PACKED_ROW && stem_of[size_t(root_of(f.in[0]))] == &f) {
-                    q.h = is.h + f.pads[0] + f.pads[2];  // the boundary conversion already wrote the padded image
-                    q.w = is.w + f.pads[1] + f.pads[3];
-                    q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+                    // the boundary conversion already wrote the padded image into this conv's input buffer
                 } else if (f.conv_mode == k::CONV_MODE_PACKED_ROW && scratch[fi].off != size_t(-1)) {
                     // materialise the zero padding so one K block can span a whole filter row
                     __half* padded = reinterpret_cast<__half*>(abase + scratch[fi].off);
@@ -581,15 +614,13 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                         return k::pad2d(x, padded, N, is.h, is.w, 8, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], k::PAD_CONSTANT, 0.f, st);
                     }, 0, double(scratch[fi].bytes) + double(N) * is.h * is.w * 16);
                     q.x = padded;
-                    q.h = is.h + f.pads[0] + f.pads[2];
-                    q.w = is.w + f.pads[1] + f.pads[3];
-                    q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
                 }
                 auto L = std::make_shared<k::ConvTcLaunch>();
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : "rows";
-                add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + "]" + suffix + " " + name,
+                add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
+                             "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,
                          io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0));
                 plan->steps.back().tensor = true;

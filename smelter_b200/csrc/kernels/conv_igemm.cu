@@ -69,8 +69,62 @@ struct Cfg {
     static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + 1024 + 512;
 };
 
+__device__ __forceinline__ void stamp(const ConvKernelParams& p, int slot) {
+    if (p.timeline && blockIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[slot] = t;
+    }
+}
+
 // Sigmoid is rare on this path (no BASELINE model fuses it): keep it out of line so the hot epilogue stays small.
 __device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
+
+// One [32 row x kCols column] chunk of the epilogue for one warp: v = fp32 accumulators of this lane's row; +bias (fp32, from
+// the warp's smem bias slot), +residual (fp32, read from the staging row where TMA put it), activation, fp16, written back
+// to the same staging row (128B-swizzled: 16-byte piece g of row r sits at piece g ^ (r & 7)).
+// Software-pipelined over the 8-column groups: the bias (and residual) of group g+1 are fetched from shared memory while
+// group g is computed, so no LDS latency sits on the dependency chain.
+template <int kCols, bool HAS_RES>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot, bool is_sigmoid,
+                                              __half2 lo2, __half2 hi2) {
+    constexpr int kGroups = kCols / 8;
+    uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
+    uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_RES) nrv = ld_shared_v4(rowbuf + (sw << 4));
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const uint4 bq0 = nb0, bq1 = nb1, rv = nrv;
+        if (g + 1 < kGroups) {
+            nb0 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u);
+            nb1 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u + 16u);
+            if (HAS_RES) nrv = ld_shared_v4(rowbuf + ((uint32_t(g + 1) ^ sw) << 4));
+        }
+        float f[8];
+        f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(bq0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(bq0.y);
+        f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(bq0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(bq0.w);
+        f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(bq1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(bq1.y);
+        f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(bq1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(bq1.w);
+        if (HAS_RES) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 r2 = __half22float2(rh[i]);
+                f[2 * i] += r2.x;
+                f[2 * i + 1] += r2.y;
+            }
+        }
+        if (is_sigmoid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
+        }
+        uint4 ov;
+        __half2* oh = reinterpret_cast<__half2*>(&ov);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
+        st_shared_v4(rowbuf + ((uint32_t(g) ^ sw) << 4), ov);
+    }
+}
 
 template <int BLOCK_N, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -88,13 +142,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
     auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };  // w in [0, 8)
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 20);
+    const uint32_t flag_slot = bar_base + 8u * (2 * C::kStages + 21);  // two 8-byte slots: "this group reduces the tile" (split-K)
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
-    const int num_kb = p.num_taps * p.kblocks_per_tap;
+    // A work item is (output tile, k-split): with p.splits > 1 several CTAs accumulate disjoint k-block ranges of the same
+    // tile and the last one to finish reduces the fp32 partials (see the split-K epilogue).  "tile" below means work item.
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles * p.splits;
+    const int total_kb = p.num_taps * p.kblocks_per_tap;
     const int my_tiles = int(blockIdx.x) < num_tiles ? (num_tiles - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+    if (threadIdx.x == 0) stamp(p, 0);  // kernel entry
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a);
@@ -122,12 +180,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
+    if (threadIdx.x == 0) stamp(p, 1);  // prologue done
     // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may overlap
     // the previous kernel's tail; from here on we read its output (and overwrite buffers it may still be reading).
     if (p.use_pdl) {
         grid_dep_launch_dependents();
         grid_dep_wait();
     }
+    if (threadIdx.x == 0) stamp(p, 2);  // dependencies resolved
 
     if (warp < kNumProducers || warp >= kBProducerWarp0) {
         // ================= TMA producers =================
@@ -136,12 +196,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const bool is_a = warp < kNumProducers;
         const int me = is_a ? warp : warp - kBProducerWarp0;
         const int n_prod = is_a ? C::kProducers : C::kBProducers;
-        const bool leader = elect_one();  // whole warp runs the loop (uniform waits); the elected lane issues the TMA
-        if (me < n_prod && !(p.debug_flags & 32)) {
+        const bool leader = elect_one();  // one lane per producer warp runs the loop
+        if (leader && me < n_prod && !(p.debug_flags & 32)) {
             int stage = 0;
             uint32_t phase = 0;
             uint32_t turn = 0;  // k-block counter modulo the number of producers of this operand
-            for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
+                const int tile = item / p.splits;
+                const int split = item - tile * p.splits;
+                const int kb0 = split * p.kb_per_split;
+                const int num_kb = min(p.kb_per_split, total_kb - kb0);
                 const int m_tile = tile / p.num_n_tiles;
                 const int n_tile = tile - m_tile * p.num_n_tiles;
                 const int m0 = m_tile * kBlockM;
@@ -155,13 +219,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     base_h = p.corner_h + op * p.stride_h;
                     base_w = p.corner_w + oq * p.stride_w;
                 }
-                int tap = 0, cblk = 0;
+                int tap = kb0 / p.kblocks_per_tap, cblk = kb0 - tap * p.kblocks_per_tap;
                 for (int kb = 0; kb < num_kb; ++kb) {
                     if (turn == uint32_t(me)) {
                         mbar_wait(empty_bar(stage), phase ^ 1);
                         const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                        if (!leader) {
-                        } else if (p.debug_flags & 16) {
+                        if (p.debug_flags & 16) {
                             mbar_arrive(full_bar(stage));
                         } else if (is_a) {
                             mbar_expect_tx(full_bar(stage), kABytes);
@@ -186,8 +249,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
-        // The whole warp runs the loop (barrier waits are warp-uniform); one elected lane issues the tcgen05 instructions.
-        // This single instruction stream feeds the tensor core, so it is kept minimal: the shared-memory descriptors are
+        // One elected lane issues the tcgen05 instructions.  This single instruction stream feeds the tensor core, so it is
+        // kept minimal: the shared-memory descriptors are
         // (constant high word, low word = stage base >> 4) and the k-advance is an immediate add.
         constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
         constexpr uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);  // SBO, version, SWIZZLE_128B
@@ -195,19 +258,22 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | desc_lbo;
         constexpr uint32_t kStage16 = C::kStageBytes >> 4;
         constexpr uint32_t kB16 = kABytes >> 4;
-        const bool leader = elect_one();
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int t = 0; t < my_tiles; ++t) {
-            const int acc = t & 1;                       // accumulator buffer == epilogue group
-            mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
-            uint32_t accumulate = 0;
-            for (int kb = 0; kb < num_kb; ++kb) {
-                if (!(p.debug_flags & 32)) mbar_wait(full_bar(stage), phase);
+        // Only the elected lane runs the loop: a barrier wait executed by all 32 lanes is 32 separate mbarrier operations.
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int t = 0; t < my_tiles; ++t) {
+                const int acc = t & 1;                       // accumulator buffer == epilogue group
+                const int split = (int(blockIdx.x) + t * int(gridDim.x)) % p.splits;
+                const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
+                mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
                 tc_fence_after();
-                if (leader) {
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+                uint32_t accumulate = 0;
+                for (int kb = 0; kb < num_kb; ++kb) {
+                    if (!(p.debug_flags & 32)) mbar_wait(full_bar(stage), phase);
+                    if (t == 0 && kb == 0) stamp(p, 3);  // first operands landed
+                    tc_fence_after();
                     const uint64_t a_desc = desc_hi | uint64_t(a_lo0 + uint32_t(stage) * kStage16);
                     const uint64_t b_desc = a_desc + kB16;
                     if (!(p.debug_flags & 64)) {
@@ -217,12 +283,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         umma_f16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
                     }
                     if (!(p.debug_flags & 32)) umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
+                    accumulate = 1u;
+                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
                 }
-                accumulate = 1u;
-                if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
+                if (t == 0) stamp(p, 4);  // all MMAs of the first tile issued
             }
-            if (leader) umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
-            __syncwarp();
         }
     } else {
         // ================= epilogue (warps 4..11) =================
@@ -244,6 +310,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const bool is_sigmoid = p.act == ACT_SIGMOID;
         const __half2 lo2 = __float2half2_rn(p.act == ACT_RELU ? 0.f : (p.act == ACT_CLIP ? p.clip_lo : -INFINITY));
         const __half2 hi2 = __float2half2_rn(p.act == ACT_CLIP ? p.clip_hi : INFINITY);
+        if (p.splits == 1) {
         const int group_tiles = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
         const int n_items = group_tiles * C::kChunks;  // (tile, chunk) stream of this warp
         auto item_coords = [&](int item, int* m_row0, int* col0) {
@@ -276,6 +343,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         int item = 0;
         for (int gt = 0; gt < group_tiles; ++gt) {
             mbar_wait(tmem_full_bar(group), acc_phase);
+            if (gt == 0 && ewarp == 0 && lane == 0) stamp(p, 5);  // first accumulator ready
             acc_phase ^= 1u;
             tc_fence_after();
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(group * BLOCK_N);
@@ -317,45 +385,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     res_phase ^= 1u << b;
                 }
                 __syncwarp();  // lane 0's wait_group.read above covers the whole warp's upcoming smem writes
-                // software-pipelined over the eight 8-column groups: the bias (and residual) of group g+1 are fetched
-                // from shared memory while group g is computed, so no LDS latency sits on the dependency chain
-                constexpr int kGroups = C::kChunkCols / 8;
-                const uint32_t rowbuf = buf + row_off;
-                uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
-                uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
-                if (HAS_RES) nrv = ld_shared_v4(rowbuf + (sw << 4));
-#pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    const uint4 bq0 = nb0, bq1 = nb1, rv = nrv;
-                    if (g + 1 < kGroups) {
-                        nb0 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u);
-                        nb1 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u + 16u);
-                        if (HAS_RES) nrv = ld_shared_v4(rowbuf + ((uint32_t(g + 1) ^ sw) << 4));
-                    }
-                    float f[8];
-                    f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(bq0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(bq0.y);
-                    f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(bq0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(bq0.w);
-                    f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(bq1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(bq1.y);
-                    f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(bq1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(bq1.w);
-                    if (HAS_RES) {
-                        const __half2* rh = reinterpret_cast<const __half2*>(&rv);
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const float2 r2 = __half22float2(rh[i]);
-                            f[2 * i] += r2.x;
-                            f[2 * i + 1] += r2.y;
-                        }
-                    }
-                    if (is_sigmoid) {
-#pragma unroll
-                        for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
-                    }
-                    uint4 ov;
-                    __half2* oh = reinterpret_cast<__half2*>(&ov);
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
-                    st_shared_v4(rowbuf + ((uint32_t(g) ^ sw) << 4), ov);
-                }
+                epilogue_math<C::kChunkCols, HAS_RES>(v, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
                 fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
                 __syncwarp();
                 if (lane == 0) {
@@ -364,7 +394,112 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
             }
         }
+        } else {
+            // ---------------- split-K epilogue ----------------
+            // Every CTA that worked on a k-range of the tile dumps its raw fp32 accumulator to its slab of the workspace,
+            // then bumps the tile's counter; the CTA that arrives last sums all slabs and runs the normal epilogue
+            // (bias, residual, activation, TMA store) and resets the counter for the next launch.
+            const int group_items = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
+            volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_raw + (flag_slot + 8u * uint32_t(group) - smem_u32(smem_raw)));
+            const int row = ew * 32 + lane;
+            uint32_t acc_phase = 0, res_phase = 0;
+            int n_stores = 0;  // TMA stores this warp has committed (selects the staging buffer)
+            for (int gi = 0; gi < group_items; ++gi) {
+                const int item = int(blockIdx.x) + (2 * gi + group) * int(gridDim.x);
+                const int tile = item / p.splits;
+                const int m_tile = tile / p.num_n_tiles;
+                const int n_tile = tile - m_tile * p.num_n_tiles;
+                mbar_wait(tmem_full_bar(group), acc_phase);
+                acc_phase ^= 1u;
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(group * BLOCK_N);
+                // workspace layout per work item: [16-byte piece = 4 columns][row], so the 32 lanes of a warp (32 consecutive
+                // rows) write / read 512 contiguous bytes per instruction although every lane owns a whole row
+                uint4* slab = reinterpret_cast<uint4*>(p.ws) + size_t(item) * (kBlockM * BLOCK_N / 4) + row;
+#pragma unroll 1
+                for (int c = 0; c < C::kChunks; ++c) {
+                    uint32_t v[C::kChunkCols];
+                    tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
+                    if (C::kChunkCols > 32) tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + (C::kChunkCols > 32 ? 32 : 0));
+                    tmem_ld_wait();
+#pragma unroll
+                    for (int j = 0; j < C::kChunkCols / 4; ++j)
+                        slab[size_t(c * (kChunkN / 4) + j) * kBlockM] = make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+                }
+                tc_fence_before();
+                mbar_arrive(tmem_empty_bar(group));
+                __threadfence();  // partials visible device-wide before the counter moves
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+                if (ew == 0 && lane == 0) {
+                    const unsigned old = atomicAdd(p.counters + tile, 1u);
+                    const bool last = old == unsigned(p.splits - 1);
+                    if (last) p.counters[tile] = 0u;
+                    *flag = last ? 1u : 0u;
+                }
+                asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+                if (*flag == 0u) continue;
+                __threadfence();
+                const int m_row0 = m_tile * kBlockM + ew * 32;
+                int col0 = n_tile * BLOCK_N;
+                float2 bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
+                auto load_res = [&](int cc, int b) {  // lane 0 only
+                    fence_proxy_async_smem();
+                    mbar_expect_tx(res_bar(ewarp, b), kEpiBufBytes);
+                    tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, n_tile * BLOCK_N + cc * kChunkN, m_row0);
+                };
+                if (HAS_RES && lane == 0) {
+                    tma_store_wait_read<0>();
+                    load_res(0, n_stores & 1);
+                }
+#pragma unroll 1
+                for (int c = 0; c < C::kChunks; ++c, ++n_stores, col0 += kChunkN) {
+                    const int b = n_stores & 1;
+                    const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
+                    if (lane == 0) {
+                        if (HAS_RES) {
+                            if (c + 1 < C::kChunks) {
+                                tma_store_wait_read<0>();
+                                load_res(c + 1, b ^ 1);
+                            }
+                        } else {
+                            tma_store_wait_read<1>();
+                        }
+                    }
+                    asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
+                    if (c + 1 < C::kChunks) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + kChunkN) + lane);
+                    float acc[C::kChunkCols];
+#pragma unroll
+                    for (int i = 0; i < C::kChunkCols; ++i) acc[i] = 0.f;
+                    for (int sp = 0; sp < p.splits; ++sp) {
+                        const float4* q = reinterpret_cast<const float4*>(p.ws) + (size_t(tile) * p.splits + sp) * (kBlockM * BLOCK_N / 4) +
+                                          size_t(c * (kChunkN / 4)) * kBlockM + row;
+#pragma unroll
+                        for (int j = 0; j < C::kChunkCols / 4; ++j) {
+                            const float4 t4 = __ldcg(q + size_t(j) * kBlockM);
+                            acc[4 * j] += t4.x; acc[4 * j + 1] += t4.y; acc[4 * j + 2] += t4.z; acc[4 * j + 3] += t4.w;
+                        }
+                    }
+                    uint32_t v[C::kChunkCols];
+#pragma unroll
+                    for (int i = 0; i < C::kChunkCols; ++i) v[i] = __float_as_uint(acc[i]);
+                    if (HAS_RES) {
+                        mbar_wait(res_bar(ewarp, b), (res_phase >> b) & 1u);
+                        res_phase ^= 1u << b;
+                    }
+                    __syncwarp();
+                    epilogue_math<C::kChunkCols, HAS_RES>(v, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tm_out, buf, col0, m_row0);
+                        tma_store_commit();
+                    }
+                }
+            }
+        }
+        if (ewarp == 0 && lane == 0) stamp(p, 6);  // last store issued
         if (lane == 0) tma_store_wait_read<0>();  // smem must stay valid until read; global visibility comes with grid completion
+        if (ewarp == 0 && lane == 0) stamp(p, 7);  // stores read
     }
 
     tc_fence_before();
@@ -372,6 +507,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, C::kTmemCols);
+        if (lane == 0) stamp(p, 8);  // exit
     }
 }
 
@@ -462,6 +598,63 @@ int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms) {
     return best;
 }
 
+ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
+    const int R = q.k_h, S = q.k_w;
+    const int P = (q.h + q.pad_t + q.pad_b - q.dil_h * (R - 1) - 1) / q.stride_h + 1;
+    const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (S - 1) - 1) / q.stride_w + 1;
+    const long M = long(q.n) * std::max(P, 0) * std::max(Q, 0);
+    const int m_tiles = int((M + kBlockM - 1) / kBlockM);
+    const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * 8 : q.c_in_pitch;
+    const int taps = q.mode == CONV_MODE_TILED ? 1 : (q.mode == CONV_MODE_PACKED_ROW ? R : R * S);
+    const int num_kb = taps * ((kc + kBlockK - 1) / kBlockK);
+    ConvTcPlanInfo best{};
+    best.block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, m_tiles, num_sms);
+    best.splits = 1;
+    if (const char* force = getenv("SMELTER_FORCE_BN")) {  // tuning experiments only
+        const int v = atoi(force);
+        if (v == 32 || v == 64 || v == 128 || v == 256) best.block_n = v;
+    }
+    const bool forced = q.block_n != 0 || q.splits == 1 || getenv("SMELTER_FORCE_BN") || getenv("SMELTER_NO_SPLITK");
+    if (q.splits > 1) {
+        best.splits = q.splits;
+    } else if (!forced && q.c_out > 32) {
+        // Single-wave layers (fewer tiles than SMs) are bound by the serial k-loop of one CTA: wider tiles make each k-block
+        // do more work per MMA-issue slot, and splitting k across otherwise idle SMs shortens the chain.  Costs in us from
+        // measurements on B200: k-block of N=64/128/256: 0.22/0.25/0.33; epilogue chunk 0.35; the split-K reduction costs a
+        // device-wide fence + counter (~2.5) and one L2 round trip (~0.8) per split per 64-column chunk in the reducing CTA
+        // (measured: splitting the 36..72 k-block layers of ResNet-50 at batch 32 lost time, so the model must be this honest).
+        auto cost = [&](int bn, int splits) {
+            const double t_kb = bn <= 64 ? 0.22 : (bn <= 128 ? 0.25 : 0.33);
+            const int kbs = (num_kb + splits - 1) / splits;
+            return kbs * t_kb + (bn / 64) * 0.35 + (splits > 1 ? 2.5 + (bn / 64) * splits * 0.8 : 0.0);
+        };
+        const int base_tiles = m_tiles * ((q.c_out + best.block_n - 1) / best.block_n);
+        if (base_tiles <= num_sms) {
+            double best_cost = cost(best.block_n, 1);
+            const int cands[3] = {64, 128, 256};
+            for (int bn : cands) {
+                if (bn / 2 >= q.c_out) continue;  // more than half of the tile would be padding
+                const int tiles = m_tiles * ((q.c_out + bn - 1) / bn);
+                for (int splits = 1; splits <= 8; ++splits) {
+                    if (tiles * splits > num_sms) break;
+                    const int kbs = (num_kb + splits - 1) / splits;
+                    if (splits > 1 && (kbs < 4 || (splits - 1) * kbs >= num_kb)) continue;
+                    const double c = cost(bn, splits);
+                    if (c < best_cost * 0.85) {  // only move for a clear win
+                        best_cost = c / 0.85;
+                        best.block_n = bn;
+                        best.splits = splits;
+                    }
+                }
+            }
+        }
+    }
+    const int tiles = m_tiles * ((q.c_out + best.block_n - 1) / best.block_n);
+    best.ws_bytes = best.splits > 1 ? size_t(tiles) * best.splits * kBlockM * best.block_n * sizeof(float) : 0;
+    best.counter_bytes = best.splits > 1 ? size_t(tiles) * sizeof(unsigned int) : 0;
+    return best;
+}
+
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err) {
     if (!load_driver_entry_points(err)) return false;
     memset(L, 0, sizeof(*L));
@@ -498,15 +691,22 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     }
     if (kc % 8) { if (err) *err = "conv: channel pitch must be a multiple of 8"; return false; }
 
-    int block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), num_sms);
-    if (const char* force = getenv("SMELTER_FORCE_BN")) {  // tuning experiments only
-        const int v = atoi(force);
-        if (v == 32 || v == 64 || v == 128 || v == 256) block_n = v;
+    const ConvTcPlanInfo plan = conv_tc_plan(q, num_sms);
+    const int block_n = plan.block_n;
+    if (plan.splits > 1 && (!q.split_ws || !q.split_counters)) {
+        if (err) *err = "conv: split-K chosen but no workspace supplied";
+        return false;
     }
     L->block_n = block_n;
     L->use_pdl = getenv("SMELTER_NO_PDL") ? 0 : 1;
     p.use_pdl = L->use_pdl;
     { const char* dbg = getenv("SMELTER_CONV_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
+    p.timeline = nullptr;
+    if (getenv("SMELTER_CONV_TIMELINE")) {
+        static unsigned long long* buf = nullptr;
+        if (!buf) cudaMalloc(&buf, 64 * sizeof(unsigned long long));
+        p.timeline = buf;
+    }
     {
         cudaError_t e = set_attr(block_n);
         if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
@@ -526,8 +726,13 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     p.corner_w = -q.pad_l;
     p.mode = mode;
     p.bias = q.bias; p.has_residual = q.residual ? 1 : 0;
+    p.splits = plan.splits;
+    p.kb_per_split = (p.num_taps * p.kblocks_per_tap + plan.splits - 1) / plan.splits;
+    p.ws = plan.splits > 1 ? q.split_ws : nullptr;
+    p.counters = plan.splits > 1 ? q.split_counters : nullptr;
     p.act = q.act; p.clip_lo = q.clip_lo; p.clip_hi = q.clip_hi;
-    L->grid = int(std::min<long>(long(p.num_m_tiles) * p.num_n_tiles, num_sms));
+    L->grid = int(std::min<long>(long(p.num_m_tiles) * p.num_n_tiles * plan.splits, num_sms));
+    L->splits = plan.splits;
     L->flops = 2.0 * double(M) * q.c_out * double(q.c_in) * R * S;
 
     // ---- B: packed weights [Cout][taps][kc] ----
@@ -902,6 +1107,16 @@ int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iter
         return 1;
     }
     return 0;
+}
+
+void conv_tc_dump_timeline(const ConvTcLaunch& L) {
+    if (!L.p.timeline) return;
+    unsigned long long h[16];
+    cudaMemcpy(h, L.p.timeline, sizeof h, cudaMemcpyDeviceToHost);
+    const char* names[9] = {"entry", "prologue_done", "deps_resolved", "first_operands", "mma_issued", "acc_ready", "last_store_issued", "stores_read", "exit"};
+    fprintf(stderr, "timeline(ns since entry):");
+    for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%lld", names[i], (long long)(h[i] - h[0]));
+    fprintf(stderr, "\n");
 }
 
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream) {

@@ -30,6 +30,11 @@ struct ConvKernelParams {
     int has_residual;        // an NHWC tensor with the output's shape (tm_res) is added before the activation
     int act;
     float clip_lo, clip_hi;
+    int splits;              // k-splits per output tile (1 = none); work items = tiles * splits
+    int kb_per_split;        // k-blocks per split (the last split may have fewer, never zero)
+    float* ws;               // split-K workspace: [tiles * splits][128][BLOCK_N] fp32 partial accumulators
+    unsigned int* counters;  // split-K: one arrival counter per tile, zero between launches
+    unsigned long long* timeline;  // perf experiments only (env SMELTER_CONV_TIMELINE): CTA 0 writes %globaltimer stamps here
     int debug_flags;         // perf experiments only (env SMELTER_CONV_DEBUG): 16 = producers skip the TMA loads (results wrong)
     int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
 };
@@ -50,12 +55,23 @@ struct ConvTcProblem {
     int act;
     float clip_lo, clip_hi;
     int block_n;            // 0 = auto
+    int splits;             // 0 = auto (conv_tc_plan), 1 = no split-K
+    float* split_ws;        // workspace of conv_tc_plan().ws_bytes when splits > 1
+    unsigned int* split_counters;  // conv_tc_plan().counter_bytes, zero-initialised once; the kernel leaves them zero
 };
+
+struct ConvTcPlanInfo {
+    int block_n, splits;
+    size_t ws_bytes, counter_bytes;
+};
+// Tile width and k-split choice for a problem (pure function of the shapes).
+ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms);
 
 struct ConvTcLaunch {
     CUtensorMap tm_a, tm_b, tm_out, tm_res;
     ConvKernelParams p;
     int block_n;
+    int splits;
     int grid;
     int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
@@ -64,6 +80,7 @@ struct ConvTcLaunch {
 int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms);
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
+void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only
 // benchmark only: TMA load rate of [128 x 64] fp16 boxes; mode 0 = 2-D tiled over [N*H*W, C], 1 = im2col (3x3, pad 1)
 int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
                std::string* err);

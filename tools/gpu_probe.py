@@ -36,6 +36,11 @@ CONV_CASES = [
     ("rows_3x3_s2_mbv2", (1, 3, 224, 224), 32, 3, 2, 1, 1, 1, 2, True, False, 0),
     ("rows_9x9_tnet", (1, 3, 72, 72), 32, 9, 1, 0, 1, 1, 0, True, False, 0),
     ("rows_3x3_c8", (1, 8, 19, 23), 16, 3, 1, 1, 1, 1, 0, True, False, 0),
+    ("splitk_3x3_512_7_b32", (32, 512, 7, 7), 512, 3, 1, 1, 1, 1, 1, True, True, 0),
+    ("splitk_1x1_2048_512_b32", (32, 2048, 7, 7), 512, 1, 1, 0, 1, 1, 1, True, False, 0),
+    ("splitk_3x3_256_14_b32", (32, 256, 14, 14), 256, 3, 1, 1, 1, 1, 1, True, False, 0),
+    ("splitk_1x1_1024_256_b8", (8, 1024, 14, 14), 256, 1, 1, 0, 1, 1, 0, False, True, 0),
+    ("splitk_gemm_like_b4", (4, 2048, 1, 1), 1000, 1, 1, 0, 1, 1, 0, True, False, 0),
     ("dw_3x3_32_112", (1, 32, 112, 112), 32, 3, 1, 1, 1, 32, 2, True, False, 0),
     ("dw_3x3_s2_144", (2, 144, 56, 56), 144, 3, 2, 1, 1, 144, 2, True, False, 0),
     ("dw_3x3_c20", (1, 20, 9, 9), 20, 3, 1, 1, 1, 20, 0, True, False, 0),

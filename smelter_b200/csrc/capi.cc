@@ -720,7 +720,7 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
 
 int32_t smelter_tma_probe(smelter_context* ctx, int32_t mode, int32_t c, int32_t w, int32_t h, int32_t n, int32_t stages, int32_t iters, int32_t grid,
                           int32_t distinct, float* ms) {
-    ARG(ctx && ms && c >= 64 && c % 8 == 0 && w > 0 && h > 0 && n > 0 && stages >= 1 && stages <= 12 && iters > 0 && grid > 0);
+    ARG(ctx && ms && c >= 8 && c % 8 == 0 && w > 0 && h > 0 && n > 0 && stages >= 1 && stages <= 12 && iters > 0 && grid > 0);
     SM_CUDA(cudaSetDevice(ctx->c.device));
     void* x = nullptr;
     const size_t bytes = size_t(n) * h * w * c * 2;

@@ -792,7 +792,12 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
             upper[1] = q.pad_b - (R - 1) * q.dil_h;
             estr[0] = 1; estr[1] = cuuint32_t(q.stride_w); estr[2] = cuuint32_t(q.stride_h); estr[3] = 1;
         } else {  // packed row: virtual tensor {S*8, Q, H, N}, overlapping W stride
-            dims[0] = cuuint64_t(kc); dims[1] = cuuint64_t(Q); dims[2] = cuuint64_t(q.h); dims[3] = cuuint64_t(q.n);
+            // When the last window of a row can read a full 64-element (128-byte) run without leaving the image row, expose
+            // 64 "channels": the extra elements are the next pixel's data and meet zero weights (the B box zero-fills past
+            // S*8), and the TMA no longer has to zero-fill the tail of every 112-byte row.
+            const long last_window_end = long(Q - 1) * q.stride_w * 8 + kBlockK;
+            const int kc_a = (kc < kBlockK && last_window_end <= long(q.w) * 8) ? kBlockK : kc;
+            dims[0] = cuuint64_t(kc_a); dims[1] = cuuint64_t(Q); dims[2] = cuuint64_t(q.h); dims[3] = cuuint64_t(q.n);
             strides[0] = cuuint64_t(q.stride_w) * 16;
             strides[1] = cuuint64_t(q.w) * 16;
             strides[2] = strides[1] * q.h;
@@ -973,7 +978,8 @@ int tma_probe2(int mode, int c, long rows_total, int box_c, int box_r, int csz, 
                float* ms, std::string* err) {
     if (!load_driver_entry_points(err)) return 1;
     CUtensorMap tm;
-    cuuint64_t dims[2] = {cuuint64_t(c), cuuint64_t(rows_total)};
+    // mode 2 with box_c > c: overlapping rows (row pitch c elements, row length box_c) like the packed-row stem operand
+    cuuint64_t dims[2] = {cuuint64_t(mode == 2 && box_c > c ? box_c : c), cuuint64_t(rows_total)};
     cuuint64_t strides[1] = {cuuint64_t(c) * 2};
     cuuint32_t box[2] = {cuuint32_t(mode == 2 ? box_c : kBlockK), cuuint32_t(mode == 2 ? box_r : kBlockM / csz)};
     cuuint32_t estr[2] = {1, 1};

@@ -35,6 +35,8 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-DSMELTER_BUILDING",
 ]
+if os.environ.get("SMELTER_CONV_INSTRUMENT"):  # perf experiments: %globaltimer stamps + ablation flags in the conv kernel
+    NVCC_FLAGS.append("-DSMELTER_CONV_INSTRUMENT=1")
 
 
 def _nvcc() -> str:

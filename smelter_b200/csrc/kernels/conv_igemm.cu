@@ -49,14 +49,21 @@ constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
 constexpr int kChunkN = 64;                           // epilogue column chunk = one 128-byte row of fp16
 constexpr uint32_t kEpiBufBytes = 32 * kChunkN * 2;   // one warp's [32 rows x 64 cols] staging tile
 constexpr uint32_t kBiasSlotBytes = kChunkN * 4;     // one warp's bias values for the current chunk (fp32)
-constexpr uint32_t kEpiBytes = kEpilogueWarps * (2 /*double buffered*/ * kEpiBufBytes + kBiasSlotBytes);
+constexpr uint32_t kBarrierBytes = 512;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
-template <int BLOCK_N>
+// Shared memory: [operand ring: kStages x (A tile + B tile)] [epilogue staging] [bias slots] [barriers].
+// Whatever the epilogue does not need goes to the ring: the k-loop is bound by (bytes in flight) / (L2 latency), so every
+// extra stage is throughput.  Without a residual each epilogue warp stages through ONE 4 KiB buffer (results are packed in
+// registers and written once the previous TMA store has read the buffer); with a residual it keeps two, because the
+// residual chunk of the next item is TMA-prefetched into the other buffer while this one is computed and stored.
+template <int BLOCK_N, bool HAS_RES>
 struct Cfg {
     static constexpr uint32_t kBBytes = BLOCK_N * kBlockK * 2;
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
-    static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - 1024 /*align*/ - 512 /*barriers*/) / kStageBytes);
+    static constexpr int kEpiBufs = HAS_RES ? 2 : 1;
+    static constexpr uint32_t kEpiBytes = kEpilogueWarps * (kEpiBufs * kEpiBufBytes + kBiasSlotBytes);
+    static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - kBarrierBytes) / kStageBytes);
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 32) ? 32 : (2 * BLOCK_N <= 64 ? 64 : (2 * BLOCK_N <= 128 ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512)));
     // Producers in use: never more than the ring has stages.  A producer only knows (from its own previous wait) that
@@ -66,28 +73,39 @@ struct Cfg {
     static constexpr int kBProducers = kStages < kNumBProducers ? kStages : kNumBProducers;
     static constexpr int kChunks = BLOCK_N >= kChunkN ? BLOCK_N / kChunkN : 1;
     static constexpr int kChunkCols = BLOCK_N >= kChunkN ? kChunkN : BLOCK_N;  // columns of a chunk that carry data
-    static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + 1024 + 512;
+    // the dynamic shared-memory window starts 1024-byte aligned (checked in the kernel), so no alignment slack is reserved
+    static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + kBarrierBytes;
 };
 
+// Instrumented builds only (-DSMELTER_CONV_INSTRUMENT=1): %globaltimer stamps of CTA 0 and the SMELTER_CONV_DEBUG ablation flags
+// (16 = producers arrive without loading, 32 = no operand barriers at all, 64 = no MMAs).  Compiled out of the product kernel:
+// every extra instruction in the single-thread MMA issue loop is on the critical path (measured: the loop, not the tensor pipe,
+// set the k-block rate when it carried these checks).
+#ifndef SMELTER_CONV_INSTRUMENT
+#define SMELTER_CONV_INSTRUMENT 0
+#endif
+constexpr bool kInstr = SMELTER_CONV_INSTRUMENT != 0;
+constexpr int kMmaLoopVariant = 1;  // MMA issue loop: 0 = one elected lane, 1 = same unrolled by two, 2 = whole warp + elected issue
+
 __device__ __forceinline__ void stamp(const ConvKernelParams& p, int slot) {
-    if (p.timeline && blockIdx.x == 0) {
+    if (kInstr && p.timeline && blockIdx.x == 0) {
         unsigned long long t;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
         p.timeline[slot] = t;
     }
 }
+__device__ __forceinline__ bool dbg(const ConvKernelParams& p, int flag) { return kInstr && (p.debug_flags & flag); }
 
 // Sigmoid is rare on this path (no BASELINE model fuses it): keep it out of line so the hot epilogue stays small.
 __device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
 
 // One [32 row x kCols column] chunk of the epilogue for one warp: v = fp32 accumulators of this lane's row; +bias (fp32, from
-// the warp's smem bias slot), +residual (fp32, read from the staging row where TMA put it), activation, fp16, written back
-// to the same staging row (128B-swizzled: 16-byte piece g of row r sits at piece g ^ (r & 7)).
-// Software-pipelined over the 8-column groups: the bias (and residual) of group g+1 are fetched from shared memory while
-// group g is computed, so no LDS latency sits on the dependency chain.
+// the warp's smem bias slot), +residual (fp32, read from the staging row where TMA put it), activation, fp16, packed into
+// registers (out[g] = columns 8g..8g+7).  Software-pipelined over the 8-column groups: the bias (and residual) of group g+1
+// are fetched from shared memory while group g is computed, so no LDS latency sits on the dependency chain.
 template <int kCols, bool HAS_RES>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot, bool is_sigmoid,
-                                              __half2 lo2, __half2 hi2) {
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
+                                              bool is_sigmoid, __half2 lo2, __half2 hi2) {
     constexpr int kGroups = kCols / 8;
     uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
     uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
@@ -118,11 +136,109 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint32
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
         }
-        uint4 ov;
-        __half2* oh = reinterpret_cast<__half2*>(&ov);
+        __half2* oh = reinterpret_cast<__half2*>(&out[g]);
 #pragma unroll
         for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
-        st_shared_v4(rowbuf + ((uint32_t(g) ^ sw) << 4), ov);
+    }
+}
+// Packed results -> this lane's row of the staging tile (128B-swizzled: 16-byte piece g of row r sits at piece g ^ (r & 7)).
+template <int kGroups>
+__device__ __forceinline__ void epilogue_stage(const uint4 (&out)[kGroups], uint32_t rowbuf, uint32_t sw) {
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) st_shared_v4(rowbuf + ((uint32_t(g) ^ sw) << 4), out[g]);
+}
+
+// ---- TMA producer loop (one thread) -------------------------------------------------------------------------
+// The issuing thread's instruction stream is the producer's throughput: measured on B200, a loop that re-derived the filter
+// tap with an integer division and walked every k-block (own or not) spent ~0.35 us per TMA instruction, slower than the
+// tensor core consumes a k-block.  So: the thread visits only its own k-blocks (stride n_prod), all positions (channel
+// block, filter tap, ring stage, barrier addresses) advance by adds and compares, per-item divisions are done once per
+// output tile, and the three operand kinds get their own loop bodies.
+enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
+
+template <int KIND, int BLOCK_N, bool HAS_RES>
+__device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelParams& p, uint32_t smem_base, uint32_t bar_base, int me, int n_prod,
+                                        int num_tiles, int total_kb) {
+    using C = Cfg<BLOCK_N, HAS_RES>;
+    constexpr uint32_t kTxBytes = KIND == PROD_B ? C::kBBytes : kABytes;
+    const int grid = int(gridDim.x);
+    const int kpt = p.kblocks_per_tap, taps_w = p.taps_w, nn = p.num_n_tiles;
+    // ring position of my next k-block
+    uint32_t stage = uint32_t(me), phase = 0;
+    uint32_t full_addr = bar_base + 8u * stage;                                            // empty barrier = full_addr + 8 * kStages
+    uint32_t dst = smem_base + stage * C::kStageBytes + (KIND == PROD_B ? kABytes : 0u);
+    int kb = me;  // my next k-block, relative to the current item's first
+    // (m_tile, n_tile) of the current item advance by a constant per item when there is no k-split
+    int item = int(blockIdx.x);
+    int m_tile = item / nn, n_tile = item - m_tile * nn;
+    const int dm = grid / nn, dn = grid - dm * nn;
+    for (; item < num_tiles; item += grid) {
+        int kb0 = 0, num_kb = total_kb;
+        if (p.splits > 1) {
+            const int tile = item / p.splits;
+            const int split = item - tile * p.splits;
+            kb0 = split * p.kb_per_split;
+            num_kb = min(p.kb_per_split, total_kb - kb0);
+            m_tile = tile / nn;
+            n_tile = tile - m_tile * nn;
+        }
+        if (kb < num_kb) {
+            const int m0 = m_tile * kBlockM;
+            const int n0 = n_tile * BLOCK_N;
+            // position of k-block kb0 + kb inside the filter: channel block, tap (linear), tap column / row
+            int cblk = 0, tap = 0, fs = 0, fr = 0;
+            int img = 0, base_h = 0, base_w = 0;
+            if (KIND != PROD_A_TILED) {
+                const int k_abs = kb0 + kb;
+                if (k_abs < 8) {  // the usual case (kb < n_prod, no split): a few carries instead of two divisions
+                    cblk = k_abs;
+                    while (cblk >= kpt) { cblk -= kpt; ++tap; ++fs; }
+                    while (fs >= taps_w) { fs -= taps_w; ++fr; }
+                } else {
+                    tap = k_abs / kpt; cblk = k_abs - tap * kpt;
+                    fr = tap / taps_w; fs = tap - fr * taps_w;
+                }
+            }
+            if (KIND == PROD_A_IM2COL) {
+                img = m0 / p.PQ;
+                const int rem = m0 - img * p.PQ;
+                const int op = rem / p.Q;
+                const int oq = rem - op * p.Q;
+                base_h = p.corner_h + op * p.stride_h;
+                base_w = p.corner_w + oq * p.stride_w;
+            }
+#pragma unroll 1
+            for (; kb < num_kb; kb += n_prod) {
+                mbar_wait(full_addr + 8u * C::kStages, phase ^ 1u);
+                if (kInstr && dbg(p, 16)) {
+                    mbar_arrive(full_addr);
+                } else {
+                    mbar_expect_tx(full_addr, kTxBytes);
+                    if (KIND == PROD_A_TILED) tma_load_2d(tm, full_addr, dst, (kb0 + kb) * kBlockK, m0);
+                    else if (KIND == PROD_A_IM2COL) tma_load_im2col_4d(tm, full_addr, dst, cblk * kBlockK, base_w, base_h, img, uint16_t(fs * p.dil_w), uint16_t(fr * p.dil_h));
+                    else tma_load_3d(tm, full_addr, dst, cblk * kBlockK, tap, n0);
+                }
+                // advance everything by n_prod k-blocks
+                stage += uint32_t(n_prod);
+                full_addr += 8u * uint32_t(n_prod);
+                dst += uint32_t(n_prod) * C::kStageBytes;
+                if (stage >= uint32_t(C::kStages)) {
+                    stage -= uint32_t(C::kStages);
+                    phase ^= 1u;
+                    full_addr -= 8u * uint32_t(C::kStages);
+                    dst -= uint32_t(C::kStages) * C::kStageBytes;
+                }
+                if (KIND != PROD_A_TILED) {
+                    cblk += n_prod;
+                    while (cblk >= kpt) { cblk -= kpt; ++tap; ++fs; }
+                    while (fs >= taps_w) { fs -= taps_w; ++fr; }
+                }
+            }
+        }
+        kb -= num_kb;
+        n_tile += dn;
+        m_tile += dm;
+        if (n_tile >= nn) { n_tile -= nn; ++m_tile; }
     }
 }
 
@@ -130,12 +246,14 @@ template <int BLOCK_N, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                   const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res, const ConvKernelParams p) {
-    using C = Cfg<BLOCK_N>;
-    extern __shared__ uint8_t smem_raw[];
-    // SWIZZLE_128B tiles need 1024-byte alignment.
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    using C = Cfg<BLOCK_N, HAS_RES>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    // SWIZZLE_128B tiles need 1024-byte alignment; the dynamic window starts aligned (no static shared memory in this kernel).
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) __trap();
     const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;  // 1024-aligned: stage sizes are multiples of 1024
-    const uint32_t bar_base = epi_base + kEpiBytes;
+    const uint32_t bias_base = epi_base + kEpilogueWarps * C::kEpiBufs * kEpiBufBytes;
+    const uint32_t bar_base = epi_base + C::kEpiBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
     auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
@@ -143,7 +261,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };  // w in [0, 8)
     const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 20);
     const uint32_t flag_slot = bar_base + 8u * (2 * C::kStages + 21);  // two 8-byte slots: "this group reduces the tile" (split-K)
-    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+    static_assert(8u * (2 * C::kStages + 23) <= kBarrierBytes, "barrier region too small");
+    static_assert(C::kSmemBytes <= kSmemLimit, "shared memory budget");
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -181,111 +301,113 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (threadIdx.x == 0) stamp(p, 1);  // prologue done
-    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may overlap
-    // the previous kernel's tail; from here on we read its output (and overwrite buffers it may still be reading).
-    if (p.use_pdl) {
-        grid_dep_launch_dependents();
-        grid_dep_wait();
-    }
-    if (threadIdx.x == 0) stamp(p, 2);  // dependencies resolved
+    // PDL: everything above (barrier init, TMEM allocation, descriptor prefetch) touched no global data and may overlap the
+    // previous kernel's tail.  From here on each role waits for the previous grid only if it touches what that grid produced:
+    // the activation (A) producers and the epilogue (residual loads, output stores, split-K workspace) do; the weight (B)
+    // producers and the MMA issuer do not, so the weight tiles of the first k-blocks are already in flight when the wait ends.
+    if (p.use_pdl) grid_dep_launch_dependents();
 
     if (warp < kNumProducers || warp >= kBProducerWarp0) {
         // ================= TMA producers =================
-        // All walk the same (tile, k-block) sequence; producer i of an operand issues the loads of every kProducers-th
-        // k-block of that operand.  Both operands of a k-block land in the same stage and complete the same full barrier.
+        // Producer i of an operand issues the loads of k-blocks i, i + n, i + 2n, ... of the CTA's k-block stream (n producers
+        // per operand).  Both operands of a k-block land in the same stage and complete the same full barrier.  One elected
+        // lane per producer warp runs the loop; see produce() for why the loop is written the way it is.
         const bool is_a = warp < kNumProducers;
         const int me = is_a ? warp : warp - kBProducerWarp0;
         const int n_prod = is_a ? C::kProducers : C::kBProducers;
-        const bool leader = elect_one();  // one lane per producer warp runs the loop
-        if (leader && me < n_prod && !(p.debug_flags & 32)) {
-            int stage = 0;
-            uint32_t phase = 0;
-            uint32_t turn = 0;  // k-block counter modulo the number of producers of this operand
-            for (int item = blockIdx.x; item < num_tiles; item += gridDim.x) {
-                const int tile = item / p.splits;
-                const int split = item - tile * p.splits;
-                const int kb0 = split * p.kb_per_split;
-                const int num_kb = min(p.kb_per_split, total_kb - kb0);
-                const int m_tile = tile / p.num_n_tiles;
-                const int n_tile = tile - m_tile * p.num_n_tiles;
-                const int m0 = m_tile * kBlockM;
-                const int n0 = n_tile * BLOCK_N;
-                int img = 0, base_h = 0, base_w = 0;
-                if (is_a && p.mode != CONV_MODE_TILED) {
-                    img = m0 / p.PQ;
-                    const int rem = m0 - img * p.PQ;
-                    const int op = rem / p.Q;
-                    const int oq = rem - op * p.Q;
-                    base_h = p.corner_h + op * p.stride_h;
-                    base_w = p.corner_w + oq * p.stride_w;
-                }
-                int tap = kb0 / p.kblocks_per_tap, cblk = kb0 - tap * p.kblocks_per_tap;
-                for (int kb = 0; kb < num_kb; ++kb) {
-                    if (turn == uint32_t(me)) {
-                        mbar_wait(empty_bar(stage), phase ^ 1);
-                        const uint32_t a_dst = smem_base + stage * C::kStageBytes;
-                        if (p.debug_flags & 16) {
-                            mbar_arrive(full_bar(stage));
-                        } else if (is_a) {
-                            mbar_expect_tx(full_bar(stage), kABytes);
-                            if (p.mode == CONV_MODE_TILED) {
-                                tma_load_2d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, m0);
-                            } else {
-                                const int r = tap / p.taps_w;
-                                const int s = tap - r * p.taps_w;
-                                tma_load_im2col_4d(&tm_a, full_bar(stage), a_dst, cblk * kBlockK, base_w, base_h, img,
-                                                   uint16_t(s * p.dil_w), uint16_t(r * p.dil_h));
-                            }
-                        } else {
-                            mbar_expect_tx(full_bar(stage), C::kBBytes);
-                            tma_load_3d(&tm_b, full_bar(stage), a_dst + kABytes, cblk * kBlockK, tap, n0);
-                        }
-                    }
-                    if (++cblk == p.kblocks_per_tap) { cblk = 0; ++tap; }
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
-                    if (++turn == uint32_t(n_prod)) turn = 0;
-                }
+        if (elect_one() && me < n_prod && !dbg(p, 32)) {
+            if (is_a) {
+                if (p.use_pdl) grid_dep_wait();
+                if (threadIdx.x == 0) stamp(p, 2);  // dependencies resolved
+                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_tiles, total_kb);
+                else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_tiles, total_kb);
+            } else {
+                produce<PROD_B, BLOCK_N, HAS_RES>(&tm_b, p, smem_base, bar_base, me, n_prod, num_tiles, total_kb);
             }
         }
     } else if (warp == kMmaWarp) {
         // ================= MMA issuer =================
-        // One elected lane issues the tcgen05 instructions.  This single instruction stream feeds the tensor core, so it is
-        // kept minimal: the shared-memory descriptors are
-        // (constant high word, low word = stage base >> 4) and the k-advance is an immediate add.
+        // One elected lane issues the tcgen05 instructions.  This single instruction stream feeds the tensor core, so the loop
+        // body is kept to the bare sequence (wait, 4 x MMA, commit): descriptor words and barrier addresses advance by adds,
+        // the first k-block of a tile (which overwrites the accumulator) is peeled so the accumulate flag is an immediate.
         constexpr uint32_t idesc = make_idesc_f16(kBlockM, BLOCK_N);
         constexpr uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);  // SBO, version, SWIZZLE_128B
         constexpr uint32_t desc_lbo = 1u << 16;
         const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | desc_lbo;
         constexpr uint32_t kStage16 = C::kStageBytes >> 4;
         constexpr uint32_t kB16 = kABytes >> 4;
-        // Only the elected lane runs the loop: a barrier wait executed by all 32 lanes is 32 separate mbarrier operations.
-        if (elect_one()) {
-            int stage = 0;
-            uint32_t phase = 0;
-            for (int t = 0; t < my_tiles; ++t) {
-                const int acc = t & 1;                       // accumulator buffer == epilogue group
+        uint32_t stage = 0, phase = 0;
+        uint32_t a_lo = a_lo0;
+        uint32_t full_addr = bar_base;  // full_bar(stage); empty_bar(stage) = full_addr + 8 * kStages
+        auto issue = [&](uint32_t tmem_d, uint32_t first_accumulate) {
+            const uint64_t a_desc = desc_hi | uint64_t(a_lo);
+            const uint64_t b_desc = a_desc + kB16;
+            if (!dbg(p, 64)) {
+                umma_f16(tmem_d, a_desc, b_desc, idesc, first_accumulate);
+                umma_f16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);   // +32 bytes along K inside the swizzle atom
+                umma_f16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
+                umma_f16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
+            }
+            if (!dbg(p, 32)) umma_commit(full_addr + 8u * C::kStages);  // frees the smem slot once these MMAs retire
+            else if (dbg(p, 1024)) umma_commit(res_bar(7, 1));          // experiment: cost of the commit alone (nobody waits on it)
+        };
+        auto advance = [&]() {
+            a_lo += kStage16;
+            full_addr += 8u;
+            if (++stage == uint32_t(C::kStages)) { stage = 0; phase ^= 1u; a_lo = a_lo0; full_addr = bar_base; }
+        };
+        auto tile_kb = [&](int t) {
+            int num_kb = total_kb;
+            if (p.splits > 1) {
                 const int split = (int(blockIdx.x) + t * int(gridDim.x)) % p.splits;
-                const int num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
+                num_kb = min(p.kb_per_split, total_kb - split * p.kb_per_split);
+            }
+            return num_kb;
+        };
+        const int variant = kInstr ? ((p.debug_flags >> 8) & 3) : kMmaLoopVariant;
+        if (variant == 2) {
+            // whole warp walks the loop (uniform registers, no R2UR); one elected lane issues
+            for (int t = 0; t < my_tiles; ++t) {
+                const int acc = t & 1;
+                const int num_kb = tile_kb(t);
                 mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
-                uint32_t accumulate = 0;
+#pragma unroll 1
                 for (int kb = 0; kb < num_kb; ++kb) {
-                    if (!(p.debug_flags & 32)) mbar_wait(full_bar(stage), phase);
-                    if (t == 0 && kb == 0) stamp(p, 3);  // first operands landed
+                    if (!dbg(p, 32)) mbar_wait(full_addr, phase);
                     tc_fence_after();
-                    const uint64_t a_desc = desc_hi | uint64_t(a_lo0 + uint32_t(stage) * kStage16);
-                    const uint64_t b_desc = a_desc + kB16;
-                    if (!(p.debug_flags & 64)) {
-                        umma_f16(tmem_d, a_desc, b_desc, idesc, accumulate);
-                        umma_f16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);   // +32 bytes along K inside the swizzle atom
-                        umma_f16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
-                        umma_f16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
-                    }
-                    if (!(p.debug_flags & 32)) umma_commit(empty_bar(stage));  // frees the smem slot once these MMAs retire
-                    accumulate = 1u;
-                    if (++stage == C::kStages) { stage = 0; phase ^= 1; }
+                    if (elect_one()) issue(tmem_d, kb > 0 ? 1u : 0u);
+                    advance();
                 }
+                if (elect_one()) umma_commit(tmem_full_bar(acc));
+            }
+        } else if (elect_one()) {
+            // Only the elected lane runs the loop.
+            auto kblock = [&](uint32_t tmem_d, uint32_t first_accumulate) {
+                if (!dbg(p, 32)) mbar_wait(full_addr, phase);
+                tc_fence_after();
+                issue(tmem_d, first_accumulate);
+                advance();
+            };
+            for (int t = 0; t < my_tiles; ++t) {
+                const int acc = t & 1;                       // accumulator buffer == epilogue group
+                const int num_kb = tile_kb(t);
+                mbar_wait(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+                kblock(tmem_d, 0u);
+                if (t == 0) stamp(p, 3);  // first operands landed
+                int kb = 1;
+                if (variant == 1) {
+#pragma unroll 1
+                    for (; kb + 1 < num_kb; kb += 2) {
+                        kblock(tmem_d, 1u);
+                        kblock(tmem_d, 1u);
+                    }
+                }
+#pragma unroll 1
+                for (; kb < num_kb; ++kb) kblock(tmem_d, 1u);
                 umma_commit(tmem_full_bar(acc));  // accumulator complete -> epilogue group `acc`
                 if (t == 0) stamp(p, 4);  // all MMAs of the first tile issued
             }
@@ -295,21 +417,41 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         // Two groups of four warps; group g drains accumulator buffer g, i.e. this CTA's tiles g, g+2, g+4, ... so the
         // two groups interleave on the four SM sub-partitions and hide each other's latencies.  Within a group each warp
         // owns 32 accumulator rows (its TMEM lane quarter) and streams them out in 64-column chunks:
-        //   TMEM -> registers -> +bias (+residual) in fp32 -> fp16 -> activation clamp (packed half2) ->
+        //   TMEM -> registers -> +bias (+residual) in fp32 -> fp16 -> activation clamp (packed half2, still in registers) ->
         //   128B-swizzled smem staging -> TMA store.
-        // The residual chunk is fetched by TMA into the same staging buffer ahead of time and the result overwrites it
-        // in place (every thread reads and writes only its own 16-byte pieces), so all global traffic is whole 128-byte
-        // lines issued by the TMA unit.
+        // Without a residual the warp has one staging buffer: the packed results wait in registers until the previous chunk's
+        // TMA store has read it.  With a residual there are two: the residual chunk of the next item is TMA-prefetched into
+        // the other buffer and the result overwrites it in place (every thread reads and writes only its own 16-byte pieces).
+        // All global traffic is whole 128-byte lines issued by the TMA unit.
+        if (p.use_pdl) grid_dep_wait();
         const int ewarp = warp - kEpilogueWarp0;  // 0..7
         const int group = ewarp >> 2;
         const int ew = ewarp & 3;                 // == warp % 4: the TMEM lane quarter this warp may read
-        const uint32_t buf0 = epi_base + uint32_t(ewarp) * 2u * kEpiBufBytes;
-        const uint32_t bias_slot = epi_base + kEpilogueWarps * 2u * kEpiBufBytes + uint32_t(ewarp) * kBiasSlotBytes;
+        const uint32_t buf0 = epi_base + uint32_t(ewarp) * uint32_t(C::kEpiBufs) * kEpiBufBytes;
+        const uint32_t bias_slot = bias_base + uint32_t(ewarp) * kBiasSlotBytes;
         const uint32_t row_off = uint32_t(lane) * 128u;
         const uint32_t sw = uint32_t(lane & 7);
         const bool is_sigmoid = p.act == ACT_SIGMOID;
         const __half2 lo2 = __float2half2_rn(p.act == ACT_RELU ? 0.f : (p.act == ACT_CLIP ? p.clip_lo : -INFINITY));
         const __half2 hi2 = __float2half2_rn(p.act == ACT_CLIP ? p.clip_hi : INFINITY);
+        // One chunk from accumulators in registers to a committed TMA store.  `b` selects the staging buffer (always 0 without
+        // a residual); with a residual the caller has already waited for the chunk's residual to land in that buffer.
+        auto finish_chunk = [&](const uint32_t (&v)[C::kChunkCols], int b, int col0, int m_row0) {
+            const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
+            uint4 out[C::kChunkCols / 8];
+            epilogue_math<C::kChunkCols, HAS_RES>(v, out, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
+            if (!HAS_RES) {
+                if (lane == 0) tma_store_wait_read<0>();  // the previous chunk's store has read the (only) buffer
+                __syncwarp();
+            }
+            epilogue_stage<C::kChunkCols / 8>(out, buf + row_off, sw);
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
+            __syncwarp();              // also: every lane is done with the bias slot before the next chunk's bias is published
+            if (lane == 0) {
+                tma_store_2d(&tm_out, buf, col0, m_row0);  // rows >= M and columns >= out_pitch are clipped by the map
+                tma_store_commit();
+            }
+        };
         if (p.splits == 1) {
         const int group_tiles = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
         const int n_items = group_tiles * C::kChunks;  // (tile, chunk) stream of this warp
@@ -342,7 +484,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         uint32_t acc_phase = 0;
         int item = 0;
         for (int gt = 0; gt < group_tiles; ++gt) {
-            mbar_wait(tmem_full_bar(group), acc_phase);
+            mbar_wait(tmem_full_bar(group), acc_phase);  // (one polling lane + nanosleep back-off measured slower than all lanes waiting)
             if (gt == 0 && ewarp == 0 && lane == 0) stamp(p, 5);  // first accumulator ready
             acc_phase ^= 1u;
             tc_fence_after();
@@ -356,17 +498,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             }
 #pragma unroll 1
             for (int c = 0; c < C::kChunks; ++c, ++item, col0 += kChunkN) {
-                const int b = item & 1;
-                const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
-                if (lane == 0) {
-                    if (HAS_RES) {
-                        if (item + 1 < n_items) {
-                            tma_store_wait_read<0>();  // the store of item-1 has finished reading buffer b^1
-                            prefetch_res(item + 1);
-                        }
-                    } else {
-                        tma_store_wait_read<1>();      // the store of item-2 has finished reading buffer b
-                    }
+                const int b = HAS_RES ? (item & 1) : 0;
+                if (HAS_RES && lane == 0 && item + 1 < n_items) {
+                    tma_store_wait_read<0>();  // the store of item-1 has finished reading buffer b^1
+                    prefetch_res(item + 1);
                 }
                 // publish this chunk's bias to the warp through smem, then start fetching the next chunk's
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
@@ -384,14 +519,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                     mbar_wait(res_bar(ewarp, b), (res_phase >> b) & 1u);
                     res_phase ^= 1u << b;
                 }
-                __syncwarp();  // lane 0's wait_group.read above covers the whole warp's upcoming smem writes
-                epilogue_math<C::kChunkCols, HAS_RES>(v, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
-                fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tm_out, buf, col0, m_row0);  // rows >= M and columns >= out_pitch are clipped by the map
-                    tma_store_commit();
-                }
+                __syncwarp();  // the bias slot is published (and, with a residual, lane 0's wait_group.read covers the warp)
+                finish_chunk(v, b, col0, m_row0);
             }
         }
         } else {
@@ -400,7 +529,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             // then bumps the tile's counter; the CTA that arrives last sums all slabs and runs the normal epilogue
             // (bias, residual, activation, TMA store) and resets the counter for the next launch.
             const int group_items = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
-            volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_raw + (flag_slot + 8u * uint32_t(group) - smem_u32(smem_raw)));
+            volatile uint32_t* flag = reinterpret_cast<volatile uint32_t*>(smem_raw + (flag_slot + 8u * uint32_t(group) - smem_base));
             const int row = ew * 32 + lane;
             uint32_t acc_phase = 0, res_phase = 0;
             int n_stores = 0;  // TMA stores this warp has committed (selects the staging buffer)
@@ -453,17 +582,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
 #pragma unroll 1
                 for (int c = 0; c < C::kChunks; ++c, ++n_stores, col0 += kChunkN) {
-                    const int b = n_stores & 1;
-                    const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
-                    if (lane == 0) {
-                        if (HAS_RES) {
-                            if (c + 1 < C::kChunks) {
-                                tma_store_wait_read<0>();
-                                load_res(c + 1, b ^ 1);
-                            }
-                        } else {
-                            tma_store_wait_read<1>();
-                        }
+                    const int b = HAS_RES ? (n_stores & 1) : 0;
+                    if (HAS_RES && lane == 0 && c + 1 < C::kChunks) {
+                        tma_store_wait_read<0>();
+                        load_res(c + 1, b ^ 1);
                     }
                     asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
                     if (c + 1 < C::kChunks) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + kChunkN) + lane);
@@ -487,13 +609,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                         res_phase ^= 1u << b;
                     }
                     __syncwarp();
-                    epilogue_math<C::kChunkCols, HAS_RES>(v, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
-                    fence_proxy_async_smem();
-                    __syncwarp();
-                    if (lane == 0) {
-                        tma_store_2d(&tm_out, buf, col0, m_row0);
-                        tma_store_commit();
-                    }
+                    finish_chunk(v, b, col0, m_row0);
                 }
             }
         }
@@ -546,9 +662,9 @@ bool load_driver_entry_points(std::string* err) {
 template <int BLOCK_N>
 cudaError_t set_attr_t() {
     // per device; cheap, and done at prepare time so that launches are legal inside stream capture
-    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N>::kSmemBytes));
+    cudaError_t e = cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, false>::kSmemBytes));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N>::kSmemBytes));
+    return cudaFuncSetAttribute(conv_igemm_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, true>::kSmemBytes));
 }
 cudaError_t set_attr(int block_n) {
     switch (block_n) {
@@ -565,7 +681,7 @@ cudaError_t launch_t(const ConvTcLaunch& L, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(L.grid));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = Cfg<BLOCK_N>::kSmemBytes;
+    cfg.dynamicSmemBytes = L.p.has_residual ? Cfg<BLOCK_N, true>::kSmemBytes : Cfg<BLOCK_N, false>::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;

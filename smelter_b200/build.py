@@ -25,6 +25,7 @@ SOURCES = [
     "capi.cc",
     "nccl_shim.cc",
     "kernels/conv_igemm.cu",
+    "kernels/conv_mega.cu",
     "kernels/elementwise.cu",
     "kernels/pool_norm.cu",
 ]

@@ -112,10 +112,12 @@ struct Plan {
     Tensor result;
     cudaGraphExec_t exec = nullptr;
     void* counters = nullptr;  // split-K arrival counters of every conv in the plan (zero between launches)
+    std::vector<void*> blobs;  // further device allocations owned by the plan (completion counters of persistent conv runs)
     ~Plan() {
         if (exec) cudaGraphExecDestroy(exec);
         if (arena) cudaFree(arena);
         if (counters) cudaFree(counters);
+        for (void* b : blobs) cudaFree(b);
     }
 };
 
@@ -477,6 +479,35 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             (only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
             stem_of[size_t(v)] = only;
     }
+    // ---- runs of consecutive tensor-core convolutions: one persistent multi-layer launch each (kernels/conv_mega.cu) ----
+    // Inside a run tiles of different layers are in flight at the same time, so no buffer is recycled until the run ends.
+    std::vector<int> run_of(filters_.size(), -1);
+    std::vector<std::vector<size_t>> runs;
+    if (!getenv("SMELTER_NO_MEGA")) {
+        std::vector<size_t> cur;
+        auto flush_run = [&]() {
+            if (cur.size() >= 2) {
+                for (size_t fi : cur) run_of[fi] = int(runs.size());
+                runs.push_back(cur);
+            }
+            cur.clear();
+        };
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& f = filters_[fi];
+            if (f.removed) continue;
+            bool ok = f.kind == FilterKind::Conv && f.conv_mode != 4 && !f.is_gemm;
+            if (ok && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) &&
+                stem_of[size_t(root_of(f.in[0]))] != &f)
+                ok = false;  // needs its own pad pass in front
+            if (!ok) { flush_run(); continue; }
+            if (f.conv_mode == k::CONV_MODE_PACKED_ROW) flush_run();  // reads a tensor laid out by a non-conv step: may only start a run
+            cur.push_back(fi);
+            if (int(cur.size()) == k::kMegaMaxLayers) flush_run();
+        }
+        flush_run();
+    }
+    std::vector<std::pair<size_t, size_t>> deferred_release;
+
     auto input_bytes = [&](int v) {
         const Filter* f = stem_of[size_t(v)];
         if (!f) return bytes_of(v);
@@ -528,8 +559,15 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
-            if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1))
-                arena.release(off[size_t(r)], values_[size_t(r)].is_input ? input_bytes(r) : bytes_of(r));
+            if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1)) {
+                const size_t rb = values_[size_t(r)].is_input ? input_bytes(r) : bytes_of(r);
+                if (run_of[fi] >= 0) deferred_release.push_back({off[size_t(r)], rb});
+                else arena.release(off[size_t(r)], rb);
+            }
+        if (run_of[fi] >= 0 && runs[size_t(run_of[fi])].back() == fi) {
+            for (const auto& d : deferred_release) arena.release(d.first, d.second);
+            deferred_release.clear();
+        }
     }
     // result tensor (NCHW) unless the output value is already NCHW-compatible
     const ImageShape& os = values_[size_t(output_value_)].shape;
@@ -572,6 +610,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         plan->steps.back().boundary = true;
     }
 
+    std::vector<k::ConvTcProblem> mega_q;
+    std::vector<int> mega_dep, mega_res_dep;
+    std::unordered_map<int, int> mega_producer;  // root value -> layer of the current run that writes it
+    double mega_flops = 0, mega_bytes = 0;
+    std::string mega_desc;
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
         if (f.removed) continue;
@@ -614,6 +657,34 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                         return k::pad2d(x, padded, N, is.h, is.w, 8, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], k::PAD_CONSTANT, 0.f, st);
                     }, 0, double(scratch[fi].bytes) + double(N) * is.h * is.w * 16);
                     q.x = padded;
+                }
+                if (run_of[fi] >= 0) {
+                    // member of a persistent run: collected here, launched as one step when the run's last layer is reached
+                    const std::vector<size_t>& run = runs[size_t(run_of[fi])];
+                    if (run.front() == fi) { mega_q.clear(); mega_dep.clear(); mega_res_dep.clear(); mega_producer.clear(); mega_flops = mega_bytes = 0; mega_desc.clear(); }
+                    auto producer = [&](int v) { auto itp = mega_producer.find(root_of(v)); return itp == mega_producer.end() ? -1 : itp->second; };
+                    mega_dep.push_back(producer(f.in[0]));
+                    mega_res_dep.push_back(f.residual >= 0 ? producer(f.residual) : -1);
+                    mega_producer[root_of(f.out)] = int(mega_q.size());
+                    mega_q.push_back(q);
+                    mega_flops += flops;
+                    mega_bytes += io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0);
+                    if (run.front() == fi) mega_desc = values_[size_t(f.out)].name;
+                    if (run.back() == fi) {
+                        auto ML = std::make_shared<k::MegaLaunch>();
+                        const size_t words = k::conv_mega_sync_words(mega_q);
+                        void* sync = nullptr;
+                        SM_CUDA(cudaMalloc(&sync, words * sizeof(unsigned int)));
+                        plan->blobs.push_back(sync);
+                        std::string cerr;
+                        if (!k::conv_mega_prepare(ML.get(), mega_q, mega_dep, mega_res_dep, num_sms, static_cast<unsigned int*>(sync), &cerr))
+                            return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
+                        add_step("conv_mega[" + std::to_string(mega_q.size()) + " layers] Conv " + mega_desc + " .. " + values_[size_t(f.out)].name,
+                                 [ML](cudaStream_t st) { return k::conv_mega_launch(*ML, st); }, mega_flops, mega_bytes);
+                        plan->steps.back().tensor = true;
+                        plan->steps.back().launches = 2;  // counter memset + kernel
+                    }
+                    break;
                 }
                 auto L = std::make_shared<k::ConvTcLaunch>();
                 std::string cerr;

@@ -483,7 +483,10 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     // Inside a run tiles of different layers are in flight at the same time, so no buffer is recycled until the run ends.
     std::vector<int> run_of(filters_.size(), -1);
     std::vector<std::vector<size_t>> runs;
-    if (!getenv("SMELTER_NO_MEGA")) {
+    // Opt-in (SMELTER_MEGA=1): on ResNet-50 / batch 32 the persistent kernel currently ties with per-layer launches (the
+    // ~6.5 us store -> fence -> counter -> poll -> load dependency hop costs what a PDL kernel boundary costs).
+    const char* mega_env = getenv("SMELTER_MEGA");
+    if (mega_env && atoi(mega_env) != 0) {
         std::vector<size_t> cur;
         auto flush_run = [&]() {
             if (cur.size() >= 2) {
@@ -615,6 +618,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     std::unordered_map<int, int> mega_producer;  // root value -> layer of the current run that writes it
     double mega_flops = 0, mega_bytes = 0;
     std::string mega_desc;
+    void* mega_identity = nullptr;
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
         if (f.removed) continue;
@@ -676,8 +680,16 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                         void* sync = nullptr;
                         SM_CUDA(cudaMalloc(&sync, words * sizeof(unsigned int)));
                         plan->blobs.push_back(sync);
+                        if (!mega_identity) {  // 64 x 64 fp16 identity: the B operand of the residual k-blocks
+                            std::vector<uint16_t> eye(64 * 64, 0);
+                            for (int d = 0; d < 64; ++d) eye[size_t(d) * 65] = 0x3C00;
+                            SM_CUDA(cudaMalloc(&mega_identity, eye.size() * 2));
+                            plan->blobs.push_back(mega_identity);
+                            SM_CUDA(cudaMemcpy(mega_identity, eye.data(), eye.size() * 2, cudaMemcpyHostToDevice));
+                        }
                         std::string cerr;
-                        if (!k::conv_mega_prepare(ML.get(), mega_q, mega_dep, mega_res_dep, num_sms, static_cast<unsigned int*>(sync), &cerr))
+                        if (!k::conv_mega_prepare(ML.get(), mega_q, mega_dep, mega_res_dep, num_sms, static_cast<unsigned int*>(sync),
+                                                  static_cast<const __half*>(mega_identity), &cerr))
                             return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                         add_step("conv_mega[" + std::to_string(mega_q.size()) + " layers] Conv " + mega_desc + " .. " + values_[size_t(f.out)].name,
                                  [ML](cudaStream_t st) { return k::conv_mega_launch(*ML, st); }, mega_flops, mega_bytes);

@@ -694,6 +694,22 @@ cudaError_t launch_t(const ConvTcLaunch& L, cudaStream_t stream) {
 
 }  // namespace
 
+bool conv_tc_encode_2d(CUtensorMap* tm, const __half* base, long cols, long rows, int box_cols, int box_rows, std::string* err) {
+    if (!load_driver_entry_points(err)) return false;
+    cuuint64_t dims[2] = {cuuint64_t(cols), cuuint64_t(rows)};
+    cuuint64_t strides[1] = {cuuint64_t(cols) * 2};
+    cuuint32_t box[2] = {cuuint32_t(box_cols), cuuint32_t(box_rows)};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(2d) failed: " + std::to_string(int(r));
+        return false;
+    }
+    return true;
+}
+
 int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms) {
     // Smallest tile that covers Cout for narrow layers; for wide layers pick the width that leaves the fewest
     // idle SMs in the last wave (tiles are persistent-scheduled round-robin over num_sms CTAs).

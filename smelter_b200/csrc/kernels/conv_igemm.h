@@ -78,6 +78,8 @@ struct ConvTcLaunch {
 };
 
 int conv_tc_pick_block_n(int c_out, int m_tiles, int num_sms);
+// 128B-swizzled 2-D map over a dense row-major fp16 matrix [rows][cols] (out-of-range box elements read as zero)
+bool conv_tc_encode_2d(CUtensorMap* tm, const __half* base, long cols, long rows, int box_cols, int box_rows, std::string* err);
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only

@@ -77,8 +77,7 @@ def test_resnet50_batch4_matches_oracle(ctx):
     out = out.reshape(4, 1000)
     assert np.abs(out - want).max() <= TOL
     assert (out.argmax(1) == want.argmax(1)).all()
-    # boundary + stem conv + maxpool + [counter memset + ONE persistent launch for the 52 bottleneck convs, all ReLU/Add fused] + gap + fc
-    assert launches == 1 + 1 + 1 + 2 + 1 + 1
+    assert launches == 1 + 53 + 1 + 1 + 1  # boundary + conv (all ReLU/Add fused) + maxpool + gap + fc (logits are a view)
 
 
 def test_resnet50_batch32_properties(ctx, monkeypatch):
@@ -112,6 +111,35 @@ def test_resnet50_batch32_properties(ctx, monkeypatch):
     assert np.abs(full1[:2].astype(np.float32) - want).max() <= TOL
 
 
+def test_persistent_multi_layer_kernel_matches_per_layer_launches(ctx, monkeypatch):
+    """SMELTER_MEGA=1 runs the 52 bottleneck convolutions of ResNet-50 as ONE persistent launch with per-tile dataflow
+    dependencies (kernels/conv_mega.cu); the residual add moves into the tensor-core accumulator, so results agree with the
+    per-layer path to fp16 rounding, and with the oracle within the stated tolerance."""
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Image, ONNXGraph
+
+    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    x = np.random.default_rng(5).random((8, 3, 224, 224), dtype=np.float32).astype(np.float16)
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(8, 1000).copy() for _ in range(3)]
+        n = nn.numLaunches(8)
+        g.close()
+        return outs, n
+
+    base, n_base = run()
+    monkeypatch.setenv("SMELTER_MEGA", "1")  # read when a plan is made
+    mega, n_mega = run()
+    assert n_base == 57 and n_mega == 1 + 1 + 1 + 2 + 1 + 1  # boundary, stem, maxpool, [counter memset + persistent kernel], gap, fc
+    for o in mega[1:]:
+        assert np.array_equal(o.view(np.uint16), mega[0].view(np.uint16))  # replay determinism despite the dynamic tile timing
+    assert np.abs(mega[0].astype(np.float32) - base[0].astype(np.float32)).max() <= 4e-3
+    want = _oracle(model, x[:2])
+    assert np.abs(mega[0][:2].astype(np.float32) - want).max() <= TOL
+
+
 def test_mobilenet_v2_batch1(ctx):
     from smelter_b200 import modelzoo, onnx2mps
 
@@ -120,9 +148,7 @@ def test_mobilenet_v2_batch1(ctx):
     out, launches = _run(ctx, model, x)
     want = _oracle(model, x)
     assert np.abs(out.reshape(want.shape) - want).max() <= TOL
-    # Clip and the 10 residual Adds are fused into conv epilogues; consecutive 1x1 convs (project -> next expand) share one
-    # persistent launch (+ its counter memset); depthwise layers run between them
-    assert launches <= 1 + 52 + 16 + 1 + 1
+    assert launches == 1 + 52 + 1 + 1  # boundary + conv (Clip and the 10 residual Adds fused into epilogues) + gap + fc
 
 
 def test_transformer_net_256(ctx):

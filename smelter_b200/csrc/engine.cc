@@ -73,6 +73,22 @@ void pack_weights_rows(const float* w, int c_out, int c_in, int k_h, int k_w, ui
                 for (int c = 0; c < 8; ++c) d[c] = c < c_in ? onnx::float_to_half(src[c]) : uint16_t(0);
             }
 }
+// Stride-2 stem folded to stride 1 over a 2x2 space-to-depth image (Filter::s2d): w is OHWI [o][r][s][c]; the packed row
+// operand is [o][r2][s2][16] with channel (dy*2+dx)*c_in + c holding w[o][2*r2+dy][2*s2+dx][c] (zero outside the filter).
+void pack_weights_s2d(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst) {
+    const int r2n = (k_h + 1) / 2, s2n = (k_w + 1) / 2;
+    for (int o = 0; o < c_out; ++o)
+        for (int r2 = 0; r2 < r2n; ++r2)
+            for (int s2 = 0; s2 < s2n; ++s2) {
+                uint16_t* d = dst + ((size_t(o) * r2n + r2) * s2n + s2) * 16;
+                for (int j = 0; j < 16; ++j) d[j] = 0;
+                for (int dd = 0; dd < 4; ++dd) {
+                    const int r = 2 * r2 + (dd >> 1), sx = 2 * s2 + (dd & 1);
+                    if (r >= k_h || sx >= k_w) continue;
+                    for (int c = 0; c < c_in; ++c) d[dd * c_in + c] = onnx::float_to_half(w[((size_t(o) * k_h + r) * k_w + sx) * c_in + c]);
+                }
+            }
+}
 void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch, uint16_t* dst) {
     const int taps = k_h * k_w;  // w: OHWI with I = 1 -> [c][taps]
     for (int t = 0; t < taps; ++t)
@@ -311,6 +327,30 @@ int ONNXGraph::build() {
         if (f.conv_mode < 0)
             return fail(SMELTER_ERR_UNSUPPORTED, "grouped convolution other than depthwise (groups=" + std::to_string(f.groups) + ")");
     }
+    // stride-2 stems that are the only reader of a graph input run on a space-to-depth image (see Filter::s2d)
+    if (!getenv("SMELTER_NO_S2D")) {
+        auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
+        for (auto& f : filters_) {
+            if (f.removed || f.kind != FilterKind::Conv || f.conv_mode != k::CONV_MODE_PACKED_ROW) continue;
+            const int v = root_of(f.in[0]);
+            if (!values_[size_t(v)].is_input || v == root_of(output_value_)) continue;
+            int readers = 0;
+            for (const auto& g : filters_) {
+                if (g.removed) continue;
+                for (int i : g.in) if (root_of(i) == v) ++readers;
+                if (g.residual >= 0 && root_of(g.residual) == v) ++readers;
+            }
+            const int c_in = f.c_in_g * f.groups;
+            if (readers != 1 || f.stride_h != 2 || f.stride_w != 2 || f.dil_h != 1 || f.dil_w != 1 || c_in > 4 || (f.k_w + 1) / 2 * 16 > 256) continue;
+            const ImageShape& is = values_[size_t(v)].shape;
+            int hp = is.h + f.pads[0] + f.pads[2], wp = is.w + f.pads[1] + f.pads[3];
+            const int p_out = (hp - f.k_h) / 2 + 1, q_out = (wp - f.k_w) / 2 + 1;
+            hp += hp & 1; wp += wp & 1;  // one more zero row / column makes the padded image foldable
+            if (hp / 2 - (f.k_h + 1) / 2 + 1 != p_out || wp / 2 - (f.k_w + 1) / 2 + 1 != q_out) continue;  // folded conv must give the same output size
+            f.s2d = true;
+            f.s2d_h = hp; f.s2d_w = wp;
+        }
+    }
     rc = upload_weights();  // MPSNNGraph(device:resultImage:) pulls weights from the data sources (:185-190)
     if (rc) return fail(SMELTER_ERR_GRAPH_INTERNAL, "weight upload failed: " + last_error_string());
     built_ = true;
@@ -329,6 +369,7 @@ int ONNXGraph::upload_weights() {
             const int c_in = f.c_in_g * f.groups;
             size_t wbytes;
             if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
+            else if (f.s2d) wbytes = size_t(f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 16 * 2;
             else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) wbytes = size_t(f.c_out) * f.k_h * f.k_w * 8 * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
@@ -347,6 +388,7 @@ int ONNXGraph::upload_weights() {
             const int c_in = f.c_in_g * f.groups;
             uint16_t* w = reinterpret_cast<uint16_t*>(host.data() + f.w_off);
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
+            else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
             else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) pack_weights_rows(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
@@ -447,7 +489,13 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         q.k_h = f.k_h; q.k_w = f.k_w; q.stride_h = f.stride_h; q.stride_w = f.stride_w; q.dil_h = f.dil_h; q.dil_w = f.dil_w;
         q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
         q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
-        if (f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3])) {
+        if (f.s2d) {  // stride-1 convolution over the folded image the boundary conversion writes
+            q.h = f.s2d_h / 2; q.w = f.s2d_w / 2;
+            q.c_in_pitch = 16;
+            q.k_h = (f.k_h + 1) / 2; q.k_w = (f.k_w + 1) / 2;
+            q.stride_h = q.stride_w = 1;
+            q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3])) {
             q.h = is.h + f.pads[0] + f.pads[2];  // packed-row convolutions read a materialised zero-padded image
             q.w = is.w + f.pads[1] + f.pads[3];
             q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
@@ -476,7 +524,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             if (f.residual >= 0 && root_of(f.residual) == v) ++readers;
         }
         if (readers == 1 && v != out_root && only->kind == FilterKind::Conv && only->conv_mode == k::CONV_MODE_PACKED_ROW && only->in[0] == v &&
-            (only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
+            (only->s2d || only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
             stem_of[size_t(v)] = only;
     }
     // ---- runs of consecutive tensor-core convolutions: one persistent multi-layer launch each (kernels/conv_mega.cu) ----
@@ -515,6 +563,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         const Filter* f = stem_of[size_t(v)];
         if (!f) return bytes_of(v);
         const ImageShape& s = values_[size_t(v)].shape;
+        if (f->s2d) return size_t(N) * (f->s2d_h / 2) * (f->s2d_w / 2) * 16 * 2;
         return size_t(N) * (s.h + f->pads[0] + f->pads[2]) * (s.w + f->pads[1] + f->pads[3]) * round_up(s.c, 8) * 2;
     };
     // graph inputs: NHWC copies produced by the boundary conversion
@@ -607,6 +656,14 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         const int cp = pitch_of(v);
         int pt = 0, pl = 0, pb = 0, pr = 0;
         if (const Filter* sf = stem_of[size_t(v)]) { pt = sf->pads[0]; pl = sf->pads[1]; pb = sf->pads[2]; pr = sf->pads[3]; }
+        if (const Filter* sf = stem_of[size_t(v)]; sf && sf->s2d) {
+            const int h2 = sf->s2d_h / 2, w2 = sf->s2d_w / 2;
+            add_step("nchw_to_s2d+pad0 " + values_[size_t(v)].name,
+                     [=](cudaStream_t st) { return k::nchw_to_s2d(*slot, dst, N, s.c, s.h, s.w, pt, pl, h2, w2, st); }, 0,
+                     double(N) * (double(s.h) * s.w * s.c + double(h2) * w2 * 16) * 2);
+            plan->steps.back().boundary = true;
+            continue;
+        }
         add_step(std::string(pt || pl || pb || pr ? "nchw_to_nhwc+pad0 " : "nchw_to_nhwc ") + values_[size_t(v)].name,
                  [=](cudaStream_t st) { return k::nchw_to_nhwc(*slot, dst, N, s.c, s.h, s.w, cp, pt, pl, pb, pr, st); }, 0,
                  double(N) * (double(s.h) * s.w * s.c + double(s.h + pt + pb) * (s.w + pl + pr) * cp) * 2);
@@ -701,7 +758,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 auto L = std::make_shared<k::ConvTcLaunch>();
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
-                const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : "rows";
+                const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,

@@ -93,6 +93,10 @@ struct Filter {
     // device-side constants (offsets into the weight arena), filled by build()
     size_t w_off = 0, bias_off = 0, p0_off = 0, p1_off = 0;
     int conv_mode = 0;             // k::ConvMode, or 4 = depthwise
+    // Stride-2 stem reading a graph input: run as a stride-1 convolution over the 2x2 space-to-depth image the boundary
+    // conversion writes (4 * Cin channels, pitch 16): a 7x7/2 stem becomes 4 dense K blocks instead of 7 sparse ones.
+    bool s2d = false;
+    int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };
 
 struct Value {

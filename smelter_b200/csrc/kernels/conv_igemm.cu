@@ -736,7 +736,7 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
     const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (S - 1) - 1) / q.stride_w + 1;
     const long M = long(q.n) * std::max(P, 0) * std::max(Q, 0);
     const int m_tiles = int((M + kBlockM - 1) / kBlockM);
-    const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * 8 : q.c_in_pitch;
+    const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * q.c_in_pitch : q.c_in_pitch;
     const int taps = q.mode == CONV_MODE_TILED ? 1 : (q.mode == CONV_MODE_PACKED_ROW ? R : R * S);
     const int num_kb = taps * ((kc + kBlockK - 1) / kBlockK);
     ConvTcPlanInfo best{};
@@ -812,11 +812,11 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     } else if (mode == CONV_MODE_IM2COL) {
         kc = q.c_in_pitch; taps = R * S; taps_w = S;
     } else if (mode == CONV_MODE_PACKED_ROW) {
-        if (q.c_in_pitch != 8 || q.dil_w != 1 || q.pad_t || q.pad_l || q.pad_b || q.pad_r) {
-            if (err) *err = "conv: packed-row mode needs Cin pitch 8, dilation_w 1 and materialised padding";
+        if ((q.c_in_pitch != 8 && q.c_in_pitch != 16) || q.dil_w != 1 || q.pad_t || q.pad_l || q.pad_b || q.pad_r || S * q.c_in_pitch > 256) {
+            if (err) *err = "conv: packed-row mode needs Cin pitch 8 or 16, dilation_w 1 and materialised padding";
             return false;
         }
-        kc = S * 8; taps = R; taps_w = 1;
+        kc = S * q.c_in_pitch; taps = R; taps_w = 1;
     } else {
         if (err) *err = "conv: unknown mode";
         return false;
@@ -927,11 +927,11 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
             // When the last window of a row can read a full 64-element (128-byte) run without leaving the image row, expose
             // 64 "channels": the extra elements are the next pixel's data and meet zero weights (the B box zero-fills past
             // S*8), and the TMA no longer has to zero-fill the tail of every 112-byte row.
-            const long last_window_end = long(Q - 1) * q.stride_w * 8 + kBlockK;
-            const int kc_a = (kc < kBlockK && last_window_end <= long(q.w) * 8) ? kBlockK : kc;
+            const long last_window_end = long(Q - 1) * q.stride_w * q.c_in_pitch + kBlockK;
+            const int kc_a = (kc < kBlockK && last_window_end <= long(q.w) * q.c_in_pitch) ? kBlockK : kc;
             dims[0] = cuuint64_t(kc_a); dims[1] = cuuint64_t(Q); dims[2] = cuuint64_t(q.h); dims[3] = cuuint64_t(q.n);
-            strides[0] = cuuint64_t(q.stride_w) * 16;
-            strides[1] = cuuint64_t(q.w) * 16;
+            strides[0] = cuuint64_t(q.stride_w) * q.c_in_pitch * 2;
+            strides[1] = cuuint64_t(q.w) * q.c_in_pitch * 2;
             strides[2] = strides[1] * q.h;
             lower[0] = 0; lower[1] = 0;
             upper[0] = 0; upper[1] = -(R - 1) * q.dil_h;

@@ -570,7 +570,7 @@ bool conv_mega_prepare(MegaLaunch* out, const std::vector<ConvTcProblem>& layers
         const int Pp = (q.h + q.pad_t + q.pad_b - q.dil_h * (R - 1) - 1) / q.stride_h + 1;
         const int Qq = (q.w + q.pad_l + q.pad_r - q.dil_w * (S - 1) - 1) / q.stride_w + 1;
         const long M = long(q.n) * std::max(Pp, 0) * std::max(Qq, 0);
-        const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * 8 : q.c_in_pitch;
+        const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * q.c_in_pitch : q.c_in_pitch;
         const int taps = q.mode == CONV_MODE_TILED ? 1 : (q.mode == CONV_MODE_PACKED_ROW ? R : R * S);
         q.block_n = conv_mega_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), taps * ((kc + kBlockK - 1) / kBlockK), num_sms);
         q.splits = 1;

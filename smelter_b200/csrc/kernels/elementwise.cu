@@ -217,6 +217,34 @@ __global__ void __launch_bounds__(128) nchw_to_nhwc8_kernel(const __half* __rest
     }
 }
 
+// Network input for a stride-2 stem (Converters.swift:253-256 feeds MPSCNNConvolutionNode the image as is; here the boundary
+// conversion also folds 2x2 pixel blocks into channels and materialises the zero padding).  One thread per destination pixel:
+// 4 * c scalar reads (adjacent threads read adjacent pixel pairs of the same source row), two 128-bit stores.
+__global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c, int h,
+                                                              int w, int pt, int pl, int h2, int w2) {
+    const size_t total = size_t(n) * h2 * w2;
+    const size_t plane = size_t(h) * w;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int x2 = int(i % w2);
+        const int y2 = int((i / w2) % h2);
+        const int img = int(i / (size_t(w2) * h2));
+        const __half* sp = src + size_t(img) * c * plane;
+        Half8 v[2];
+        __half* hv = reinterpret_cast<__half*>(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hv[j] = __float2half(0.f);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int sy = 2 * y2 + (d >> 1) - pt, sx = 2 * x2 + (d & 1) - pl;
+            if (sy >= 0 && sy < h && sx >= 0 && sx < w) {
+                for (int ch = 0; ch < c; ++ch) hv[d * c + ch] = sp[size_t(ch) * plane + size_t(sy) * w + sx];
+            }
+        }
+        st8(dst + i * 16, v[0]);
+        st8(dst + i * 16 + 8, v[1]);
+    }
+}
+
 // One thread per (pixel, 8-channel group), pixel fastest so plane writes are coalesced along W.
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c,
                                                                int hw, int cp, long dst_image_pitch) {
@@ -409,6 +437,11 @@ cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, in
         }
     }
     nchw_to_nhwc_kernel<<<grid_for(size_t(n) * hp * wp), kThreads, 0, s>>>(src, dst, n, c, h, w, cp, pad_t, pad_l, hp, wp);
+    return cudaGetLastError();
+}
+cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s) {
+    if (c < 1 || c > 4) return cudaErrorInvalidValue;
+    nchw_to_s2d_kernel<<<grid_for(size_t(n) * h2 * w2), kThreads, 0, s>>>(src, dst, n, c, h, w, pad_t, pad_l, h2, w2);
     return cudaGetLastError();
 }
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s) {

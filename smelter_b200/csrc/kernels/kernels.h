@@ -21,6 +21,8 @@ enum PadMode : int { PAD_CONSTANT = 0, PAD_REFLECT = 1, PAD_EDGE = 2 };
 enum UpsampleMode : int { UP_NEAREST = 0, UP_BILINEAR = 1 };
 
 // Boundary layout conversion.  dst is [N, H+pt+pb, W+pl+pr, cp] with zero borders and zero padded channels.
+// NCHW (c <= 4) -> zero-padded, 2x2 space-to-depth NHWC with 16-channel pixels: out[n][y][x][(dy*2+dx)*c + ch] = in[n][ch][2y+dy-pad_t][2x+dx-pad_l]
+cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s);
 cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, int w, int cp, int pad_t, int pad_l, int pad_b,
                          int pad_r, cudaStream_t s);
 // dst[n * dst_image_pitch + (c*H + h)*W + w] = src[n,h,w,c]

@@ -439,8 +439,48 @@ cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, in
     nchw_to_nhwc_kernel<<<grid_for(size_t(n) * hp * wp), kThreads, 0, s>>>(src, dst, n, c, h, w, cp, pad_t, pad_l, hp, wp);
     return cudaGetLastError();
 }
+// Row-staged variant: one block per (image, folded row).  The 2 * c source rows it needs are copied into shared memory with
+// coalesced 128-bit loads (source reads are the expensive side: the scalar gather above re-reads every line 4 * c times from
+// L1), then each thread assembles folded pixels from shared memory and writes 32 contiguous bytes.
+__global__ void __launch_bounds__(128) nchw_to_s2d_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int c, int h, int w, int pt,
+                                                              int pl, int h2, int w2) {
+    extern __shared__ __align__(16) __half rows[];  // [2][c][w]
+    const int y2 = blockIdx.x, img = blockIdx.y;
+    const size_t plane = size_t(h) * w;
+    const int vec_per_row = w / 8;
+    for (int i = threadIdx.x; i < 2 * c * vec_per_row; i += blockDim.x) {
+        const int r = i / vec_per_row, vx = i - r * vec_per_row;
+        const int dy = r / c, ch = r - dy * c;
+        const int sy = 2 * y2 + dy - pt;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (sy >= 0 && sy < h) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t(img) * c + ch) * plane + size_t(sy) * w) + vx);
+        reinterpret_cast<uint4*>(rows + size_t(r) * w)[vx] = v;
+    }
+    __syncthreads();
+    __half* drow = dst + (size_t(img) * h2 + y2) * w2 * 16;
+    for (int x2 = threadIdx.x; x2 < w2; x2 += blockDim.x) {
+        Half8 v[2];
+        __half* hv = reinterpret_cast<__half*>(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hv[j] = __float2half(0.f);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int sx = 2 * x2 + (d & 1) - pl;
+            if (sx >= 0 && sx < w)
+                for (int ch = 0; ch < c; ++ch) hv[d * c + ch] = rows[size_t((d >> 1) * c + ch) * w + sx];
+        }
+        st8(drow + size_t(x2) * 16, v[0]);
+        st8(drow + size_t(x2) * 16 + 8, v[1]);
+    }
+}
+
 cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s) {
     if (c < 1 || c > 4) return cudaErrorInvalidValue;
+    const size_t smem = size_t(2) * c * w * sizeof(__half);
+    if (w % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && smem <= 48 * 1024 && n <= 65535) {
+        nchw_to_s2d_rows_kernel<<<dim3(unsigned(h2), unsigned(n)), 128, smem, s>>>(src, dst, c, h, w, pad_t, pad_l, h2, w2);
+        return cudaGetLastError();
+    }
     nchw_to_s2d_kernel<<<grid_for(size_t(n) * h2 * w2), kThreads, 0, s>>>(src, dst, n, c, h, w, pad_t, pad_l, h2, w2);
     return cudaGetLastError();
 }

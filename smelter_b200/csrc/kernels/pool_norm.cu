@@ -111,6 +111,39 @@ __global__ void __launch_bounds__(kThreads) pool2d_kernel(const __half* __restri
     }
 }
 
+// 3x3 max pooling (the ResNet stem pool): nine 128-bit loads in flight per thread, packed half2 maxima (max is exact in fp16,
+// so no conversion is needed; the generic kernel spends more issue slots on cvt than on the compare).
+__global__ void __launch_bounds__(kThreads) pool_max3x3_kernel(const __half* __restrict__ x, __half* __restrict__ y, int h, int w, int cp8, int p, int q,
+                                                              int sh, int sw, int ph, int pw) {
+    const int op = blockIdx.y % p;
+    const int img = blockIdx.y / p;
+    const int row_items = q * cp8;
+    const __half2 neg = __float2half2_rn(-65504.f);
+    for (int it = blockIdx.x * blockDim.x + threadIdx.x; it < row_items; it += gridDim.x * blockDim.x) {
+        const int g = it % cp8;
+        const int oq = it / cp8;
+        Half8 v[9];
+#pragma unroll
+        for (int t = 0; t < 9; ++t) {
+            const int iy = op * sh - ph + t / 3, ix = oq * sw - pw + t % 3;
+            const bool ok = iy >= 0 && iy < h && ix >= 0 && ix < w;
+            if (ok) {
+                v[t] = ld8(x + (((size_t(img) * h + iy) * w + ix) * cp8 + g) * 8);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) v[t].v[j] = neg;
+            }
+        }
+        Half8 m = v[0];
+#pragma unroll
+        for (int t = 1; t < 9; ++t) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) m.v[j] = __hmax2(m.v[j], v[t].v[j]);
+        }
+        st8(y + ((size_t(blockIdx.y) * q + oq) * cp8 + g) * 8, m);
+    }
+}
+
 // ---- global average pool: block = (n, 8-channel group chunk); threads split the pixels, shuffle + smem reduce.
 // grid = (cp8 groups, n); 256 threads over pixels.
 __global__ void __launch_bounds__(kThreads) global_avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int hw, int cp8) {
@@ -363,7 +396,8 @@ cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int 
     if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
     const int row_items = q * (cp / 8);
     dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
-    pool2d_kernel<<<grid, kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
+    if (kh == 3 && kw == 3 && is_max) pool_max3x3_kernel<<<grid, kThreads, 0, s>>>(x, y, h, w, cp / 8, p, q, sh, sw, ph, pw);
+    else pool2d_kernel<<<grid, kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
     return cudaGetLastError();
 }
 

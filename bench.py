@@ -51,6 +51,22 @@ def peaks() -> dict:
     return {"hbm_gbs": 6650.0, "tflops_burst": 1590.0, "tflops_sustained": 1400.0, "source": "fallback"}
 
 
+def ncu_conv_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv kernels of one encode, summed over the launches of a step, from
+    the committed `ncu --set full` capture of this same command (profiles/r1_encode_full.csv; cold-cache replay).  None when the
+    capture is absent."""
+    path = os.path.join(ROOT, "profiles", "r1_encode_full.csv")
+    try:
+        import csv
+        with open(path) as f:
+            rows = list(csv.reader(f))
+        head = rows[0]
+        ir, iw, ik = head.index("dram_read"), head.index("dram_write"), head.index("kernel")
+        return sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_igemm" in r[ik] or "conv_mega" in r[ik])
+    except (OSError, ValueError):
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -60,7 +76,7 @@ class ClockSampler:
         self.rows = []
         self.proc = None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(device)],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "50", "-i", str(device)],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -218,21 +234,34 @@ def run_native(args) -> int:
     copy_stream = torch.cuda.Stream(device=dev)
     dev_in = [Image(ctx, B, *IMAGE), Image(ctx, B, *IMAGE)]
     copied = [torch.cuda.Event(), torch.cuda.Event()]
-    host_out = torch.empty((B, 1000), dtype=torch.float32).pin_memory()
-    out_np = host_out.numpy()
+    host_out = torch.empty((2, B, 1000), dtype=torch.float32).pin_memory()  # double-buffered results
+    out_np = [host_out[0].numpy(), host_out[1].numpy()]
+    landed = [torch.cuda.Event(), torch.cuda.Event()]
+    checksum = [0.0]
 
     def e2e_loop(n_steps: int) -> float:
+        """Every step: H2D of its input batch (copy stream), encode, D2H of its logits into pinned host memory; the host reads
+        step i-1's logits while step i runs (one step of queue depth, like committing the next Metal command buffer before
+        waiting on the previous one), and the last step's logits before the clock stops."""
         t0 = time.perf_counter()
         dev_in[0].copyFromPointer(host_in[0].data_ptr(), n_in, copy_stream.cuda_stream)  # step 0's upload, inside the timed region
         copied[0].record(copy_stream)
         for i in range(n_steps):
             cur, nxt = i % 2, (i + 1) % 2
             if i + 1 < n_steps:  # overlap the next batch's upload with this batch's compute (double-buffered source images)
+                if i > 0:
+                    copy_stream.wait_event(landed[nxt])  # step i-1 read dev_in[nxt]: do not overwrite it before that encode is done
                 dev_in[nxt].copyFromPointer(host_in[(i + 1) % N_INPUT_SETS].data_ptr(), n_in, copy_stream.cuda_stream)
                 copied[nxt].record(copy_stream)
             stream.wait_event(copied[cur])
             res = nn.encode(sourceImages=[dev_in[cur]])
-            res.toFloatArray(out=out_np)  # D2H + stream sync: the step's result is on the host
+            res.toFloatArrayAsync(out_np[cur])   # fp32 logits -> pinned host buffer, enqueued behind the encode
+            landed[cur].record(stream)
+            if i > 0:
+                landed[nxt].synchronize()         # step i-1's logits are on the host: use them
+                checksum[0] += float(out_np[nxt][0, 0])
+        landed[(n_steps - 1) % 2].synchronize()
+        checksum[0] += float(out_np[(n_steps - 1) % 2][0, 0])
         return time.perf_counter() - t0
 
     e2e_loop(W)
@@ -262,7 +291,7 @@ def run_native(args) -> int:
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": None, "kernel": "conv_igemm_kernel<BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
+                "traffic": ncu_conv_traffic(), "kernel": "conv_igemm_kernel<BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
                 "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": share,
                 "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
                 "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,
@@ -286,7 +315,8 @@ def run_native(args) -> int:
                        "cuda_graph": True, "accumulate": "fp32 (TMEM)"},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": n_in * 2, "d2h_bytes_per_step": B * 1000 * 4,
                     "ms_per_step": e2e_s / K * 1e3, "how": "pinned host fp16 batch -> Image.copyFromPointer (copy stream, double-buffered) -> encode -> "
-                    "toFloatArray (fp32 logits on host, stream sync) every step; wall clock"},
+                    "toFloatArrayAsync (fp32 logits into pinned host memory every step; the host consumes step i-1's logits while step i runs, "
+                    "the last step's before the clock stops); wall clock"},
             "gpu_launches": launches, "launches_per_step": nn.numLaunches(B), "clocks": clocks, "roofline": roofline}
     if bcast_ms is not None:
         line["weight_broadcast_ms"] = bcast_ms
@@ -303,7 +333,7 @@ def run_native(args) -> int:
 def main() -> int:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step (the metric is quoted at 32)")

@@ -105,6 +105,10 @@ int32_t smelter_tensor_from_half(smelter_tensor* t, void* cuda_stream, const uin
 /* MPSImage.toFloatArray() (Extensions/Foundation/MPSImage+Extensions.swift:9-59): device fp16 → host fp32,
  * NCHW order (the reference returns MPS slice order).  Synchronises the stream. */
 int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity);
+/* Same, but only enqueues the conversion and the device→host copy on the stream (the Metal analogue: read the image in a
+ * command buffer's completion handler instead of after waitUntilCompleted()).  `host` must stay valid — and should be pinned —
+ * until the stream reaches this point; the tensor may be overwritten by a later encode() on the same stream. */
+int32_t smelter_tensor_to_float_async(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity);
 int32_t smelter_tensor_to_half(const smelter_tensor* t, void* cuda_stream, uint16_t* host, size_t capacity);
 
 /* ---- graph construction --------------------------------------------------------------------------------

@@ -192,6 +192,12 @@ class Image:
         _check(L.lib().smelter_tensor_to_float(self._h, C.c_void_p(stream) if stream else None, out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
+    def toFloatArrayAsync(self, out: np.ndarray, stream: Optional[int] = None) -> np.ndarray:
+        """Enqueue device fp16 -> host fp32 (NCHW) on the stream without waiting: `out` (ideally pinned) holds the values once the
+        stream has passed this point — the analogue of reading an MPSImage in a command buffer's completion handler."""
+        _check(L.lib().smelter_tensor_to_float_async(self._h, C.c_void_p(stream) if stream else None, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
     def toHalfArray(self, stream: Optional[int] = None, out: Optional[np.ndarray] = None) -> np.ndarray:
         if out is None:
             out = np.empty(self.shape, dtype=np.float16)

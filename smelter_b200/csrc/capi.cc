@@ -169,6 +169,17 @@ int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, floa
     SM_CUDA(cudaStreamSynchronize(s));
     return SMELTER_OK;
 }
+int32_t smelter_tensor_to_float_async(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity) {
+    ARG(t && host && capacity >= t->t.count());
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
+    SM_CUDA(cudaSetDevice(t->t.ctx->device));
+    const size_t count = t->t.count();
+    int rc = ensure_staging(count * 4);  // one staging buffer: uses on the same stream are ordered by the stream
+    if (rc) return rc;
+    SM_CUDA(k::f16_to_f32(t->t.ptr, static_cast<float*>(g_staging.ptr), count, s));
+    SM_CUDA(cudaMemcpyAsync(host, g_staging.ptr, count * 4, cudaMemcpyDeviceToHost, s));
+    return SMELTER_OK;
+}
 int32_t smelter_tensor_to_half(const smelter_tensor* t, void* cuda_stream, uint16_t* host, size_t capacity) {
     ARG(t && host && capacity >= t->t.count());
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;

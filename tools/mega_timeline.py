@@ -1,6 +1,7 @@
 """Per-layer timeline of the persistent conv kernel on ResNet-50 batch 32 (instrumented build, no CUDA graph).
-Usage: SMELTER_CONV_INSTRUMENT=1 SMELTER_MEGA_TIMELINE=1 python tools/mega_timeline.py"""
+Usage: SMELTER_CONV_INSTRUMENT=1 python -m smelter_b200.build && SMELTER_CONV_INSTRUMENT=1 SMELTER_MEGA_TIMELINE=1 python tools/mega_timeline.py"""
 import os, sys
+os.environ.setdefault("SMELTER_MEGA", "1")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from smelter_b200 import modelzoo, onnx2mps

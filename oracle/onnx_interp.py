@@ -102,6 +102,25 @@ class Interpreter:
                     x = F.pad(x, (pd[1], pd[3], pd[0], pd[2]))
                     pd = [0, 0, 0, 0]
                 y = F.conv2d(x, w, b, stride=tuple(st), padding=(pd[0], pd[1]), dilation=tuple(dl), groups=grp)
+            elif t == "ConvTranspose":  # Converters.swift:266-287; ONNX weight layout [Cin, Cout, kH, kW]
+                w = self._w(n.input[1])
+                if self.mps:  # ONNX2MPS.py:54-79: [Cout, kH, kW, Cin], spatially flipped -> undo both
+                    w = w.flip(1, 2).permute(3, 0, 1, 2).contiguous()
+                b = self._w(n.input[2]) if len(n.input) > 2 and n.input[2] else None
+                st = a["strides"].ints if "strides" in a else [1, 1]
+                dl = a["dilations"].ints if "dilations" in a else [1, 1]
+                pd = a["pads"].ints if "pads" in a else [0, 0, 0, 0]
+                op_ = a["output_padding"].ints if "output_padding" in a else [0, 0]
+                if pd[0] != pd[2] or pd[1] != pd[3]:
+                    raise NotImplementedError("asymmetric ConvTranspose pads")
+                y = F.conv_transpose2d(x, w, b, stride=tuple(st), padding=(pd[0], pd[1]), output_padding=tuple(op_), dilation=tuple(dl))
+            elif t == "custom_group_norm":  # Converters.swift:1273-1300: X, groups, gamma, beta
+                groups = _ints(host(n.input[1]))[0]
+                eps = a["epsilon"].f if "epsilon" in a else 1e-5
+                y = F.group_norm(x, groups, weight=self._w(n.input[2]), bias=self._w(n.input[3]), eps=eps)
+            elif t == "Pow":
+                e = float(host(n.input[1]).reshape(-1)[0]) if len(n.input) > 1 and n.input[1] else 1.0
+                y = torch.pow(x, e)
             elif t == "Gemm":
                 w = self._w(n.input[1])
                 alpha = a["alpha"].f if "alpha" in a else 1.0

@@ -39,6 +39,7 @@ int convert_conv(ONNXGraph& g, int ni) {
     const TensorProto* bias = node.input.size() > 2 ? g.tensor(node.input[2]) : nullptr;            // :196-199
 
     const bool is_gemm = node.op_type == "Gemm";
+    const bool is_transpose = node.op_type == "ConvTranspose";  // :266-287
     bool have_k = false, have_d = false, have_s = false;
     Filter f;
     f.kind = FilterKind::Conv;
@@ -54,6 +55,7 @@ int convert_conv(ONNXGraph& g, int ni) {
         else if (a.name == "pads" && a.ints.size() >= 4) { for (int i = 0; i < 4; ++i) f.pads[i] = int(a.ints[size_t(i)]); }
         else if (a.name == "kernel_shape" && a.ints.size() >= 2) { f.k_h = int(a.ints[0]); f.k_w = int(a.ints[1]); have_k = true; }
         else if (a.name == "auto_pad") auto_pad = std::string(a.s);
+        else if (a.name == "output_padding" && a.ints.size() >= 2) { f.out_pad_h = int(a.ints[0]); f.out_pad_w = int(a.ints[1]); }  // :220-221
         else if (a.name == "alpha") alpha = a.f;
         else if (a.name == "beta") beta = a.f;
         else if (a.name == "transA") trans_a = int(a.i);
@@ -87,6 +89,7 @@ int convert_conv(ONNXGraph& g, int ni) {
         if (weight->dims.size() != 4) return err(SMELTER_ERR_UNSUPPORTED, node, "Conv weight must be rank 4 (2-D convolution)");
         int o, i, kh, kw;
         if (mps) { o = int(weight->dims[0]); kh = int(weight->dims[1]); kw = int(weight->dims[2]); i = int(weight->dims[3]); }  // :40-44
+        else if (is_transpose) { i = int(weight->dims[0]); o = int(weight->dims[1]); kh = int(weight->dims[2]); kw = int(weight->dims[3]); }  // :48-50
         else { o = int(weight->dims[0]); i = int(weight->dims[1]); kh = int(weight->dims[2]); kw = int(weight->dims[3]); }      // :46-54
         if (kh != f.k_h || kw != f.k_w) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "kernel_shape disagrees with the weight dims");
         if (size_t(o) * i * kh * kw != wv.size()) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "weight size mismatch");
@@ -94,7 +97,7 @@ int convert_conv(ONNXGraph& g, int ni) {
         if (mps) f.w = std::move(wv);  // already OHWI (ONNX2MPS.py:75), the reference skips the re-layout too (:91)
         else {
             f.w.resize(wv.size());
-            reformat_conv_weight(wv.data(), f.w.data(), 4, o, i, kh, kw, false);  // :94-120
+            reformat_conv_weight(wv.data(), f.w.data(), 4, o, i, kh, kw, is_transpose);  // :94-120 (ConvTranspose: IOHW -> OHWI + 180 degree flip)
         }
     }
     if (in_shape->c != f.c_in_g * f.groups) {
@@ -106,6 +109,25 @@ int convert_conv(ONNXGraph& g, int ni) {
         std::vector<float> bv;
         if (!weight_floats(*bias, &bv) || int(bv.size()) != f.c_out) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "bias must be FLOAT/FLOAT16 of length Cout");
         for (int i = 0; i < f.c_out; ++i) f.bias[size_t(i)] = bv[size_t(i)] * (is_gemm ? beta : 1.f);
+    }
+    if (is_transpose) {
+        // executed as a stride-1 convolution over the zero-stuffed input (engine.cc); ONNX output size incl. dilation and output_padding
+        if (f.groups != 1) return err(SMELTER_ERR_UNSUPPORTED, node, "grouped ConvTranspose");
+        if (auto_pad != "NOTSET" && auto_pad != "VALID") return err(SMELTER_ERR_UNSUPPORTED, node, "ConvTranspose auto_pad");
+        const int lo_h = f.dil_h * (f.k_h - 1) - f.pads[0], hi_h = f.dil_h * (f.k_h - 1) - f.pads[2] + f.out_pad_h;
+        const int lo_w = f.dil_w * (f.k_w - 1) - f.pads[1], hi_w = f.dil_w * (f.k_w - 1) - f.pads[3] + f.out_pad_w;
+        if (lo_h < 0 || hi_h < 0 || lo_w < 0 || hi_w < 0) return err(SMELTER_ERR_UNSUPPORTED, node, "ConvTranspose pads larger than the dilated kernel");
+        ImageShape out;
+        out.c = f.c_out;
+        out.h = conv_output_size(in_shape->h, f.k_h, f.stride_h, f.dil_h, f.pads[0], f.pads[2], f.out_pad_h, true);  // ONNXConvolutionPadding.swift:97-103
+        out.w = conv_output_size(in_shape->w, f.k_w, f.stride_w, f.dil_w, f.pads[1], f.pads[3], f.out_pad_w, true);
+        if (out.h <= 0 || out.w <= 0) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "empty output");
+        f.transposed = true;
+        f.tr_stride_h = f.stride_h; f.tr_stride_w = f.stride_w;
+        f.stride_h = f.stride_w = 1;  // the convolution that actually runs
+        f.pads[0] = lo_h; f.pads[1] = lo_w; f.pads[2] = hi_h; f.pads[3] = hi_w;  // border of the stuffed image
+        f.in = {input};
+        return g.addFilter(std::move(f), out, node.output);
     }
     if (!is_gemm && auto_pad != "NOTSET" && auto_pad != "VALID") {
         // reference ignores auto_pad; ONNX semantics honoured for SAME_*
@@ -383,6 +405,46 @@ int convert_instancenorm(ONNXGraph& g, int ni) {
     return g.addFilter(std::move(f), *s, node.output);
 }
 
+// ---- custom_group_norm: GroupNormConverter, Converters.swift:1273-1300 — inputs X, groups (int tensor), gamma, beta ----------
+// (the op the reference's own exporter emits for torch.nn.GroupNorm; MPSCNNGroupNormalizationNode, epsilon = MPS default)
+int convert_groupnorm(ONNXGraph& g, int ni) {
+    const NodeProto& node = g.node(ni);
+    const int input = node.input.empty() ? -1 : g.output(node.input[0]);
+    const ImageShape* s = node.input.empty() ? nullptr : g.shape(node.input[0]);
+    const TensorProto* groups = node.input.size() >= 4 ? g.tensor(node.input[1]) : nullptr;
+    const TensorProto* gamma = node.input.size() >= 4 ? g.tensor(node.input[2]) : nullptr;
+    const TensorProto* beta = node.input.size() >= 4 ? g.tensor(node.input[3]) : nullptr;
+    Filter f;
+    std::vector<int64_t> gi;
+    if (input < 0 || !s || !groups || !gamma || !beta || !groups->integers(&gi) || gi.empty() || !gamma->floats(&f.p0) || !beta->floats(&f.p1))
+        return err(SMELTER_ERR_NO_SUCH_OUTPUT, node, "needs an image input and groups/gamma/beta initializers");  // :1275-1281
+    const int ng = int(gi[0]);
+    if (int(f.p0.size()) != s->c || int(f.p1.size()) != s->c) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "gamma/beta length != channels");
+    if (ng < 1 || s->c % ng != 0) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "channels must be divisible by groups");
+    f.kind = FilterKind::InstanceNorm;
+    f.op_type = node.op_type;
+    f.sub = s->c / ng;  // channels per group (InstanceNormalization leaves this 0 = one channel per group)
+    f.eps = 1e-5f;
+    if (const AttributeProto* a = node.attr("epsilon")) f.eps = a->f;
+    f.in = {input};
+    return g.addFilter(std::move(f), *s, node.output);
+}
+
+// ---- Pow: PowConverter, Converters.swift:1160-1175 ------------------------------------------------------------------------
+// The reference builds MPSCNNNeuronPowerNode with its default parameters and never reads the exponent.  Here the
+// ONNX meaning: the exponent must be a one-element initializer (no tensor-valued exponents on an image path).
+int convert_pow(ONNXGraph& g, int ni) {
+    const NodeProto& node = g.node(ni);
+    float e = 1.f;
+    if (node.input.size() >= 2) {
+        const TensorProto* t = g.tensor(node.input[1]);
+        std::vector<float> v;
+        if (!t || !t->floats(&v) || v.size() != 1) return err(SMELTER_ERR_UNSUPPORTED, node, "exponent must be a one-element initializer");
+        e = v[0];
+    }
+    return add_unary(g, node, k::UN_POW, e, 0);
+}
+
 // ---- Reshape / Flatten: Converters.swift:830-915 -------------------------------------------------------------------
 // Reference reads shape[0..2] as (W,H,C) and has no batch axis.  Here: ONNX semantics on NCHW
 // with the batch axis carried implicitly — the target must keep dim 0 (N, 0 or -1 resolving to N).
@@ -480,8 +542,8 @@ int convert_pad(ONNXGraph& g, int ni) {
 
 }  // namespace
 
-// ONNXGraph.swift:110-155.  Not registered (=> unknownNodeOpType, exactly like an op the reference lacks):
-// ConvTranspose, Pow, custom_group_norm — outside SURVEY §8's scope ("next", §8f N3).
+// ONNXGraph.swift:110-155: all 36 entries of the reference's registry, plus Clip and Identity.  Anything else is
+// unknownNodeOpType, exactly like an op the reference lacks.
 void ONNXGraph::registerBuiltins() {
     registerConverter("Conv", convert_conv);
     registerConverter("Gemm", convert_conv);
@@ -509,6 +571,9 @@ void ONNXGraph::registerBuiltins() {
     registerConverter("BatchNormalization", convert_batchnorm);
     registerConverter("Dropout", convert_identity);
     registerConverter("InstanceNormalization", convert_instancenorm);
+    registerConverter("custom_group_norm", convert_groupnorm);
+    registerConverter("Pow", convert_pow);
+    registerConverter("ConvTranspose", convert_conv);
     registerConverter("Log", convert_log);
     registerConverter("Exp", convert_exp);
     registerConverter("Reshape", convert_reshape);

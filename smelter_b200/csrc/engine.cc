@@ -324,6 +324,7 @@ int ONNXGraph::build() {
     for (auto& f : filters_) {
         if (f.removed || f.kind != FilterKind::Conv) continue;
         f.conv_mode = pick_conv_mode(f.c_in_g * f.groups, f.c_out, f.groups, f.k_h, f.k_w, f.stride_h, f.stride_w, f.dil_w, f.pads);
+        if (f.transposed) f.conv_mode = (f.k_h == 1 && f.k_w == 1) ? k::CONV_MODE_TILED : k::CONV_MODE_IM2COL;  // reads a materialised image
         if (f.conv_mode < 0)
             return fail(SMELTER_ERR_UNSUPPORTED, "grouped convolution other than depthwise (groups=" + std::to_string(f.groups) + ")");
     }
@@ -489,7 +490,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         q.k_h = f.k_h; q.k_w = f.k_w; q.stride_h = f.stride_h; q.stride_w = f.stride_w; q.dil_h = f.dil_h; q.dil_w = f.dil_w;
         q.pad_t = f.pads[0]; q.pad_l = f.pads[1]; q.pad_b = f.pads[2]; q.pad_r = f.pads[3];
         q.act = f.act; q.clip_lo = f.clip_lo; q.clip_hi = f.clip_hi;
-        if (f.s2d) {  // stride-1 convolution over the folded image the boundary conversion writes
+        if (f.transposed) {  // stride-1 convolution over the zero-stuffed, bordered image
+            q.h = (is.h - 1) * f.tr_stride_h + 1 + f.pads[0] + f.pads[2];
+            q.w = (is.w - 1) * f.tr_stride_w + 1 + f.pads[1] + f.pads[3];
+            q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.s2d) {  // stride-1 convolution over the folded image the boundary conversion writes
             q.h = f.s2d_h / 2; q.w = f.s2d_w / 2;
             q.c_in_pitch = 16;
             q.k_h = (f.k_h + 1) / 2; q.k_w = (f.k_w + 1) / 2;
@@ -546,7 +551,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         for (size_t fi = 0; fi < filters_.size(); ++fi) {
             const Filter& f = filters_[fi];
             if (f.removed) continue;
-            bool ok = f.kind == FilterKind::Conv && f.conv_mode != 4 && !f.is_gemm;
+            bool ok = f.kind == FilterKind::Conv && f.conv_mode != 4 && !f.is_gemm && !f.transposed;
             if (ok && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) &&
                 stem_of[size_t(root_of(f.in[0]))] != &f)
                 ok = false;  // needs its own pad pass in front
@@ -576,6 +581,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             stem_of[size_t(root_of(f.in[0]))] != &f) {
             const ImageShape& s = values_[size_t(f.in[0])].shape;
             scratch[fi].bytes = size_t(N) * (s.h + f.pads[0] + f.pads[2]) * (s.w + f.pads[1] + f.pads[3]) * 8 * 2;
+            scratch[fi].off = arena.alloc(scratch[fi].bytes);
+        }
+        if (f.kind == FilterKind::Conv && f.transposed) {
+            const k::ConvTcProblem tq = conv_problem(f, stem_of);
+            scratch[fi].bytes = size_t(N) * tq.h * tq.w * tq.c_in_pitch * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
         if (f.kind == FilterKind::Conv && f.conv_mode != 4) {
@@ -693,7 +703,8 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 const __half* res = f.residual >= 0 ? ptr_of(f.residual) : nullptr;
                 std::string suffix = f.act == k::ACT_RELU ? "+relu" : f.act == k::ACT_CLIP ? "+clip" : f.act == k::ACT_SIGMOID ? "+sigmoid" : "";
                 if (res) suffix = "+add" + suffix;
-                const double flops = 2.0 * N * osz.h * osz.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w;
+                const double flops = f.transposed ? 2.0 * N * is.h * is.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w
+                                                  : 2.0 * N * osz.h * osz.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w;
                 if (f.conv_mode == 4) {
                     const Filter* fp = &f;
                     add_step("depthwise" + suffix + " " + name, [=](cudaStream_t st) {
@@ -708,7 +719,15 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                     q.split_ws = reinterpret_cast<float*>(abase + scratch2[fi].off);
                     q.split_counters = reinterpret_cast<unsigned int*>(static_cast<char*>(plan->counters) + counter_off[fi]);
                 }
-                if (f.conv_mode == k::CONV_MODE_PACKED_ROW && stem_of[size_t(root_of(f.in[0]))] == &f) {
+                if (f.transposed) {
+                    __half* stuffed = reinterpret_cast<__half*>(abase + scratch[fi].off);
+                    const Filter* fp = &f;
+                    const int hz = q.h, wz = q.w;
+                    add_step("zero_stuff " + name, [=](cudaStream_t st) {
+                        return k::zero_stuff2d(x, stuffed, N, is.h, is.w, icp, hz, wz, fp->tr_stride_h, fp->tr_stride_w, fp->pads[0], fp->pads[1], st);
+                    }, 0, double(scratch[fi].bytes) + double(N) * is.h * is.w * icp * 2);
+                    q.x = stuffed;
+                } else if (f.conv_mode == k::CONV_MODE_PACKED_ROW && stem_of[size_t(root_of(f.in[0]))] == &f) {
                     // the boundary conversion already wrote the padded image into this conv's input buffer
                 } else if (f.conv_mode == k::CONV_MODE_PACKED_ROW && scratch[fi].off != size_t(-1)) {
                     // materialise the zero padding so one K block can span a whole filter row
@@ -779,7 +798,9 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 float* partials = reinterpret_cast<float*>(abase + scratch[fi].off);
                 const int act = f.act;
                 const float eps = f.eps;
-                add_step("instance_norm " + name, [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st); }, 0,
+                const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c;
+                add_step(std::string(group_size > 1 ? "group_norm " : "instance_norm ") + name,
+                         [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels); }, 0,
                          io_bytes + double(N) * is.h * is.w * icp * 2);
                 plan->steps.back().launches = 2;
                 break;

@@ -95,6 +95,10 @@ struct Filter {
     int conv_mode = 0;             // k::ConvMode, or 4 = depthwise
     // Stride-2 stem reading a graph input: run as a stride-1 convolution over the 2x2 space-to-depth image the boundary
     // conversion writes (4 * Cin channels, pitch 16): a 7x7/2 stem becomes 4 dense K blocks instead of 7 sparse ones.
+    // ConvTranspose (Converters.swift:266-287): run as a stride-1 convolution with the 180-degree-flipped filter over the input with
+    // stride-1 zeros inserted between pixels and a (k-1)*d - pad border (weights are already flipped, reformat_conv_weight).
+    bool transposed = false;
+    int tr_stride_h = 1, tr_stride_w = 1, out_pad_h = 0, out_pad_w = 0;
     bool s2d = false;
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };

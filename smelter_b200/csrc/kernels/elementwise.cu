@@ -69,6 +69,7 @@ __device__ __forceinline__ float unary_op(float x, int kind, float a, float b) {
         case UN_HARD_SIGMOID: return fminf(fmaxf(a * x + b, 0.f), 1.f);
         case UN_SOFTPLUS: return x > 20.f ? x : log1pf(__expf(x));
         case UN_SOFTSIGN: return x / (1.f + fabsf(x));
+        case UN_POW: return powf(x, a);
         default: return x;
     }
 }
@@ -242,6 +243,26 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const __half* __r
         }
         st8(dst + i * 16, v[0]);
         st8(dst + i * 16 + 8, v[1]);
+    }
+}
+
+// ConvTranspose = stride-1 convolution over the zero-stuffed, bordered input (MPSCNNConvolutionTransposeNode's job, Converters.swift
+// :266-287).  One thread per destination (pixel, 8 channels): copies the source vector when the pixel sits on the stride lattice.
+__global__ void __launch_bounds__(kThreads) zero_stuff2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
+                                                               int hz, int wz, int sh, int sw, int lo_h, int lo_w) {
+    const size_t total = size_t(n) * hz * wz * cp8;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int g = int(i % cp8);
+        const size_t pix = i / cp8;
+        const int xx = int(pix % wz) - lo_w;
+        const int yy = int((pix / wz) % hz) - lo_h;
+        const int img = int(pix / (size_t(wz) * hz));
+        Half8 v;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) v.v[j] = __float2half2_rn(0.f);
+        if (yy >= 0 && xx >= 0 && yy % sh == 0 && xx % sw == 0 && yy / sh < h && xx / sw < w)
+            v = ld8(x + ((size_t(img) * h + yy / sh) * w + xx / sw) * cp8 * 8 + g * 8);
+        st8(y + i * 8, v);
     }
 }
 
@@ -482,6 +503,11 @@ cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int
         return cudaGetLastError();
     }
     nchw_to_s2d_kernel<<<grid_for(size_t(n) * h2 * w2), kThreads, 0, s>>>(src, dst, n, c, h, w, pad_t, pad_l, h2, w2);
+    return cudaGetLastError();
+}
+cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
+                         cudaStream_t s) {
+    zero_stuff2d_kernel<<<grid_for(size_t(n) * hz * wz * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, hz, wz, stride_h, stride_w, lo_h, lo_w);
     return cudaGetLastError();
 }
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s) {

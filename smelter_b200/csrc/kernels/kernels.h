@@ -14,7 +14,7 @@ namespace k {
 
 enum UnaryKind : int {
     UN_RELU = 0, UN_SIGMOID = 1, UN_CLIP = 2, UN_TANH = 3, UN_ABS = 4, UN_EXP = 5, UN_LOG = 6, UN_ELU = 7,
-    UN_LEAKY_RELU = 8, UN_HARD_SIGMOID = 9, UN_SOFTPLUS = 10, UN_SOFTSIGN = 11, UN_IDENTITY = 12
+    UN_LEAKY_RELU = 8, UN_HARD_SIGMOID = 9, UN_SOFTPLUS = 10, UN_SOFTSIGN = 11, UN_IDENTITY = 12, UN_POW = 13
 };
 enum BinaryKind : int { BIN_ADD = 0, BIN_SUB = 1, BIN_MUL = 2, BIN_DIV = 3 };
 enum PadMode : int { PAD_CONSTANT = 0, PAD_REFLECT = 1, PAD_EDGE = 2 };
@@ -28,6 +28,9 @@ cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, in
 // dst[n * dst_image_pitch + (c*H + h)*W + w] = src[n,h,w,c]
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s);
 
+// ConvTranspose input: y[n][lo_h + s_h*i][lo_w + s_w*j][c] = x[n][i][j][c], zero elsewhere; y is [n][hz][wz][cp]
+cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
+                         cudaStream_t s);
 cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s);
 cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s);
 // y = act(x * scale[c] + shift[c])  (un-fused BatchNormalization)
@@ -43,8 +46,9 @@ cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int p
                   cudaStream_t s);
 // Instance normalisation: deterministic two-kernel scheme.  `partials` holds n * splits * cp * 2 floats.
 int instance_norm_splits(int hw, int cp);
+// group_size = channels that share one mean / variance: 1 = InstanceNormalization, C / groups = group normalisation
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
-                          int act, float* partials, cudaStream_t s);
+                          int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0);
 // copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s);

@@ -319,18 +319,25 @@ __global__ void __launch_bounds__(kThreads) inorm_stats_kernel(const __half* __r
 // pass 2: y = act((x - mean) * rstd * gamma + beta); block (chunk, image) recomputes the tiny reduction into smem.
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y,
                                                               const float* __restrict__ partials, const float* __restrict__ gamma,
-                                                              const float* __restrict__ beta, int hw, int cp8, int splits, float eps, int act) {
+                                                              const float* __restrict__ beta, int hw, int cp8, int splits, float eps, int act,
+                                                              int group_size, int channels) {
     extern __shared__ float sm[];  // [cp][2] scale, shift
     const int img = blockIdx.y;
     const int cp = cp8 * 8;
     for (int ch = threadIdx.x; ch < cp; ch += blockDim.x) {
         double a = 0.0, b = 0.0;
-        for (int sp = 0; sp < splits; ++sp) {
-            const float* o = partials + ((size_t(img) * splits + sp) * cp + ch) * 2;
-            a += o[0]; b += o[1];
-        }
-        const double mean = a / hw;
-        double var = b / hw - mean * mean;
+        // statistics are shared by the `group_size` channels of ch's group (custom_group_norm, Converters.swift:1273-1300);
+        // group_size == 1 is InstanceNormalization
+        const int c_lo = ch < channels ? (ch / group_size) * group_size : ch;
+        const int c_hi = ch < channels ? min(c_lo + group_size, channels) : ch + 1;
+        for (int cc = c_lo; cc < c_hi; ++cc)
+            for (int sp = 0; sp < splits; ++sp) {
+                const float* o = partials + ((size_t(img) * splits + sp) * cp + cc) * 2;
+                a += o[0]; b += o[1];
+            }
+        const double cnt = double(hw) * (c_hi - c_lo);
+        const double mean = a / cnt;
+        double var = b / cnt - mean * mean;
         if (var < 0.0) var = 0.0;
         const float rstd = float(1.0 / sqrt(var + double(eps)));
         const float sc = rstd * gamma[ch];
@@ -470,7 +477,9 @@ int instance_norm_splits(int hw, int cp) {
 }
 
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                          float* partials, cudaStream_t s) {
+                          float* partials, cudaStream_t s, int group_size, int channels) {
+    if (group_size < 1) group_size = 1;
+    if (channels <= 0) channels = cp;
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
     const int splits = instance_norm_splits(hw, cp);
@@ -485,7 +494,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
     const int cap = (kSMs * 8 + n - 1) / n;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
-    inorm_apply_kernel<<<dim3(chunks, n), kThreads, size_t(cp) * 2 * sizeof(float), s>>>(x, y, partials, gamma, beta, hw, cp8, splits, eps, act);
+    inorm_apply_kernel<<<dim3(chunks, n), kThreads, size_t(cp) * 2 * sizeof(float), s>>>(x, y, partials, gamma, beta, hw, cp8, splits, eps, act, group_size, channels);
     return cudaGetLastError();
 }
 

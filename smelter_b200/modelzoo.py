@@ -67,6 +67,26 @@ class GraphBuilder:
         return self._node("Conv", ins, {"dilations": [dilation, dilation], "group": groups, "kernel_shape": [k, k],
                                        "pads": [pad, pad, pad, pad], "strides": [stride, stride]}, c_out)
 
+    def conv_transpose(self, x: str, c_out: int, k: int, stride: int = 1, pad: int = 0, output_padding: int = 0, bias: bool = True) -> str:
+        c_in = self.channels[x]
+        w = self.rng.standard_normal((c_in, c_out, k, k)).astype(np.float32) * np.float32(np.sqrt(2.0 * stride * stride / (c_in * k * k)))
+        ins = [x, self._init("wt", w)]
+        if bias:
+            ins.append(self._init("b", (self.rng.standard_normal(c_out) * 0.1).astype(np.float32)))
+        return self._node("ConvTranspose", ins, {"dilations": [1, 1], "group": 1, "kernel_shape": [k, k], "pads": [pad, pad, pad, pad],
+                                                "strides": [stride, stride], "output_padding": [output_padding, output_padding]}, c_out)
+
+    def group_norm(self, x: str, groups: int) -> str:
+        """`custom_group_norm` as the reference's exporter emits it: X, groups, gamma, beta (Converters.swift:1273-1300)."""
+        c = self.channels[x]
+        gamma = self.rng.uniform(0.5, 1.5, c).astype(np.float32)
+        beta = (self.rng.standard_normal(c) * 0.1).astype(np.float32)
+        return self._node("custom_group_norm", [x, self._init("groups", np.asarray([groups], dtype=np.int64)), self._init("gamma", gamma),
+                                                self._init("beta", beta)], {}, c)
+
+    def pow(self, x: str, exponent: float) -> str:
+        return self._node("Pow", [x, self._init("exponent", np.asarray([exponent], dtype=np.float32))], {}, self.channels[x])
+
     def _bn_params(self, c: int, gamma_scale: float = 1.0):
         gamma = (self.rng.uniform(0.5, 1.5, c) * gamma_scale).astype(np.float32)
         beta = (self.rng.standard_normal(c) * 0.1).astype(np.float32)
@@ -251,6 +271,18 @@ def synthetic_ops(seed: int = 0, hw: int = 12, c: int = 16) -> op.Model:
     y = g.reshape(y, [-1, 10, 1, 1], 10)
     y = g.softmax(y)
     g.output(y, [1, 10, 1, 1])
+    return g.model()
+
+
+def decoder_ops(seed: int = 0, hw: int = 10, c: int = 32) -> op.Model:
+    """ConvTranspose / custom_group_norm / Pow: the registry entries (ONNXGraph.swift:116,143,154) no BASELINE model uses."""
+    g = GraphBuilder(seed, name="decoder_ops")
+    x = g.input("input", [1, c, hw, hw])
+    y = g.relu(g.group_norm(g.conv(x, 64, 3, 1, 1), 8))
+    y = g.relu(g.conv_transpose(y, 48, 3, stride=2, pad=1, output_padding=1))   # hw -> 2 hw
+    y = g.pow(g.sigmoid(g.conv_transpose(y, 24, 4, stride=2, pad=1)), 2.0)      # 2 hw -> 4 hw
+    y = g.conv_transpose(y, 8, 1, stride=1, pad=0)                              # 1x1: the tiled path
+    g.output(y, [1, 8, 4 * hw, 4 * hw])
     return g.model()
 
 

@@ -39,6 +39,15 @@ def infer_shapes(model: op.Model, inputs: Dict[str, Tuple[int, ...]]) -> Dict[st
             dl = a["dilations"].ints if "dilations" in a else [1, 1]
             pd = a["pads"].ints if "pads" in a else [0, 0, 0, 0]
             shapes[n.output[0]] = (x[0], co, conv_out(x[2], kh, st[0], dl[0], pd[0], pd[2]), conv_out(x[3], kw, st[1], dl[1], pd[1], pd[3]))
+        elif t == "ConvTranspose":
+            w = inits[n.input[1]].dims
+            co, kh, kw = (w[0], w[1], w[2]) if mps else (w[1], w[2], w[3])
+            st = a["strides"].ints if "strides" in a else [1, 1]
+            dl = a["dilations"].ints if "dilations" in a else [1, 1]
+            pd = a["pads"].ints if "pads" in a else [0, 0, 0, 0]
+            opd = a["output_padding"].ints if "output_padding" in a else [0, 0]
+            shapes[n.output[0]] = (x[0], co, (x[2] - 1) * st[0] - pd[0] - pd[2] + dl[0] * (kh - 1) + 1 + opd[0],
+                                   (x[3] - 1) * st[1] - pd[1] - pd[3] + dl[1] * (kw - 1) + 1 + opd[1])
         elif t == "Gemm":
             w = inits[n.input[1]].dims
             trans_b = a["transB"].i if "transB" in a else 0

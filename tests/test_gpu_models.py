@@ -164,6 +164,23 @@ def test_transformer_net_256(ctx):
     assert np.abs(out - want).mean() <= 2e-3
 
 
+@pytest.mark.parametrize("half", [False, True], ids=["onnx", "onnx2mps-half"])
+def test_conv_transpose_group_norm_pow(ctx, half):
+    """The registry entries no BASELINE model uses (ONNXGraph.swift:116,143,154): ConvTranspose (3x3/2 with output_padding,
+    4x4/2, 1x1) as a stride-1 convolution over the zero-stuffed input with the flipped filter, custom_group_norm, Pow — as plain
+    ONNX and through the ONNX2MPS weight swizzle ([1,2,3,0] + 180 degree flip, ONNX2MPS.py:54-79)."""
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = modelzoo.decoder_ops(seed=3).serialize()
+    if half:
+        model = onnx2mps.convert_bytes(model, half=True)
+    x = np.random.default_rng(4).standard_normal((3, 32, 10, 10)).astype(np.float16)
+    out, _ = _run(ctx, model, x)
+    want = _oracle(model, x)
+    assert out.shape == (3, 8, 40, 40)
+    assert np.abs(out - want).max() <= TOL
+
+
 def test_batch_override_through_configuration_dims(ctx):
     """Configuration.dims overrides input dims by axis (ONNXGraph.swift:200-202); spatial override re-plans shapes."""
     from smelter_b200 import modelzoo

@@ -102,6 +102,11 @@ int32_t smelter_tensor_device_ptr(const smelter_tensor* t, void** ptr);
  * `host` should be pinned for true asynchrony). */
 int32_t smelter_tensor_from_float(smelter_tensor* t, void* cuda_stream, const float* host, size_t count);
 int32_t smelter_tensor_from_half(smelter_tensor* t, void* cuda_stream, const uint16_t* host, size_t count);
+/* The step in front of the path in real use (README.md:33-39, `MTLContext.texture(from: CGImage)`): interleaved 8-bit pixels
+ * [N][H][W][src_channels] (RGB, RGBA, grey ...) -> device fp16 NCHW, value = byte * scale[c] + bias[c] for the tensor's first
+ * C <= src_channels channels (scale / bias: C floats each, NULL = 1/255 and 0).  Asynchronous on `cuda_stream`. */
+int32_t smelter_tensor_from_u8(smelter_tensor* t, void* cuda_stream, const uint8_t* host, int32_t src_channels, const float* scale,
+                               const float* bias);
 /* MPSImage.toFloatArray() (Extensions/Foundation/MPSImage+Extensions.swift:9-59): device fp16 → host fp32,
  * NCHW order (the reference returns MPS slice order).  Synchronises the stream. */
 int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity);

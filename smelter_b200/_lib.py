@@ -64,6 +64,7 @@ SIGNATURES = {
     "smelter_tensor_device_ptr": (i32, [vp, P(vp)]),
     "smelter_tensor_from_float": (i32, [vp, vp, vp, sz]),
     "smelter_tensor_from_half": (i32, [vp, vp, vp, sz]),
+    "smelter_tensor_from_u8": (i32, [vp, vp, vp, i32, vp, vp]),
     "smelter_tensor_to_float": (i32, [vp, vp, vp, sz]),
     "smelter_tensor_to_float_async": (i32, [vp, vp, vp, sz]),
     "smelter_tensor_to_half": (i32, [vp, vp, vp, sz]),

@@ -159,6 +159,22 @@ class Image:
         return img
 
     @staticmethod
+    def fromBytes(context: Context, pixels: np.ndarray, channels: int = 3, scale: Optional[Sequence[float]] = None,
+                  bias: Optional[Sequence[float]] = None, stream: Optional[int] = None) -> "Image":
+        """`MTLContext.texture(from:)` analogue (README.md:33-39): interleaved uint8 pixels [N,H,W,S] or [H,W,S] (RGB, RGBA ...)
+        -> device fp16 [N,channels,H,W] with value = byte * scale[c] + bias[c] (default 1/255, 0)."""
+        a = np.ascontiguousarray(pixels, dtype=np.uint8)
+        if a.ndim == 3:
+            a = a[None]
+        n, h, w, s = a.shape
+        img = Image(context, n, channels, h, w)
+        sc = (C.c_float * channels)(*scale) if scale is not None else None
+        bi = (C.c_float * channels)(*bias) if bias is not None else None
+        _check(L.lib().smelter_tensor_from_u8(img._h, C.c_void_p(stream) if stream else None, a.ctypes.data_as(C.c_void_p), s, sc, bi))
+        context.synchronize()  # `a` may be a temporary
+        return img
+
+    @staticmethod
     def wrap(context: Context, device_ptr: int, n: int, c: int, h: int, w: int) -> "Image":
         h_ = C.c_void_p()
         _check(L.lib().smelter_tensor_wrap(context._h, C.c_void_p(device_ptr), n, c, h, w, C.byref(h_)))

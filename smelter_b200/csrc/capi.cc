@@ -157,6 +157,19 @@ int32_t smelter_tensor_from_half(smelter_tensor* t, void* cuda_stream, const uin
     SM_CUDA(cudaMemcpyAsync(t->t.ptr, host, count * 2, cudaMemcpyHostToDevice, s));
     return SMELTER_OK;
 }
+int32_t smelter_tensor_from_u8(smelter_tensor* t, void* cuda_stream, const uint8_t* host, int32_t src_channels, const float* scale, const float* bias) {
+    ARG(t && host && t->t.c >= 1 && t->t.c <= 4 && src_channels >= t->t.c && src_channels <= 4);
+    cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
+    SM_CUDA(cudaSetDevice(t->t.ctx->device));
+    const size_t hw = size_t(t->t.h) * t->t.w, bytes = size_t(t->t.n) * hw * src_channels;
+    int rc = ensure_staging(bytes);
+    if (rc) return rc;
+    float sc4[4], b4[4];
+    for (int i = 0; i < 4; ++i) { sc4[i] = scale && i < t->t.c ? scale[i] : 1.f / 255.f; b4[i] = bias && i < t->t.c ? bias[i] : 0.f; }
+    SM_CUDA(cudaMemcpyAsync(g_staging.ptr, host, bytes, cudaMemcpyHostToDevice, s));
+    SM_CUDA(k::u8_to_nchw_f16(static_cast<const uint8_t*>(g_staging.ptr), t->t.ptr, t->t.n, t->t.c, hw, src_channels, sc4, b4, s));
+    return SMELTER_OK;
+}
 int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity) {
     ARG(t && host && capacity >= t->t.count());
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;

@@ -542,6 +542,25 @@ cudaError_t f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s) 
     f32_to_f16_kernel<<<grid_for(n), kThreads, 0, s>>>(src, dst, n);
     return cudaGetLastError();
 }
+namespace {
+struct U8Params { float scale[4], bias[4]; };
+__global__ void __launch_bounds__(kThreads) u8_to_nchw_kernel(const uint8_t* __restrict__ src, __half* __restrict__ dst, int n, int c, size_t hw, int sc,
+                                                             U8Params p) {
+    const size_t total = size_t(n) * hw;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const size_t img = i / hw, pix = i - img * hw;
+        const uint8_t* sp = src + i * sc;
+        for (int ch = 0; ch < c; ++ch) dst[(img * c + ch) * hw + pix] = __float2half_rn(__fadd_rn(__fmul_rn(float(sp[ch]), p.scale[ch]), p.bias[ch]));  // no fma: bit-identical to fp32 mul, add
+    }
+}
+}  // namespace
+cudaError_t u8_to_nchw_f16(const uint8_t* src, __half* dst, int n, int c, size_t hw, int sc, const float* scale4, const float* bias4, cudaStream_t s) {
+    if (c < 1 || c > 4 || sc < c) return cudaErrorInvalidValue;
+    U8Params p;
+    for (int i = 0; i < 4; ++i) { p.scale[i] = scale4[i]; p.bias[i] = bias4[i]; }
+    u8_to_nchw_kernel<<<grid_for(size_t(n) * hw), kThreads, 0, s>>>(src, dst, n, c, hw, sc, p);
+    return cudaGetLastError();
+}
 cudaError_t f16_to_f32(const __half* src, float* dst, size_t n, cudaStream_t s) {
     f16_to_f32_kernel<<<grid_for(n), kThreads, 0, s>>>(src, dst, n);
     return cudaGetLastError();

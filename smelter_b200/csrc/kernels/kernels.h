@@ -58,6 +58,8 @@ cudaError_t depthwise_conv(const __half* x, const __half* w, const float* bias, 
 
 cudaError_t f32_to_f16(const float* src, __half* dst, size_t n, cudaStream_t s);
 cudaError_t f16_to_f32(const __half* src, float* dst, size_t n, cudaStream_t s);
+// interleaved u8 [n][hw][sc] -> planar fp16 [n][c][hw], dst = byte * scale[ch] + bias[ch] (scale/bias passed by value, c <= 4)
+cudaError_t u8_to_nchw_f16(const uint8_t* src, __half* dst, int n, int c, size_t hw, int sc, const float* scale4, const float* bias4, cudaStream_t s);
 // 64-bit order-independent checksum (sum of 32-bit words with a position-mixing multiplier), result on device.
 cudaError_t checksum64(const void* p, size_t bytes, unsigned long long* out_dev, cudaStream_t s);
 

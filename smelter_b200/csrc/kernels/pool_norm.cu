@@ -26,6 +26,28 @@ inline int grid_for(size_t work_items, int per_block = kThreads) {
     return int(blocks);
 }
 
+// Programmatic dependent launch for the few non-conv kernels that sit between conv kernels of a model (stem pool, global average
+// pool): the kernel may be scheduled while its predecessor drains and tells its successor to do the same; it reads nothing
+// before griddepcontrol.wait.  Saves ~2 us per boundary against a plain stream-ordered launch.
+__device__ __forceinline__ void pdl_prologue() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 struct alignas(16) Half8 {
     __half2 v[4];
 };
@@ -115,6 +137,7 @@ __global__ void __launch_bounds__(kThreads) pool2d_kernel(const __half* __restri
 // so no conversion is needed; the generic kernel spends more issue slots on cvt than on the compare).
 __global__ void __launch_bounds__(kThreads) pool_max3x3_kernel(const __half* __restrict__ x, __half* __restrict__ y, int h, int w, int cp8, int p, int q,
                                                               int sh, int sw, int ph, int pw) {
+    pdl_prologue();
     const int op = blockIdx.y % p;
     const int img = blockIdx.y / p;
     const int row_items = q * cp8;
@@ -403,7 +426,7 @@ cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int 
     if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
     const int row_items = q * (cp / 8);
     dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
-    if (kh == 3 && kw == 3 && is_max) pool_max3x3_kernel<<<grid, kThreads, 0, s>>>(x, y, h, w, cp / 8, p, q, sh, sw, ph, pw);
+    if (kh == 3 && kw == 3 && is_max) return launch_pdl(pool_max3x3_kernel, grid, dim3(kThreads), s, x, y, h, w, cp / 8, p, q, sh, sw, ph, pw);
     else pool2d_kernel<<<grid, kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
     return cudaGetLastError();
 }
@@ -412,6 +435,7 @@ cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int 
 // summing every 8th pixel, then a 3-step shuffle reduction.  Consecutive 8-lane teams read consecutive 16-byte vectors.
 __global__ void __launch_bounds__(kThreads) global_avgpool_team_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int hw,
                                                                       int cp8) {
+    pdl_prologue();
     const size_t total = size_t(n) * cp8;
     const int sub = threadIdx.x & 7;
     for (size_t i = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 3; i < ((total + 31) & ~size_t(31)); i += (size_t(gridDim.x) * blockDim.x) >> 3) {
@@ -453,7 +477,7 @@ __global__ void __launch_bounds__(kThreads) global_avgpool_team_kernel(const __h
 cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cudaStream_t s) {
     if (hw <= 64 || size_t(n) * (cp / 8) >= size_t(kSMs) * 64) {
         const size_t teams = size_t(n) * (cp / 8);
-        global_avgpool_team_kernel<<<grid_for(teams * 8), kThreads, 0, s>>>(x, y, n, hw, cp / 8);
+        return launch_pdl(global_avgpool_team_kernel, dim3(unsigned(grid_for(teams * 8))), dim3(kThreads), s, x, y, n, hw, cp / 8);
     } else {
         dim3 grid(cp / 8, n);
         global_avgpool_kernel<<<grid, kThreads, 0, s>>>(x, y, hw, cp / 8);

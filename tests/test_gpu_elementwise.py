@@ -174,3 +174,20 @@ def test_layout_roundtrip_is_exact(ctx, shape):
     x = _rand(shape, 15)
     y, _ = run_elementwise(ctx, "layout_roundtrip", _img(ctx, x), out_shape=shape)
     assert np.array_equal(y.toHalfArray().view(np.uint16), x.view(np.uint16))
+
+
+@pytest.mark.parametrize("src_channels", [3, 4])
+def test_uint8_image_ingestion(ctx, src_channels):
+    """smelter_tensor_from_u8: interleaved 8-bit pixels -> fp16 NCHW with per-channel scale/bias (the `texture(from:)` step of
+    README.md:33-39); exact against numpy in fp32 rounded once to fp16."""
+    from smelter_b200.api import Image
+
+    rng = np.random.default_rng(7)
+    px = rng.integers(0, 256, size=(2, 19, 23, src_channels), dtype=np.uint8)
+    scale, bias = [1 / 255.0, 2 / 255.0, 0.5], [-0.485, 0.0, 1.25]
+    got = Image.fromBytes(ctx, px, channels=3, scale=scale, bias=bias).toHalfArray()
+    want = (px[..., :3].astype(np.float32) * np.asarray(scale, np.float32) + np.asarray(bias, np.float32)).astype(np.float16).transpose(0, 3, 1, 2)
+    assert got.shape == (2, 3, 19, 23)
+    assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
+    default = Image.fromBytes(ctx, px[0], channels=3).toHalfArray()
+    assert np.array_equal(default.view(np.uint16), (px[:1, ..., :3].astype(np.float32) * np.float32(1 / 255.0)).astype(np.float16).transpose(0, 3, 1, 2).view(np.uint16))

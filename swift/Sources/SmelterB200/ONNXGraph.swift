@@ -35,6 +35,16 @@ public final class DeviceImage {
     public func upload(_ values: [Float]) throws {
         try values.withUnsafeBufferPointer { try ONNXGraph.check(smelter_tensor_from_float(handle, nil, $0.baseAddress, $0.count)) }
     }
+    /// `texture(from: CGImage)` analogue for interleaved 8-bit pixels [N][H][W][sourceChannels]: value = byte * scale[c] + bias[c].
+    public func upload(pixels: [UInt8], sourceChannels: Int32, scale: [Float]? = nil, bias: [Float]? = nil) throws {
+        try pixels.withUnsafeBufferPointer { px in
+            try ONNXGraph.check(smelter_tensor_from_u8(handle, nil, px.baseAddress, sourceChannels, scale, bias))
+        }
+    }
+    /// Enqueue the read-back without waiting (read `into` in the stream's completion callback, like an MTLCommandBuffer handler).
+    public func toFloatArrayAsync(into buffer: UnsafeMutableBufferPointer<Float>, stream: UnsafeMutableRawPointer? = nil) throws {
+        try ONNXGraph.check(smelter_tensor_to_float_async(handle, stream, buffer.baseAddress, buffer.count))
+    }
     /// MPSImage.toFloatArray() (MPSImage+Extensions.swift:9-59); NCHW order.
     public func toFloatArray() -> [Float]? {
         var dims = [Int32](repeating: 0, count: 4)

@@ -286,7 +286,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             mbar_init(empty_bar(lane), 1);
         } else if (lane < C::kStages + 2) {
             mbar_init(tmem_full_bar(lane - C::kStages), 1);
-            mbar_init(tmem_empty_bar(lane - C::kStages), 128);
+            // arrivals per accumulator hand-back: one group of four warps, or both when they share every tile (see the epilogue)
+            mbar_init(tmem_empty_bar(lane - C::kStages), (C::kChunks >= 2 && p.splits == 1) ? 256 : 128);
         } else if (lane >= 16) {
             mbar_init(res_bar((lane - 16) >> 1, lane & 1), 1);
         }
@@ -431,6 +432,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
         const uint32_t bias_slot = bias_base + uint32_t(ewarp) * kBiasSlotBytes;
         const uint32_t row_off = uint32_t(lane) * 128u;
         const uint32_t sw = uint32_t(lane & 7);
+        const uint64_t pol_keep = l2_policy_evict_last(), pol_drop = l2_policy_evict_first();
         const bool is_sigmoid = p.act == ACT_SIGMOID;
         const __half2 lo2 = __float2half2_rn(p.act == ACT_RELU ? 0.f : (p.act == ACT_CLIP ? p.clip_lo : -INFINITY));
         const __half2 hi2 = __float2half2_rn(p.act == ACT_CLIP ? p.clip_hi : INFINITY);
@@ -448,17 +450,26 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the TMA (async proxy)
             __syncwarp();              // also: every lane is done with the bias slot before the next chunk's bias is published
             if (lane == 0) {
-                tma_store_2d(&tm_out, buf, col0, m_row0);  // rows >= M and columns >= out_pitch are clipped by the map
+                // rows >= M and columns >= out_pitch are clipped by the map
+                if (p.l2_hints & 1) tma_store_2d_hint(&tm_out, buf, col0, m_row0, pol_keep);
+                else tma_store_2d(&tm_out, buf, col0, m_row0);
                 tma_store_commit();
             }
         };
         if (p.splits == 1) {
-        const int group_tiles = my_tiles > group ? (my_tiles - group + 1) / 2 : 0;
-        const int n_items = group_tiles * C::kChunks;  // (tile, chunk) stream of this warp
+        // Which (tile, chunk) pairs this warp drains.  Tiles of one 64-column chunk: the two groups alternate whole tiles
+        // (group g = accumulator buffer g).  Wider tiles: BOTH groups work on every tile, group g taking chunks g, g+2, ... —
+        // same throughput, but a tile's epilogue takes half as long, which is what the last tile of a CTA (and every tile of a
+        // layer with at most one tile per CTA) exposes.
+        constexpr bool kSplit = C::kChunks >= 2;
+        constexpr int kCPW = kSplit ? C::kChunks / 2 : C::kChunks;  // chunks per warp per tile
+        const int group_tiles = kSplit ? my_tiles : (my_tiles > group ? (my_tiles - group + 1) / 2 : 0);
+        const int n_items = group_tiles * kCPW;  // (tile, chunk) stream of this warp
         auto item_coords = [&](int item, int* m_row0, int* col0) {
-            const int gt = item / C::kChunks;           // kChunks is a power of two: shifts
-            const int c = item - gt * C::kChunks;
-            const int tile = int(blockIdx.x) + (2 * gt + group) * int(gridDim.x);
+            const int gt = item / kCPW;           // kCPW is a power of two: shifts
+            const int j = item - gt * kCPW;
+            const int c = kSplit ? group + 2 * j : j;
+            const int tile = int(blockIdx.x) + (kSplit ? gt : 2 * gt + group) * int(gridDim.x);
             const int m_tile = tile / p.num_n_tiles;
             const int n_tile = tile - m_tile * p.num_n_tiles;
             *m_row0 = m_tile * kBlockM + ew * 32;
@@ -470,7 +481,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             const int b = item & 1;
             fence_proxy_async_smem();
             mbar_expect_tx(res_bar(ewarp, b), kEpiBufBytes);
-            tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0);
+            if (p.l2_hints & 2) tma_load_2d_hint(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0, pol_drop);
+            else tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0);
         };
         if (HAS_RES && n_items > 0 && lane == 0) prefetch_res(0);
         // bias of the next chunk, two columns per lane, fetched one chunk ahead (weights: no dependency on the previous kernel)
@@ -481,23 +493,19 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
             bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
         }
         uint32_t res_phase = 0;  // bit b = parity of res_bar(ewarp, b)
-        uint32_t acc_phase = 0;
         int item = 0;
         for (int gt = 0; gt < group_tiles; ++gt) {
-            mbar_wait(tmem_full_bar(group), acc_phase);  // (one polling lane + nanosleep back-off measured slower than all lanes waiting)
+            const int acc = kSplit ? (gt & 1) : group;                             // accumulator buffer of this tile
+            const uint32_t acc_parity = uint32_t(kSplit ? (gt >> 1) : gt) & 1u;    // how often this warp has used that buffer's barrier
+            mbar_wait(tmem_full_bar(acc), acc_parity);  // (one polling lane + nanosleep back-off measured slower than all lanes waiting)
             if (gt == 0 && ewarp == 0 && lane == 0) stamp(p, 5);  // first accumulator ready
-            acc_phase ^= 1u;
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(group * BLOCK_N);
-            int m_row0, col0;
-            item_coords(item, &m_row0, &col0);
-            int next_tile_col0 = 0;
-            if (gt + 1 < group_tiles) {
-                int nm;
-                item_coords(item + C::kChunks, &nm, &next_tile_col0);
-            }
+            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
 #pragma unroll 1
-            for (int c = 0; c < C::kChunks; ++c, ++item, col0 += kChunkN) {
+            for (int j = 0; j < kCPW; ++j, ++item) {
+                int m_row0, col0;
+                item_coords(item, &m_row0, &col0);
+                const int c = kSplit ? group + 2 * j : j;
                 const int b = HAS_RES ? (item & 1) : 0;
                 if (HAS_RES && lane == 0 && item + 1 < n_items) {
                     tma_store_wait_read<0>();  // the store of item-1 has finished reading buffer b^1
@@ -505,15 +513,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constan
                 }
                 // publish this chunk's bias to the warp through smem, then start fetching the next chunk's
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
-                if (c + 1 < C::kChunks) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0 + kChunkN) + lane);
-                else if (item + 1 < n_items) bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + next_tile_col0) + lane);
+                if (item + 1 < n_items) {
+                    int nm, ncol0;
+                    item_coords(item + 1, &nm, &ncol0);
+                    bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + ncol0) + lane);
+                }
                 uint32_t v[C::kChunkCols];
                 tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
                 if (C::kChunkCols > 32) tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + (C::kChunkCols > 32 ? 32 : 0));
                 tmem_ld_wait();
-                if (c == C::kChunks - 1) {  // the accumulator is in registers: hand the TMEM buffer back to the MMA warp
+                if (j == kCPW - 1) {  // this warp's part of the accumulator is in registers: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
-                    mbar_arrive(tmem_empty_bar(group));
+                    mbar_arrive(tmem_empty_bar(acc));
                 }
                 if (HAS_RES) {
                     mbar_wait(res_bar(ewarp, b), (res_phase >> b) & 1u);
@@ -832,6 +843,8 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     L->block_n = block_n;
     L->use_pdl = getenv("SMELTER_NO_PDL") ? 0 : 1;
     p.use_pdl = L->use_pdl;
+    p.l2_hints = q.l2_hints;
+    if (const char* h = getenv("SMELTER_L2_HINTS")) p.l2_hints = atoi(h);  // experiments: force for every layer
     { const char* dbg = getenv("SMELTER_CONV_DEBUG"); p.debug_flags = dbg ? atoi(dbg) : 0; }
     p.timeline = nullptr;
     if (getenv("SMELTER_CONV_TIMELINE")) {

@@ -37,6 +37,7 @@ struct ConvKernelParams {
     unsigned long long* timeline;  // perf experiments only (env SMELTER_CONV_TIMELINE): CTA 0 writes %globaltimer stamps here
     int debug_flags;         // perf experiments only (env SMELTER_CONV_DEBUG): 16 = producers skip the TMA loads (results wrong)
     int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
+    int l2_hints;            // 1 = output stores evict_last (tensor re-read by later layers), 2 = residual loads evict_first (last use)
 };
 
 struct ConvTcProblem {
@@ -55,6 +56,7 @@ struct ConvTcProblem {
     int act;
     float clip_lo, clip_hi;
     int block_n;            // 0 = auto
+    int l2_hints;           // ConvKernelParams::l2_hints
     int splits;             // 0 = auto (conv_tc_plan), 1 = no split-K
     float* split_ws;        // workspace of conv_tc_plan().ws_bytes when splits > 1
     unsigned int* split_counters;  // conv_tc_plan().counter_bytes, zero-initialised once; the kernel leaves them zero

@@ -390,6 +390,7 @@ __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __res
                                                             int cp8, int p, int q, int kh, int kw, int sh, int sw, int dh, int dw, int pt,
                                                             int pl, int act, float lo, float hi) {
     // grid.y walks output rows (image, op); threads walk (oq, channel group) of that row
+    pdl_prologue();
     const int op = blockIdx.y % p;
     const int img = blockIdx.y / p;
     const int row_items = q * cp8;
@@ -527,8 +528,7 @@ cudaError_t depthwise_conv(const __half* x, const __half* w, const float* bias, 
     if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
     const int row_items = q * (cp / 8);
     dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
-    depthwise_kernel<<<grid, kThreads, 0, s>>>(x, w, bias, y, n, h, wd, cp / 8, p, q, kh, kw, sh, sw, dh, dw, pt, pl, act, lo, hi);
-    return cudaGetLastError();
+    return launch_pdl(depthwise_kernel, grid, dim3(kThreads), s, x, w, bias, y, n, h, wd, cp / 8, p, q, kh, kw, sh, sw, dh, dw, pt, pl, act, lo, hi);
 }
 
 }  // namespace k

@@ -150,7 +150,7 @@ def run_reference(args) -> int:
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "ResNet-50 224x224 batch=32 per GPU (BASELINE.json configs[2]); CPU arm runs a bounded sample per step",
-                       "model": "seeded random ResNet-50 -> ONNX2MPS --half", "note": "reference = Swift + Apple MPS, not runnable here; "
+                       "onnx_graph": "seeded random ResNet-50 -> ONNX2MPS --half", "note": "reference = Swift + Apple MPS, not runnable here; "
                        "this arm is the oracle port on host cores"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -309,7 +309,7 @@ def run_native(args) -> int:
     line = {"metric": "ResNet-50 fp16 224x224 images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": {"workload": "ResNet-50 fp16 224x224 batch=32 per GPU (BASELINE.json configs[2]; N GPUs = configs[4] weak-scaled)",
-                       "model": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": world * B,
+                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": world * B,
                        "per_gpu_batch": B, "parallelism": f"batch-sharded dp{world}, one NCCL weight broadcast, no steady-state collective",
                        "l2": f"inputs larger than L2: {N_INPUT_SETS} distinct resident batches (154 MB) rotated, no flush",
                        "cuda_graph": True, "accumulate": "fp32 (TMEM)"},

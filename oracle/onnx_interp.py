@@ -23,6 +23,8 @@ Per-op citations give the reference converter whose MPS node the op replaces:
   Reshape/Flatten        :830-915 (ONNX semantics on NCHW)
   Softmax/LogSoftmax     :697-714, :1213-1231 (axis 1)
   Pad                    :942-989 (constant/reflect/edge; `value` honoured)
+  ConvTranspose          ConvolutionConverter :266-287 (+ Array+Extensions.swift:70-76 flip; ONNX2MPS.py:54-79 swizzle undone)
+  custom_group_norm      GroupNormConverter :1273-1300;  Pow  PowConverter :1160-1175 (ONNX meaning: scalar exponent)
   Constant / Dropout / Identity   :716-727, :918-939
 
 The `.mpsFlavor` format (producer_name == "ONNX2MPS", ONNXGraph.swift:98-103) is honoured: conv weights are OHWI

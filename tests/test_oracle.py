@@ -142,3 +142,35 @@ def test_model_op_inventories_match_the_survey():
     t = modelzoo.transformer_net(seed=0)
     assert modelzoo.count_ops(t) == {"Pad": 16, "Conv": 16, "InstanceNormalization": 15, "Relu": 10, "Add": 5, "Constant": 2, "Upsample": 2}
     assert modelzoo.macs(t, (1, 3, 512, 512)) == 40_315_650_048
+
+
+def test_conv_transpose_group_norm_pow_against_torch_modules():
+    """Pins the oracle's ConvTranspose / custom_group_norm / Pow (the registry entries no BASELINE model uses) against eager
+    nn.ConvTranspose2d / nn.GroupNorm loaded with the graph's initializers, in ONNX flavour and after the ONNX2MPS swizzle."""
+    from smelter_b200 import onnx2mps
+
+    m = modelzoo.decoder_ops(seed=3)
+    nodes = {n.op_type + str(i): n for i, n in enumerate(m.graph.node)}
+    conv_n = m.graph.node[0]
+    gn_n = m.graph.node[1]
+    ct = [n for n in m.graph.node if n.op_type == "ConvTranspose"]
+    assert [n.op_type for n in m.graph.node] == ["Conv", "custom_group_norm", "Relu", "ConvTranspose", "Relu", "ConvTranspose", "Sigmoid", "Pow",
+                                                 "ConvTranspose"] and nodes
+    conv = nn.Conv2d(32, 64, 3, padding=1)
+    gn = nn.GroupNorm(8, 64, eps=1e-5)
+    t1 = nn.ConvTranspose2d(64, 48, 3, stride=2, padding=1, output_padding=1)
+    t2 = nn.ConvTranspose2d(48, 24, 4, stride=2, padding=1)
+    t3 = nn.ConvTranspose2d(24, 8, 1)
+    with torch.no_grad():
+        conv.weight.copy_(_t(m, conv_n.input[1])); conv.bias.copy_(_t(m, conv_n.input[2]))
+        gn.weight.copy_(_t(m, gn_n.input[2])); gn.bias.copy_(_t(m, gn_n.input[3]))
+        for mod, n in zip((t1, t2, t3), ct):
+            mod.weight.copy_(_t(m, n.input[1])); mod.bias.copy_(_t(m, n.input[2]))
+    x = torch.randn(2, 32, 10, 10)
+    with torch.no_grad():
+        want = t3(torch.sigmoid(t2(torch.relu(t1(torch.relu(gn(conv(x))))))) ** 2.0)
+    got = Interpreter(m.serialize()).run(x)
+    assert got.shape == want.shape == (2, 8, 40, 40)
+    assert torch.allclose(got, want, atol=1e-5)
+    got_mps = Interpreter(onnx2mps.convert_bytes(m.serialize(), half=False)).run(x)  # [1,2,3,0] swizzle + flip, fp32 kept
+    assert torch.allclose(got_mps, want, atol=1e-5)

@@ -46,8 +46,8 @@ typedef enum smelter_format { SMELTER_FORMAT_ONNX = 0, SMELTER_FORMAT_MPS_FLAVOR
 /* ONNXGraph.Configuration (ONNXGraph.swift:6-36). */
 typedef enum smelter_input_constraint {
     SMELTER_INPUT_NONE = 0,                 /* .none */
-    SMELTER_INPUT_FORCE_SCALE_LANCZOS = 1,  /* .forceInputScale(.lanczos)  — accepted, not implemented: encode fails */
-    SMELTER_INPUT_FORCE_SCALE_BILINEAR = 2  /* .forceInputScale(.bilinear) — accepted, not implemented: encode fails */
+    SMELTER_INPUT_FORCE_SCALE_LANCZOS = 1,  /* .forceInputScale(.lanczos): sources of any H x W are resampled (Lanczos-3) to the graph input */
+    SMELTER_INPUT_FORCE_SCALE_BILINEAR = 2  /* .forceInputScale(.bilinear): same with bilinear interpolation (half-pixel centres) */
 } smelter_input_constraint;
 
 typedef struct smelter_config {

@@ -128,6 +128,7 @@ struct Plan {
     Tensor result;
     cudaGraphExec_t exec = nullptr;
     void* counters = nullptr;  // split-K arrival counters of every conv in the plan (zero between launches)
+    std::vector<__half*> resized;  // per graph input: NCHW staging the source is resized into under .forceInputScale (lazily allocated)
     std::vector<void*> blobs;  // further device allocations owned by the plan (completion counters of persistent conv runs)
     ~Plan() {
         if (exec) cudaGraphExecDestroy(exec);
@@ -206,8 +207,7 @@ int ONNXGraph::initOutputs() {
         else if (dims.size() == 4) { s.c = int(dims[1]); s.h = int(dims[2]); s.w = int(dims[3]); }   // :209-212 (N dropped)
         else return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "graph input '" + vi.name + "' must have rank 3 or 4");  // :213-214
         if (s.c <= 0 || s.h <= 0 || s.w <= 0) return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "graph input '" + vi.name + "' has unknown dims");
-        if (cfg_.input_constraint != SMELTER_INPUT_NONE)
-            return fail(SMELTER_ERR_UNSUPPORTED, "forceInputScale is not implemented (SURVEY §8f N4)");  // :219-241
+        // .forceInputScale (:219-241): sources of any H x W are resized to the graph input at encode time (ONNXGraph::encode)
         Value v;
         v.name = vi.name;
         v.shape = s;
@@ -925,6 +925,22 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     for (int i = 0; i < n_sources; ++i) {
         const ImageShape& s = plan->src_shapes[size_t(i)];
         const Tensor* t = sources[i];
+        if (cfg_.input_constraint != SMELTER_INPUT_NONE && t->n == batch && t->c == s.c && (t->h != s.h || t->w != s.w) && t->h > 0 && t->w > 0) {
+            // MPSNNLanczosScaleNode / MPSNNBilinearScaleNode in front of the graph (ONNXGraph.swift:219-241): eager, like the boundary step
+            if (plan->resized.size() < size_t(n_sources)) plan->resized.resize(size_t(n_sources), nullptr);
+            if (!plan->resized[size_t(i)]) {
+                void* buf = nullptr;
+                SM_CUDA(cudaSetDevice(ctx_->device));
+                SM_CUDA(cudaMalloc(&buf, size_t(batch) * s.c * s.h * s.w * 2));
+                plan->blobs.push_back(buf);
+                plan->resized[size_t(i)] = static_cast<__half*>(buf);
+            }
+            cudaError_t e = k::resize_planes(t->ptr, plan->resized[size_t(i)], batch * s.c, t->h, t->w, s.h, s.w,
+                                             cfg_.input_constraint == SMELTER_INPUT_FORCE_SCALE_LANCZOS ? 1 : 0, stream ? stream : ctx_->stream);
+            if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, std::string("input resize: ") + cudaGetErrorString(e));
+            *plan->src_slots[size_t(i)] = plan->resized[size_t(i)];
+            continue;
+        }
         if (t->n != batch || t->c != s.c || t->h != s.h || t->w != s.w)
             return fail(SMELTER_ERR_UNSUPPORTED_INPUT, "source " + std::to_string(i) + " is [" + std::to_string(t->n) + "," + std::to_string(t->c) + "," +
                                                            std::to_string(t->h) + "," + std::to_string(t->w) + "], graph input is [N," + std::to_string(s.c) + "," +

@@ -266,6 +266,51 @@ __global__ void __launch_bounds__(kThreads) zero_stuff2d_kernel(const __half* __
     }
 }
 
+// Input resize for Configuration.inputConstraint = .forceInputScale (ONNXGraph.swift:219-241; MPSNNBilinearScaleNode /
+// MPSNNLanczosScaleNode are closed source, so the kernels are defined here: sample positions at half-pixel centres,
+// src = (dst + 0.5) * (in / out) - 0.5, taps clamped to the edge, Lanczos window a = 3 with the weights normalised to 1).
+__device__ __forceinline__ float lanczos3(float x) {
+    x = fabsf(x);
+    if (x < 1e-6f) return 1.f;
+    if (x >= 3.f) return 0.f;
+    const float px = 3.14159265358979f * x;
+    return 3.f * sinf(px) * sinf(px / 3.f) / (px * px);
+}
+__global__ void __launch_bounds__(kThreads) resize_planes_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int planes, int hs, int ws,
+                                                                int hd, int wd, int mode) {
+    const size_t total = size_t(planes) * hd * wd;
+    const float sy = float(hs) / float(hd), sx = float(ws) / float(wd);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int x = int(i % wd), y = int((i / wd) % hd);
+        const __half* sp = src + (i / (size_t(wd) * hd)) * size_t(hs) * ws;
+        const float fy = (y + 0.5f) * sy - 0.5f, fx = (x + 0.5f) * sx - 0.5f;
+        const int y0 = int(floorf(fy)), x0 = int(floorf(fx));
+        float acc = 0.f, wsum = 0.f;
+        if (mode == 0) {
+            const float wy1 = fy - y0, wx1 = fx - x0;
+            for (int dy = 0; dy < 2; ++dy)
+                for (int dx = 0; dx < 2; ++dx) {
+                    const int yy = min(max(y0 + dy, 0), hs - 1), xx = min(max(x0 + dx, 0), ws - 1);
+                    const float w = (dy ? wy1 : 1.f - wy1) * (dx ? wx1 : 1.f - wx1);
+                    acc += w * __half2float(sp[size_t(yy) * ws + xx]);
+                    wsum += w;
+                }
+        } else {
+            for (int dy = -2; dy <= 3; ++dy) {
+                const float wy = lanczos3(fy - float(y0 + dy));
+                const int yy = min(max(y0 + dy, 0), hs - 1);
+                for (int dx = -2; dx <= 3; ++dx) {
+                    const float w = wy * lanczos3(fx - float(x0 + dx));
+                    const int xx = min(max(x0 + dx, 0), ws - 1);
+                    acc += w * __half2float(sp[size_t(yy) * ws + xx]);
+                    wsum += w;
+                }
+            }
+        }
+        dst[i] = __float2half_rn(acc / wsum);
+    }
+}
+
 // One thread per (pixel, 8-channel group), pixel fastest so plane writes are coalesced along W.
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c,
                                                                int hw, int cp, long dst_image_pitch) {
@@ -508,6 +553,10 @@ cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int
 cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
                          cudaStream_t s) {
     zero_stuff2d_kernel<<<grid_for(size_t(n) * hz * wz * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, hz, wz, stride_h, stride_w, lo_h, lo_w);
+    return cudaGetLastError();
+}
+cudaError_t resize_planes(const __half* src, __half* dst, int planes, int hs, int ws, int hd, int wd, int mode, cudaStream_t s) {
+    resize_planes_kernel<<<grid_for(size_t(planes) * hd * wd), kThreads, 0, s>>>(src, dst, planes, hs, ws, hd, wd, mode);
     return cudaGetLastError();
 }
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s) {

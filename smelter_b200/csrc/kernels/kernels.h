@@ -31,6 +31,9 @@ cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, in
 // ConvTranspose input: y[n][lo_h + s_h*i][lo_w + s_w*j][c] = x[n][i][j][c], zero elsewhere; y is [n][hz][wz][cp]
 cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
                          cudaStream_t s);
+// Configuration.inputConstraint = .forceInputScale (ONNXGraph.swift:219-241): planar NCHW fp16 [planes][hs][ws] -> [planes][hd][wd].
+// mode 0 = bilinear, 1 = Lanczos-3; half-pixel centres, taps clamped to the image edge, weights normalised.
+cudaError_t resize_planes(const __half* src, __half* dst, int planes, int hs, int ws, int hd, int wd, int mode, cudaStream_t s);
 cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s);
 cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s);
 // y = act(x * scale[c] + shift[c])  (un-fused BatchNormalization)

@@ -299,3 +299,46 @@ def test_weight_arena_checksum_and_deferred_weights(ctx):
     assert ptr != 0 and nbytes == ca[1]
     for g in (a, b, c):
         g.close()
+
+
+@pytest.mark.parametrize("scale", ["bilinear", "lanczos"])
+def test_force_input_scale_resizes_sources(ctx, scale):
+    """Configuration(inputConstraint: .forceInputScale(...)) (ONNXGraph.swift:219-241): sources of any H x W are resampled to the graph
+    input in front of the path.  MPS's scale nodes are closed source; the kernels are defined as half-pixel-centre bilinear (== torch
+    align_corners=False) and Lanczos-3 with edge clamping, restated in numpy below."""
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = onnx2mps.convert_bytes(modelzoo.conv_bn_relu(seed=0).serialize(), half=True)   # graph input [N,3,16,16]
+    x = np.random.default_rng(9).random((2, 3, 23, 29), dtype=np.float32).astype(np.float16)
+
+    def lanczos(t):
+        t = np.abs(t)
+        with np.errstate(divide="ignore", invalid="ignore"):
+            v = 3.0 * np.sin(np.pi * t) * np.sin(np.pi * t / 3.0) / (np.pi * t) ** 2
+        return np.where(t < 1e-6, 1.0, np.where(t >= 3.0, 0.0, v))
+
+    def resample_axis(a, n_out, axis):
+        n_in = a.shape[axis]
+        pos = (np.arange(n_out) + 0.5) * (n_in / n_out) - 0.5
+        base = np.floor(pos).astype(int)
+        taps = range(0, 2) if scale == "bilinear" else range(-2, 4)
+        out, wsum = 0.0, 0.0
+        for d in taps:
+            idx = np.clip(base + d, 0, n_in - 1)
+            w = (1.0 - np.abs(pos - (base + d))) if scale == "bilinear" else lanczos(pos - (base + d))
+            shape = [1] * a.ndim
+            shape[axis] = n_out
+            out = out + np.take(a, idx, axis=axis) * w.reshape(shape)
+            wsum = wsum + w.reshape(shape)
+        return out / wsum
+
+    xr = resample_axis(resample_axis(x.astype(np.float64), 16, 2), 16, 3).astype(np.float16)  # separable: same as the 2-D kernel
+    if scale == "bilinear":
+        want_t = torch.nn.functional.interpolate(torch.from_numpy(x.astype(np.float32)), size=(16, 16), mode="bilinear", align_corners=False)
+        assert np.abs(want_t.numpy() - xr.astype(np.float32)).max() <= 2e-3  # the numpy restatement is torch's definition
+    out, _ = _run(ctx, model, x, inputConstraint=scale)
+    want = _oracle(model, xr)
+    assert out.shape == want.shape
+    assert np.abs(out - want).max() <= TOL
+    with pytest.raises(Exception):  # without the constraint a mis-sized source is still unsupportedInput
+        _run(ctx, model, x)

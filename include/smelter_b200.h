@@ -110,6 +110,10 @@ int32_t smelter_tensor_from_u8(smelter_tensor* t, void* cuda_stream, const uint8
 /* MPSImage.toFloatArray() (Extensions/Foundation/MPSImage+Extensions.swift:9-59): device fp16 → host fp32,
  * NCHW order (the reference returns MPS slice order).  Synchronises the stream. */
 int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity);
+/* toFloatArray() in the reference's own element order (MPSImage+Extensions.swift:26-59): per image, slices of four channels,
+ * each slice [H][W][4] (for C < 3: one slice [H][W][C]); C is padded with zeros to a multiple of 4 when C >= 3.  `capacity` must be
+ * at least N * H * W * (C < 3 ? C : 4 * ceil(C / 4)).  Synchronises the stream. */
+int32_t smelter_tensor_to_float_mps(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity);
 /* Same, but only enqueues the conversion and the device→host copy on the stream (the Metal analogue: read the image in a
  * command buffer's completion handler instead of after waitUntilCompleted()).  `host` must stay valid — and should be pinned —
  * until the stream reaches this point; the tensor may be overwritten by a later encode() on the same stream. */

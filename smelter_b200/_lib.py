@@ -67,6 +67,7 @@ SIGNATURES = {
     "smelter_tensor_from_u8": (i32, [vp, vp, vp, i32, vp, vp]),
     "smelter_tensor_to_float": (i32, [vp, vp, vp, sz]),
     "smelter_tensor_to_float_async": (i32, [vp, vp, vp, sz]),
+    "smelter_tensor_to_float_mps": (i32, [vp, vp, vp, sz]),
     "smelter_tensor_to_half": (i32, [vp, vp, vp, sz]),
     "smelter_graph_create": (i32, [vp, vp, sz, P(smelter_config), P(vp)]),
     "smelter_graph_build": (i32, [vp]),

@@ -208,6 +208,15 @@ class Image:
         _check(L.lib().smelter_tensor_to_float(self._h, C.c_void_p(stream) if stream else None, out.ctypes.data_as(C.c_void_p), out.size))
         return out
 
+    def toFloatArrayMPS(self, stream: Optional[int] = None) -> np.ndarray:
+        """toFloatArray() in the reference's element order (MPSImage+Extensions.swift:26-59): flat array of N x slices x H x W x 4
+        (channels in groups of four, zero padded; C < 3: N x H x W x C)."""
+        n, c, h, w = self.shape
+        cpp = c if c < 3 else 4 * ((c + 3) // 4)
+        out = np.empty(n * h * w * cpp, dtype=np.float32)
+        _check(L.lib().smelter_tensor_to_float_mps(self._h, C.c_void_p(stream) if stream else None, out.ctypes.data_as(C.c_void_p), out.size))
+        return out
+
     def toFloatArrayAsync(self, out: np.ndarray, stream: Optional[int] = None) -> np.ndarray:
         """Enqueue device fp16 -> host fp32 (NCHW) on the stream without waiting: `out` (ideally pinned) holds the values once the
         stream has passed this point — the analogue of reading an MPSImage in a command buffer's completion handler."""

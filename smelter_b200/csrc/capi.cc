@@ -182,6 +182,26 @@ int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, floa
     SM_CUDA(cudaStreamSynchronize(s));
     return SMELTER_OK;
 }
+int32_t smelter_tensor_to_float_mps(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity) {
+    ARG(t && host);
+    const int N = t->t.n, Cc = t->t.c, H = t->t.h, W = t->t.w;
+    const int comps = Cc < 3 ? Cc : 4, slices = (Cc + 3) / 4, cpp = Cc < 3 ? Cc : slices * 4;  // MPSImage+Extensions.swift:27-36
+    ARG(capacity >= size_t(N) * H * W * cpp);
+    std::vector<float> nchw(t->t.count());
+    int rc = smelter_tensor_to_float(t, cuda_stream, nchw.data(), nchw.size());
+    if (rc) return rc;
+    const size_t hw = size_t(H) * W;
+    for (int n = 0; n < N; ++n)
+        for (int s = 0; s < slices; ++s) {
+            float* dst = host + (size_t(n) * slices + s) * hw * comps;  // :49-57 slice i = n * numSlices + s
+            for (size_t p = 0; p < hw; ++p)
+                for (int j = 0; j < comps; ++j) {
+                    const int c = s * 4 + j;
+                    dst[p * comps + j] = c < Cc ? nchw[(size_t(n) * Cc + c) * hw + p] : 0.f;
+                }
+        }
+    return SMELTER_OK;
+}
 int32_t smelter_tensor_to_float_async(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity) {
     ARG(t && host && capacity >= t->t.count());
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;

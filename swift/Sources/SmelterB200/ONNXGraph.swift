@@ -41,6 +41,15 @@ public final class DeviceImage {
             try ONNXGraph.check(smelter_tensor_from_u8(handle, nil, px.baseAddress, sourceChannels, scale, bias))
         }
     }
+    /// toFloatArray() in the reference's own element order (slices of four channels, MPSImage+Extensions.swift:26-59).
+    public func toFloatArrayMPSOrder() -> [Float]? {
+        var dims = [Int32](repeating: 0, count: 4)
+        guard smelter_tensor_dims(handle, &dims) == 0 else { return nil }
+        let c = Int(dims[1]), cpp = c < 3 ? c : 4 * ((c + 3) / 4)
+        var out = [Float](repeating: 0, count: Int(dims[0]) * Int(dims[2]) * Int(dims[3]) * cpp)
+        let rc = out.withUnsafeMutableBufferPointer { smelter_tensor_to_float_mps(handle, nil, $0.baseAddress, $0.count) }
+        return rc == 0 ? out : nil
+    }
     /// Enqueue the read-back without waiting (read `into` in the stream's completion callback, like an MTLCommandBuffer handler).
     public func toFloatArrayAsync(into buffer: UnsafeMutableBufferPointer<Float>, stream: UnsafeMutableRawPointer? = nil) throws {
         try ONNXGraph.check(smelter_tensor_to_float_async(handle, stream, buffer.baseAddress, buffer.count))

@@ -191,3 +191,19 @@ def test_uint8_image_ingestion(ctx, src_channels):
     assert np.array_equal(got.view(np.uint16), want.view(np.uint16))
     default = Image.fromBytes(ctx, px[0], channels=3).toHalfArray()
     assert np.array_equal(default.view(np.uint16), (px[:1, ..., :3].astype(np.float32) * np.float32(1 / 255.0)).astype(np.float16).transpose(0, 3, 1, 2).view(np.uint16))
+
+
+@pytest.mark.parametrize("c", [1, 2, 3, 6, 8])
+def test_read_back_in_mps_slice_order(ctx, c):
+    """smelter_tensor_to_float_mps: the element order MPSImage.toFloatArray() returns (MPSImage+Extensions.swift:26-59): per image,
+    slices of four channels stored [H][W][4] with zero padding; one [H][W][C] slice when C < 3."""
+    from smelter_b200.api import Image
+
+    x = np.random.default_rng(c).standard_normal((2, c, 5, 7)).astype(np.float16)
+    got = Image.fromArray(ctx, x).toFloatArrayMPS()
+    comps, slices = (c, 1) if c < 3 else (4, (c + 3) // 4)
+    want = np.zeros((2, slices, 5, 7, comps), dtype=np.float32)
+    for ch in range(c):
+        want[:, ch // 4 if c >= 3 else 0, :, :, ch % 4 if c >= 3 else ch] = x[:, ch].astype(np.float32)
+    assert got.shape == (want.size,)
+    assert np.array_equal(got, want.reshape(-1))

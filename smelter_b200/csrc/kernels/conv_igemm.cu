@@ -13,8 +13,8 @@
 // * W is pre-packed [Cout][tap][Cin_pad] fp16 (the OHWI order ONNX2MPS.py:75 produces) and fetched with a 3-D map.
 // * tcgen05.mma (kind::f16, fp32 accumulate) issued by one thread; accumulators double-buffered in TMEM so the
 //   epilogue of tile i overlaps the MMAs of tile i+1; persistent CTAs, one per SM.
-// * Warp roles: 0 = TMA producer, 1 = MMA issuer, 2 = TMEM allocator, 4..7 = epilogue (TMEM -> regs -> bias /
-//   residual / activation -> fp16 -> global).
+// * Warp roles (16 warps): 0-3 TMA producers of the activation operand, 4-11 epilogue (TMEM -> regs -> bias / residual /
+//   activation -> fp16 -> swizzled smem -> TMA store), 12 MMA issuer + TMEM allocator, 13-15 TMA producers of the weight operand.
 #include "conv_igemm.h"
 
 #include <cstdio>
@@ -32,7 +32,6 @@ namespace {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;  // fp16 elements = one 128-byte swizzle row
-constexpr int kUmmaK = 16;
 // 16 warps (512 threads x 128 registers = the whole register file): 0-3 TMA producers of the A (activation) operand,
 // 4-11 epilogue (two groups of four), 12 MMA issuer + TMEM allocator, 13-15 TMA producers of the B (weight) operand.
 // Several producers because TMA operations issued by one thread complete strictly one after another (~0.35 us each on

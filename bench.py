@@ -97,7 +97,9 @@ class ClockSampler:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        rows = self.rows[lo:hi] or self.rows
+        rows = self.rows[lo:hi]
+        if len(rows) < 3:  # a short timed region sees few 50 ms samples: widen to everything under load after its start (the e2e loop)
+            rows = self.rows[lo:] or self.rows
         sm, mx, reasons = [], [], set()
         for r in rows:
             try:

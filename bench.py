@@ -62,7 +62,7 @@ def ncu_conv_traffic():
             rows = list(csv.reader(f))
         head = rows[0]
         ir, iw, ik = head.index("dram_read"), head.index("dram_write"), head.index("kernel")
-        return sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_igemm" in r[ik] or "conv_mega" in r[ik])
+        return sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_igemm" in r[ik] or "conv_mega" in r[ik] or "conv_pair" in r[ik])
     except (OSError, ValueError):
         return None
 
@@ -293,7 +293,7 @@ def run_native(args) -> int:
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": ncu_conv_traffic(), "kernel": "conv_igemm_kernel<BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
+                "traffic": ncu_conv_traffic(), "kernel": "conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
                 "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": share,
                 "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
                 "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,

@@ -26,6 +26,7 @@ SOURCES = [
     "nccl_shim.cc",
     "kernels/conv_igemm.cu",
     "kernels/conv_mega.cu",
+    "kernels/conv_pair.cu",
     "kernels/elementwise.cu",
     "kernels/pool_norm.cu",
 ]

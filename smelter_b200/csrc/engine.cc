@@ -782,7 +782,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
-                add_step(std::string("conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
+                add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,
                          io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0));

@@ -752,6 +752,24 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
     ConvTcPlanInfo best{};
     best.block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, m_tiles, num_sms);
     best.splits = 1;
+    const bool pair_mode = q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"));
+    if (pair_mode && !q.block_n && q.c_out > 64) {
+        // Two-CTA clusters (conv_pair.cu): work items are (m-tile pair, n-tile) on num_sms / 2 clusters.  Per k-block a pair needs
+        // ~0.125 / 0.15 / 0.26 us for N = 64 / 128 / 256 (N = 256 is bound by its MMAs, the others by bytes in flight), the epilogue
+        // ~0.35 us per 64 columns; pick the width with the shortest span.
+        const long pairs = (m_tiles + 1) / 2;
+        double best_span = 1e30;
+        const int cands[3] = {64, 128, 256};
+        const double t_kb[3] = {0.125, 0.15, 0.26};
+        for (int i = 0; i < 3; ++i) {
+            const int bn = cands[i];
+            if (bn / 2 >= q.c_out) continue;
+            const long items = pairs * ((q.c_out + bn - 1) / bn);
+            const long waves = (items + num_sms / 2 - 1) / (num_sms / 2);
+            const double span = double(waves) * std::max(num_kb * t_kb[i], 0.35 * (bn / 64));
+            if (span < best_span * 0.97) { best_span = span; best.block_n = bn; }
+        }
+    }
     if (const char* force = getenv("SMELTER_FORCE_BN")) {  // tuning experiments only
         const int v = atoi(force);
         if (v == 32 || v == 64 || v == 128 || v == 256) best.block_n = v;
@@ -853,6 +871,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     }
     {
         cudaError_t e = set_attr(block_n);
+        if (e == cudaSuccess && (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && (block_n == 64 || block_n == 128 || block_n == 256)) e = conv_pair_set_attr(block_n);
         if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
     }
     p.M = int(M);
@@ -883,7 +902,11 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     {
         cuuint64_t dims[3] = {cuuint64_t(kc), cuuint64_t(taps), cuuint64_t(q.c_out)};
         cuuint64_t strides[2] = {cuuint64_t(kc) * 2, cuuint64_t(kc) * 2 * taps};
-        cuuint32_t box[3] = {kBlockK, 1, cuuint32_t(block_n)};
+        // two-CTA clusters (conv_pair.cu): each CTA loads half of the weight tile
+        const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
+        L->pair = want_pair ? 1 : 0;
+        L->num_sms = num_sms;
+        cuuint32_t box[3] = {kBlockK, 1, cuuint32_t(want_pair ? block_n / 2 : block_n)};
         cuuint32_t estr[3] = {1, 1, 1};
         CUresult r = g_encode_tiled(&L->tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(q.w_packed), dims, strides,
                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -1270,6 +1293,7 @@ void conv_tc_dump_timeline(const ConvTcLaunch& L) {
 }
 
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream) {
+    if (L.pair) return conv_pair_launch(L, L.num_sms, stream);
     switch (L.block_n) {
         case 32: return launch_t<32>(L, stream);
         case 64: return launch_t<64>(L, stream);

@@ -57,6 +57,7 @@ struct ConvTcProblem {
     float clip_lo, clip_hi;
     int block_n;            // 0 = auto
     int l2_hints;           // ConvKernelParams::l2_hints
+    int pair;               // 1 = two-CTA clusters with cta_group::2 MMAs (conv_pair.cu); 0 = single-CTA kernel
     int splits;             // 0 = auto (conv_tc_plan), 1 = no split-K
     float* split_ws;        // workspace of conv_tc_plan().ws_bytes when splits > 1
     unsigned int* split_counters;  // conv_tc_plan().counter_bytes, zero-initialised once; the kernel leaves them zero
@@ -76,6 +77,8 @@ struct ConvTcLaunch {
     int splits;
     int grid;
     int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
+    int pair;      // launched as conv_pair_kernel (two-CTA clusters): tm_b boxes hold BLOCK_N / 2 rows
+    int num_sms;
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
 };
 
@@ -85,6 +88,10 @@ bool conv_tc_encode_2d(CUtensorMap* tm, const __half* base, long cols, long rows
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only
+// two-CTA variant (conv_pair.cu)
+bool conv_pair_supported(const ConvTcLaunch& L);
+cudaError_t conv_pair_set_attr(int block_n);
+cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
 // benchmark only: TMA load rate of [128 x 64] fp16 boxes; mode 0 = 2-D tiled over [N*H*W, C], 1 = im2col (3x3, pad 1)
 int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
                std::string* err);

@@ -574,6 +574,7 @@ bool conv_mega_prepare(MegaLaunch* out, const std::vector<ConvTcProblem>& layers
         const int taps = q.mode == CONV_MODE_TILED ? 1 : (q.mode == CONV_MODE_PACKED_ROW ? R : R * S);
         q.block_n = conv_mega_pick_block_n(q.c_out, int((M + kBlockM - 1) / kBlockM), taps * ((kc + kBlockK - 1) / kBlockK), num_sms);
         q.splits = 1;
+        q.pair = -1;  // the persistent kernel loads whole weight tiles
         ConvTcLaunch one;
         if (!conv_tc_prepare(&one, q, num_sms, err)) return false;
         MegaLayer& L = P.L[i];

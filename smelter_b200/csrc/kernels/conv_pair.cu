@@ -1,0 +1,513 @@
+// Two-CTA ("pair") variant of the tcgen05 implicit-GEMM convolution: a cluster of two CTAs on one TPC computes a 256 x BLOCK_N
+// output tile with `tcgen05.mma.cta_group::2`.  Each CTA loads the activation rows of its own 128-pixel half and only HALF of the
+// weight tile (BLOCK_N / 2 output channels); the tensor cores of both SMs read both halves.  Per SM and k-block that is
+// 16 KiB + BLOCK_N/2 x 128 B instead of 16 KiB + BLOCK_N x 128 B — the k-loop of the single-CTA kernel is bound by the bytes a
+// 192 KiB operand ring can keep in flight, so fewer bytes per FLOP is k-loop speed.
+//
+// Protocol (leader = cluster rank 0):
+//   full[s]       lives in the leader: its A and its B producer each arrive.expect_tx the bytes of BOTH CTAs' loads of that operand;
+//                 the TMA loads of both CTAs are the `.cta_group::2` forms and complete the leader's barrier.
+//   empty[s]      one per CTA, arrived by the leader's `tcgen05.commit.cta_group::2 ... multicast::cluster` (mask 0b11).
+//   tmem_full[a]  one per CTA, same multicast commit; each CTA's epilogue drains its own 128 TMEM lanes.
+//   tmem_empty[a] lives in the leader: arrivals from the epilogue threads of both CTAs (remote arrive from the peer).
+//   Only the leader's MMA warp issues MMAs; the peer's takes part in the cta_group::2 TMEM allocation only.
+// Everything else (operand modes, epilogue, fusion, PDL) is conv_igemm.cu's.  Default for 64/128/256-column tiles without split-K
+// (same-box A/B on ResNet-50: -1.2 % step time at batch 32, +6..8 % images/s at batch 128/256); SMELTER_NO_PAIR=1 turns it off.
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+#include "conv_igemm.h"
+#include "ptx.cuh"
+
+namespace smelter {
+namespace k {
+
+using namespace ptx;
+
+namespace {
+
+constexpr int kBlockM = 128;  // rows per CTA; the pair's MMA is M = 256
+constexpr int kBlockK = 64;
+constexpr int kThreads = 512;
+constexpr int kNumProducers = 4;
+constexpr int kNumBProducers = 3;
+constexpr int kBProducerWarp0 = 13;
+constexpr int kEpilogueWarp0 = 4;
+constexpr int kEpilogueWarps = 8;
+constexpr int kMmaWarp = 12;
+constexpr uint32_t kABytes = kBlockM * kBlockK * 2;
+constexpr int kChunkN = 64;
+constexpr uint32_t kEpiBufBytes = 32 * kChunkN * 2;
+constexpr uint32_t kBiasSlotBytes = kChunkN * 4;
+constexpr uint32_t kBarrierBytes = 512;
+constexpr uint32_t kSmemLimit = 227 * 1024;
+constexpr uint32_t kPeerMask = 0xFEFFFFFFu;                // clears the CTA-rank bit of a shared::cluster address -> the leader's copy
+constexpr long long kSpinLimitCycles = 4000000000LL;      // a broken hand-shake traps instead of hanging the GPU
+
+template <int BLOCK_N, bool HAS_RES>
+struct Cfg {
+    static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // this CTA's half of the weight tile
+    static constexpr uint32_t kStageBytes = kABytes + kBBytes;
+    static constexpr int kEpiBufs = HAS_RES ? 2 : 1;
+    static constexpr uint32_t kEpiBytes = kEpilogueWarps * (kEpiBufs * kEpiBufBytes + kBiasSlotBytes);
+    static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - kBarrierBytes) / kStageBytes);
+    static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
+    static constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
+    static constexpr int kProducers = kStages < kNumProducers ? kStages : kNumProducers;
+    static constexpr int kBProducers = kStages < kNumBProducers ? kStages : kNumBProducers;
+    static constexpr int kChunks = BLOCK_N / kChunkN;
+    static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + kBarrierBytes;
+};
+
+// ---- cta_group::2 / cluster forms of the PTX wrappers -------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar_cluster_addr) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar_cluster_addr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > kSpinLimitCycles) __trap();
+    }
+}
+__device__ __forceinline__ void tma2_load_2d(const void* desc, uint32_t leader_bar, uint32_t dst, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_3d(const void* desc, uint32_t leader_bar, uint32_t dst, int c0, int c1, int c2) {
+    asm volatile("cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_bar), "r"(c0), "r"(c1), "r"(c2)
+                 : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d(const void* desc, uint32_t leader_bar, uint32_t dst, int c, int w, int h, int n, uint16_t off_w,
+                                                    uint16_t off_h) {
+    asm volatile("cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(desc)), "r"(leader_bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(off_w), "h"(off_h)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem2_alloc(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem2_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem2_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+        "}\n"
+        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit(uint32_t bar) {  // arrives on `bar` in BOTH CTAs when the MMAs issued so far have retired
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar), "h"(uint16_t(3)) : "memory");
+}
+
+__device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
+
+template <int kCols, bool HAS_RES>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
+                                              bool is_sigmoid, __half2 lo2, __half2 hi2) {
+    constexpr int kGroups = kCols / 8;
+    uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
+    uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
+    if (HAS_RES) nrv = ld_shared_v4(rowbuf + (sw << 4));
+#pragma unroll
+    for (int g = 0; g < kGroups; ++g) {
+        const uint4 bq0 = nb0, bq1 = nb1, rv = nrv;
+        if (g + 1 < kGroups) {
+            nb0 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u);
+            nb1 = ld_shared_v4(bias_slot + uint32_t(g + 1) * 32u + 16u);
+            if (HAS_RES) nrv = ld_shared_v4(rowbuf + ((uint32_t(g + 1) ^ sw) << 4));
+        }
+        float f[8];
+        f[0] = __uint_as_float(v[g * 8 + 0]) + __uint_as_float(bq0.x); f[1] = __uint_as_float(v[g * 8 + 1]) + __uint_as_float(bq0.y);
+        f[2] = __uint_as_float(v[g * 8 + 2]) + __uint_as_float(bq0.z); f[3] = __uint_as_float(v[g * 8 + 3]) + __uint_as_float(bq0.w);
+        f[4] = __uint_as_float(v[g * 8 + 4]) + __uint_as_float(bq1.x); f[5] = __uint_as_float(v[g * 8 + 5]) + __uint_as_float(bq1.y);
+        f[6] = __uint_as_float(v[g * 8 + 6]) + __uint_as_float(bq1.z); f[7] = __uint_as_float(v[g * 8 + 7]) + __uint_as_float(bq1.w);
+        if (HAS_RES) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&rv);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const float2 r2 = __half22float2(rh[i]);
+                f[2 * i] += r2.x;
+                f[2 * i + 1] += r2.y;
+            }
+        }
+        if (is_sigmoid) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
+        }
+        __half2* oh = reinterpret_cast<__half2*>(&out[g]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
+    }
+}
+
+enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
+
+// One elected thread per producer warp (see conv_igemm.cu produce()).  Work items are (m-pair, n-tile): cluster c visits items
+// c, c + #clusters, ...; this CTA's rows are m-tile 2 * pair + rank, its weight half is rows n0 + rank * BLOCK_N / 2.
+template <int KIND, int BLOCK_N, bool HAS_RES>
+__device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelParams& p, uint32_t smem_base, uint32_t bar_base, int me, int n_prod,
+                                        int num_items, int total_kb, uint32_t rank) {
+    using C = Cfg<BLOCK_N, HAS_RES>;
+    constexpr uint32_t kTxBytes = KIND == PROD_B ? C::kBBytes : kABytes;
+    const int n_clusters = int(gridDim.x) >> 1;
+    const int kpt = p.kblocks_per_tap, taps_w = p.taps_w, nn = p.num_n_tiles;
+    uint32_t stage = uint32_t(me), phase = 0;
+    uint32_t full_addr = bar_base + 8u * stage;  // local address of full[stage]; the leader's copy is full_addr & kPeerMask
+    uint32_t dst = smem_base + stage * C::kStageBytes + (KIND == PROD_B ? kABytes : 0u);
+    int kb = me;
+    for (int item = int(blockIdx.x) >> 1; item < num_items; item += n_clusters) {
+        const int num_kb = total_kb;
+        if (kb < num_kb) {
+            const int pair = item / nn, n_tile = item - pair * nn;
+            const int m0 = (2 * pair + int(rank)) * kBlockM;
+            const int n0 = n_tile * BLOCK_N + int(rank) * (BLOCK_N / 2);
+            int cblk = 0, tap = 0, fs = 0, fr = 0;
+            int img = 0, base_h = 0, base_w = 0;
+            if (KIND != PROD_A_TILED) {
+                if (kb < 8) {
+                    cblk = kb;
+                    while (cblk >= kpt) { cblk -= kpt; ++tap; ++fs; }
+                    while (fs >= taps_w) { fs -= taps_w; ++fr; }
+                } else {
+                    tap = kb / kpt; cblk = kb - tap * kpt;
+                    fr = tap / taps_w; fs = tap - fr * taps_w;
+                }
+            }
+            if (KIND == PROD_A_IM2COL) {
+                img = m0 / p.PQ;
+                const int rem = m0 - img * p.PQ;
+                const int op = rem / p.Q;
+                const int oq = rem - op * p.Q;
+                base_h = p.corner_h + op * p.stride_h;
+                base_w = p.corner_w + oq * p.stride_w;
+            }
+#pragma unroll 1
+            for (; kb < num_kb; kb += n_prod) {
+                mbar_wait_bounded(full_addr + 8u * C::kStages, phase ^ 1u);  // local empty[stage]: the pair's MMAs have consumed it
+                // The leader's producer announces the bytes of BOTH CTAs' loads of this operand; the peer only issues its loads (their
+                // complete_tx lands on the leader's barrier, possibly before the announcement: the count may go negative inside a phase).
+                const uint32_t leader_full = full_addr & kPeerMask;
+                if (rank == 0) mbar_expect_tx(full_addr, 2u * kTxBytes);
+                if (KIND == PROD_A_TILED) tma2_load_2d(tm, leader_full, dst, kb * kBlockK, m0);
+                else if (KIND == PROD_A_IM2COL) tma2_load_im2col_4d(tm, leader_full, dst, cblk * kBlockK, base_w, base_h, img, uint16_t(fs * p.dil_w), uint16_t(fr * p.dil_h));
+                else tma2_load_3d(tm, leader_full, dst, cblk * kBlockK, tap, n0);
+                stage += uint32_t(n_prod);
+                full_addr += 8u * uint32_t(n_prod);
+                dst += uint32_t(n_prod) * C::kStageBytes;
+                if (stage >= uint32_t(C::kStages)) {
+                    stage -= uint32_t(C::kStages);
+                    phase ^= 1u;
+                    full_addr -= 8u * uint32_t(C::kStages);
+                    dst -= uint32_t(C::kStages) * C::kStageBytes;
+                }
+                if (KIND != PROD_A_TILED) {
+                    cblk += n_prod;
+                    while (cblk >= kpt) { cblk -= kpt; ++tap; ++fs; }
+                    while (fs >= taps_w) { fs -= taps_w; ++fr; }
+                }
+            }
+        }
+        kb -= num_kb;
+    }
+}
+
+template <int BLOCK_N, bool HAS_RES>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res, const ConvKernelParams p) {
+    using C = Cfg<BLOCK_N, HAS_RES>;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    if (smem_base & 1023u) __trap();
+    const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;
+    const uint32_t bias_base = epi_base + kEpilogueWarps * C::kEpiBufs * kEpiBufBytes;
+    const uint32_t bar_base = epi_base + C::kEpiBytes;
+    auto full_bar = [&](int s) { return bar_base + 8u * s; };
+    auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
+    auto tmem_full_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + a); };
+    auto tmem_empty_bar = [&](int a) { return bar_base + 8u * (2 * C::kStages + 2 + a); };
+    auto res_bar = [&](int w, int b) { return bar_base + 8u * (2 * C::kStages + 4 + w * 2 + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * C::kStages + 20);
+    static_assert(8u * (2 * C::kStages + 21) <= kBarrierBytes, "barrier region too small");
+    static_assert(C::kSmemBytes <= kSmemLimit, "shared memory budget");
+    static_assert(C::kStageBytes % 1024 == 0, "stages must keep the 1024-byte alignment of the swizzled tiles");
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int n_clusters = int(gridDim.x) >> 1;
+    const int cluster_id = int(blockIdx.x) >> 1;
+    const int num_pairs = (p.num_m_tiles + 1) / 2;
+    const int num_items = num_pairs * p.num_n_tiles;
+    const int total_kb = p.num_taps * p.kblocks_per_tap;
+    const int my_tiles = cluster_id < num_items ? (num_items - 1 - cluster_id) / n_clusters + 1 : 0;
+    constexpr bool kSplit = C::kChunks >= 2;  // both epilogue groups share every tile (see conv_igemm.cu)
+
+    if (warp == 0 && lane == 0) {
+        prefetch_tensormap(&tm_a);
+        prefetch_tensormap(&tm_b);
+        prefetch_tensormap(&tm_out);
+        if (HAS_RES) prefetch_tensormap(&tm_res);
+    }
+    if (warp == 1) {
+        if (lane < C::kStages) {
+            mbar_init(full_bar(lane), 2);   // the leader's A and B producer, each announcing both CTAs' bytes (only the leader's copy is used)
+            mbar_init(empty_bar(lane), 1);  // the leader's multicast commit
+        } else if (lane < C::kStages + 2) {
+            mbar_init(tmem_full_bar(lane - C::kStages), 1);
+            mbar_init(tmem_empty_bar(lane - C::kStages), 2 * (kSplit ? 256 : 128));  // epilogue threads of both CTAs (leader's copy)
+        } else if (lane >= 16) {
+            mbar_init(res_bar((lane - 16) >> 1, lane & 1), 1);
+        }
+        fence_barrier_init();
+    }
+    if (warp == kMmaWarp) {
+        tmem2_alloc(tmem_slot, C::kTmemCols);
+        tmem2_relinquish();
+    }
+    tc_fence_before();
+    cluster_sync_all();  // both CTAs' barriers exist before anybody arrives remotely or multicasts
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot_ptr;
+    if (p.use_pdl) grid_dep_launch_dependents();
+
+    if (warp < kNumProducers || warp >= kBProducerWarp0) {
+        const bool is_a = warp < kNumProducers;
+        const int me = is_a ? warp : warp - kBProducerWarp0;
+        const int n_prod = is_a ? C::kProducers : C::kBProducers;
+        if (elect_one() && me < n_prod) {
+            if (is_a) {
+                if (p.use_pdl) grid_dep_wait();
+                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
+                else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
+            } else {
+                produce<PROD_B, BLOCK_N, HAS_RES>(&tm_b, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
+            }
+        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (leader CTA only) =================
+        constexpr uint32_t idesc = make_idesc_f16(2 * kBlockM, BLOCK_N);
+        constexpr uint64_t desc_hi = (uint64_t(1024 >> 4) << 32) | (uint64_t(1) << 46) | (uint64_t(2) << 61);
+        constexpr uint32_t desc_lbo = 1u << 16;
+        const uint32_t a_lo0 = ((smem_base & 0x3FFFFu) >> 4) | desc_lbo;
+        constexpr uint32_t kStage16 = C::kStageBytes >> 4;
+        constexpr uint32_t kB16 = kABytes >> 4;
+        if (leader && elect_one()) {
+            uint32_t stage = 0, phase = 0;
+            uint32_t a_lo = a_lo0;
+            uint32_t full_addr = bar_base;
+            auto kblock = [&](uint32_t tmem_d, uint32_t first_accumulate) {
+                mbar_wait_bounded(full_addr, phase);
+                tc_fence_after();
+                const uint64_t a_desc = desc_hi | uint64_t(a_lo);
+                const uint64_t b_desc = a_desc + kB16;
+                umma2_f16(tmem_d, a_desc, b_desc, idesc, first_accumulate);
+                umma2_f16(tmem_d, a_desc + 2, b_desc + 2, idesc, 1u);
+                umma2_f16(tmem_d, a_desc + 4, b_desc + 4, idesc, 1u);
+                umma2_f16(tmem_d, a_desc + 6, b_desc + 6, idesc, 1u);
+                umma2_commit(full_addr + 8u * C::kStages);  // empty[stage] in both CTAs
+                a_lo += kStage16;
+                full_addr += 8u;
+                if (++stage == uint32_t(C::kStages)) { stage = 0; phase ^= 1u; a_lo = a_lo0; full_addr = bar_base; }
+            };
+            for (int t = 0; t < my_tiles; ++t) {
+                const int acc = t & 1;
+                mbar_wait_bounded(tmem_empty_bar(acc), ((uint32_t(t) >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + uint32_t(acc * BLOCK_N);
+                kblock(tmem_d, 0u);
+                int kb = 1;
+#pragma unroll 1
+                for (; kb + 1 < total_kb; kb += 2) {
+                    kblock(tmem_d, 1u);
+                    kblock(tmem_d, 1u);
+                }
+                if (kb < total_kb) kblock(tmem_d, 1u);
+                umma2_commit(tmem_full_bar(acc));  // accumulator complete -> the epilogues of both CTAs
+            }
+        }
+    } else {
+        // ================= epilogue (warps 4..11), each CTA drains its own 128 accumulator rows =================
+        if (p.use_pdl) grid_dep_wait();
+        const int ewarp = warp - kEpilogueWarp0;
+        const int group = ewarp >> 2;
+        const int ew = ewarp & 3;
+        const uint32_t buf0 = epi_base + uint32_t(ewarp) * uint32_t(C::kEpiBufs) * kEpiBufBytes;
+        const uint32_t bias_slot = bias_base + uint32_t(ewarp) * kBiasSlotBytes;
+        const uint32_t row_off = uint32_t(lane) * 128u;
+        const uint32_t sw = uint32_t(lane & 7);
+        const uint64_t pol_drop = l2_policy_evict_first();
+        const bool is_sigmoid = p.act == ACT_SIGMOID;
+        const __half2 lo2 = __float2half2_rn(p.act == ACT_RELU ? 0.f : (p.act == ACT_CLIP ? p.clip_lo : -INFINITY));
+        const __half2 hi2 = __float2half2_rn(p.act == ACT_CLIP ? p.clip_hi : INFINITY);
+        constexpr int kCPW = kSplit ? C::kChunks / 2 : C::kChunks;
+        const int group_tiles = kSplit ? my_tiles : (my_tiles > group ? (my_tiles - group + 1) / 2 : 0);
+        const int n_items = group_tiles * kCPW;
+        auto item_coords = [&](int item, int* m_row0, int* col0) {
+            const int gt = item / kCPW;
+            const int j = item - gt * kCPW;
+            const int c = kSplit ? group + 2 * j : j;
+            const int work = cluster_id + (kSplit ? gt : 2 * gt + group) * n_clusters;
+            const int pair = work / p.num_n_tiles;
+            const int n_tile = work - pair * p.num_n_tiles;
+            *m_row0 = (2 * pair + int(rank)) * kBlockM + ew * 32;
+            *col0 = n_tile * BLOCK_N + c * kChunkN;
+        };
+        auto prefetch_res = [&](int item) {
+            int m_row0, col0;
+            item_coords(item, &m_row0, &col0);
+            const int b = item & 1;
+            fence_proxy_async_smem();
+            mbar_expect_tx(res_bar(ewarp, b), kEpiBufBytes);
+            if (p.l2_hints & 2) tma_load_2d_hint(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0, pol_drop);
+            else tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0);
+        };
+        if (HAS_RES && n_items > 0 && lane == 0) prefetch_res(0);
+        float2 bias_next = make_float2(0.f, 0.f);
+        if (n_items > 0) {
+            int m_row0, col0;
+            item_coords(0, &m_row0, &col0);
+            bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
+        }
+        uint32_t res_phase = 0;
+        int item = 0;
+        for (int gt = 0; gt < group_tiles; ++gt) {
+            const int acc = kSplit ? (gt & 1) : group;
+            const uint32_t acc_parity = uint32_t(kSplit ? (gt >> 1) : gt) & 1u;
+            mbar_wait_bounded(tmem_full_bar(acc), acc_parity);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
+#pragma unroll 1
+            for (int j = 0; j < kCPW; ++j, ++item) {
+                int m_row0, col0;
+                item_coords(item, &m_row0, &col0);
+                const int c = kSplit ? group + 2 * j : j;
+                const int b = HAS_RES ? (item & 1) : 0;
+                if (HAS_RES && lane == 0 && item + 1 < n_items) {
+                    tma_store_wait_read<0>();
+                    prefetch_res(item + 1);
+                }
+                asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
+                if (item + 1 < n_items) {
+                    int nm, ncol0;
+                    item_coords(item + 1, &nm, &ncol0);
+                    bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + ncol0) + lane);
+                }
+                uint32_t v[kChunkN];
+                tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
+                tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + 32);
+                tmem_ld_wait();
+                if (j == kCPW - 1) {  // hand the accumulator back to the leader's MMA warp (remote arrive from the peer CTA)
+                    tc_fence_before();
+                    mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);
+                }
+                if (HAS_RES) {
+                    mbar_wait_bounded(res_bar(ewarp, b), (res_phase >> b) & 1u);
+                    res_phase ^= 1u << b;
+                }
+                __syncwarp();
+                const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
+                uint4 out[kChunkN / 8];
+                epilogue_math<kChunkN, HAS_RES>(v, out, buf + row_off, sw, bias_slot, is_sigmoid, lo2, hi2);
+                if (!HAS_RES) {
+                    if (lane == 0) tma_store_wait_read<0>();
+                    __syncwarp();
+                }
+#pragma unroll
+                for (int g = 0; g < kChunkN / 8; ++g) st_shared_v4(buf + row_off + ((uint32_t(g) ^ sw) << 4), out[g]);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tm_out, buf, col0, m_row0);
+                    tma_store_commit();
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_read<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();  // nobody exits (or frees TMEM) while the other CTA may still signal its barriers or read its operands
+    if (warp == kMmaWarp) {
+        tc_fence_after();
+        tmem2_dealloc(tmem_base, C::kTmemCols);
+    }
+}
+
+template <int BLOCK_N>
+cudaError_t set_attr_t() {
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, false>::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, true>::kSmemBytes));
+}
+
+template <int BLOCK_N>
+cudaError_t launch_t(const ConvTcLaunch& L, int grid, cudaStream_t stream) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(unsigned(grid));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = L.p.has_residual ? Cfg<BLOCK_N, true>::kSmemBytes : Cfg<BLOCK_N, false>::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = L.use_pdl ? 2 : 1;
+    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, true>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, false>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
+}
+
+}  // namespace
+
+bool conv_pair_supported(const ConvTcLaunch& L) { return L.splits == 1 && (L.block_n == 64 || L.block_n == 128 || L.block_n == 256); }
+
+cudaError_t conv_pair_set_attr(int block_n) {
+    switch (block_n) {
+        case 64: return set_attr_t<64>();
+        case 128: return set_attr_t<128>();
+        case 256: return set_attr_t<256>();
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream) {
+    const int pairs = (L.p.num_m_tiles + 1) / 2;
+    const long items = long(pairs) * L.p.num_n_tiles;
+    const int grid = 2 * int(std::min<long>(items, num_sms / 2));
+    switch (L.block_n) {
+        case 64: return launch_t<64>(L, grid, stream);
+        case 128: return launch_t<128>(L, grid, stream);
+        case 256: return launch_t<256>(L, grid, stream);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+}  // namespace k
+}  // namespace smelter

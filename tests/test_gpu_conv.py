@@ -100,3 +100,34 @@ def test_linearity_at_full_size(ctx):
     for n_, co, hh, ww in idx:
         want = float(np.dot(x1[n_, :, hh, ww].astype(np.float64), wt[co, :, 0, 0].astype(np.float64)))
         assert abs(y1[n_, co, hh, ww] - want) <= 4e-3 * max(1.0, abs(want))
+
+
+_SINGLE_CTA = [c for c in CONV_CASES if c[0] in ("tiled_64_256_56", "tiled_256_64_56_res", "tiled_1024_2048_bn256", "im2col_3x3_64_56", "im2col_3x3_s2_128_56",
+                                                 "im2col_3x3_odd_16", "im2col_3x3_512_7", "rows_7x7_s2_stem")]
+
+
+@pytest.mark.parametrize("case", _SINGLE_CTA, ids=[c[0] for c in _SINGLE_CTA])
+def test_single_cta_kernel_matches_the_two_cta_default(ctx, case, monkeypatch):
+    """The default for 64/128/256-column tiles is the two-CTA cluster kernel (conv_pair.cu, tcgen05.mma.cta_group::2); the single-CTA
+    kernel behind SMELTER_NO_PAIR=1 must give bit-identical results (same k order, same fp32 accumulation, same epilogue)."""
+    from smelter_b200.api import Image, run_conv
+
+    name, shape, co, k, s, p, d, g, act, has_bias, has_res, force = case
+    rng = np.random.default_rng(11)
+    n, c, h, w = shape
+    x = rng.standard_normal(shape).astype(np.float16)
+    wt = (rng.standard_normal((co, c // g, k, k)) * np.sqrt(2.0 / (c // g * k * k))).astype(np.float16)
+    b = rng.standard_normal(co).astype(np.float32) if has_bias else None
+    oh = (h + 2 * p - (d * (k - 1) + 1)) // s + 1
+    ow = (w + 2 * p - (d * (k - 1) + 1)) // s + 1
+    r = rng.standard_normal((n, co, oh, ow)).astype(np.float16) if has_res else None
+
+    def run():
+        y, _ = run_conv(ctx, Image.fromArray(ctx, x), wt, b, stride=(s, s), pads=(p, p, p, p), dilation=(d, d), groups=g, act=act, clip=(0.0, 6.0),
+                        residual=Image.fromArray(ctx, r) if has_res else None, force_path=force)
+        return y.toHalfArray()
+
+    pair = run()
+    monkeypatch.setenv("SMELTER_NO_PAIR", "1")  # read when the launch is prepared
+    single = run()
+    assert np.array_equal(pair.view(np.uint16), single.view(np.uint16))

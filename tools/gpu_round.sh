@@ -18,6 +18,6 @@ timeout 900 ncu --set full --clock-control none --launch-skip 171 -c 57 -f -o /t
     python bench.py --steps 1 --warmup 3 --no-cpu > gpurun_out/ncu_full_$TAG.log 2>&1; echo "ncu full rc=$?"
 ncu -i /tmp/encode_$TAG.ncu-rep --page raw --csv > gpurun_out/encode_${TAG}_raw.csv 2>/dev/null
 # three representative conv launches with source correlation (3x3 im2col, 1x1 tiled + residual, stem)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_igemm --launch-skip 162 -c 4 -f -o gpurun_out/conv_src_$TAG \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:conv_ --launch-skip 162 -c 4 -f -o gpurun_out/conv_src_$TAG \
     python bench.py --steps 1 --warmup 3 --no-cpu > /dev/null 2>&1; echo "ncu src rc=$?"
 ls -la gpurun_out | tail -20; du -sh gpurun_out

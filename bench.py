@@ -27,6 +27,8 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
+# rank 0 prints ONE JSON line on stdout: NCCL's own banner ("NCCL version ...") goes to stderr
+os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 

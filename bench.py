@@ -27,8 +27,6 @@ import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
-# rank 0 prints ONE JSON line on stdout: NCCL's own banner ("NCCL version ...") goes to stderr
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
@@ -67,6 +65,23 @@ def ncu_conv_traffic():
         return sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_igemm" in r[ik] or "conv_mega" in r[ik] or "conv_pair" in r[ik])
     except (OSError, ValueError):
         return None
+
+
+class stdout_to_stderr:
+    """Rank 0 prints ONE JSON line on stdout; whatever libraries write to file descriptor 1 while the communicators come up
+    (NCCL's "NCCL version ..." banner) is sent to stderr instead."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
 
 
 class ClockSampler:
@@ -174,6 +189,8 @@ def run_native(args) -> int:
         raise SystemExit("bench.py: no CUDA device — this engine has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    quiet = stdout_to_stderr()
+    quiet.__enter__()  # until the weight replicas are in place (below)
     if world > 1:
         sdist.init_process_group("nccl")
     import torch.distributed as dist
@@ -200,6 +217,8 @@ def run_native(args) -> int:
         checksum, _ = nn.weightChecksum()
         if not sdist.all_equal(checksum, dev):
             raise SystemExit("weight replicas differ after the broadcast")
+    barrier()
+    quiet.__exit__()
 
     rng = np.random.default_rng(1 + rank)
     host_in = torch.empty((N_INPUT_SETS, B) + IMAGE, dtype=torch.float16).pin_memory()

@@ -314,7 +314,8 @@ def run_native(args) -> int:
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": ncu_conv_traffic(), "kernel": "conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> (53 conv + 1 gemm launches per step, aggregated)",
+                "traffic": ncu_conv_traffic(), "kernel": f"conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> ({len(conv)} conv/gemm launches per step, aggregated; "
+                          f"{sum('+conv1x1(' in p['desc'] for p in conv)} of them carry a folded 1x1 projection shortcut)",
                 "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": share,
                 "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
                 "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,

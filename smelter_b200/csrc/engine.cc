@@ -465,17 +465,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     auto pitch_of = [&](int v) { return round_up(values_[size_t(v)].shape.c, 8); };
     auto bytes_of = [&](int v) { const ImageShape& s = values_[size_t(v)].shape; return size_t(N) * s.h * s.w * round_up(s.c, 8) * 2; };
 
-    // ---- which convs read a graph input / need a materialised padded input (packed-row mode) ----
-    // last use of every root value (filter index); the output value lives forever
-    std::vector<int> last_use(values_.size(), -1);
-    for (size_t fi = 0; fi < filters_.size(); ++fi) {
-        const Filter& f = filters_[fi];
-        if (f.removed) continue;
-        for (int i : f.in) last_use[size_t(root_of(i))] = int(fi);
-        if (f.residual >= 0) last_use[size_t(root_of(f.residual))] = int(fi);
-    }
     const int out_root = root_of(output_value_);
-    last_use[size_t(out_root)] = int(filters_.size()) + 1;
 
     // shape part of the tensor-core conv problem of filter f (pointers are bound later)
     auto conv_problem = [&](const Filter& f, const std::vector<const Filter*>& stem_map) {
@@ -508,6 +498,63 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         (void)stem_map;
         return q;
     };
+    // ---- projection shortcuts folded into the consuming convolution's k-loop ----
+    // A residual block whose skip path is a 1x1 convolution (ResNet "downsample"): conv3(a) + conv_ds(x) is one GEMM over the
+    // concatenated K axis, so the shortcut runs as extra k-blocks of conv3's launch (kernels/conv_pair.cu) -- no launch of its
+    // own, and its output never exists in HBM.  side_of[conv3] = index of the absorbed shortcut filter.
+    std::vector<int> side_of(filters_.size(), -1);
+    std::vector<char> absorbed(filters_.size(), 0);
+    auto side_fields = [&](k::ConvTcProblem& q, const Filter& g) {
+        const ImageShape gs = values_[size_t(g.in[0])].shape;
+        q.side_h = gs.h; q.side_w = gs.w;
+        q.side_c_in = g.c_in_g; q.side_c_in_pitch = round_up(gs.c, 8);
+        q.side_stride_h = g.stride_h; q.side_stride_w = g.stride_w;
+    };
+    const char* mega_env = getenv("SMELTER_MEGA");
+    const bool mega_on = mega_env && atoi(mega_env) != 0;
+    if (!getenv("SMELTER_NO_SIDE") && !mega_on) {
+        std::vector<int> reads(values_.size(), 0), producer(values_.size(), -1);
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& f = filters_[fi];
+            if (f.removed) continue;
+            for (int i : f.in) ++reads[size_t(root_of(i))];
+            if (f.residual >= 0) ++reads[size_t(root_of(f.residual))];
+            if (f.out >= 0 && values_[size_t(f.out)].alias_of < 0) producer[size_t(f.out)] = int(fi);
+        }
+        auto plain_tc_conv = [&](const Filter& f) {
+            return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
+        };
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& f = filters_[fi];
+            if (f.removed || !plain_tc_conv(f) || f.residual < 0) continue;
+            const int r = root_of(f.residual);
+            const int gi = producer[size_t(r)];
+            if (gi < 0 || gi >= int(fi) || r == out_root || reads[size_t(r)] != 1) continue;
+            const Filter& g = filters_[size_t(gi)];
+            if (!plain_tc_conv(g) || absorbed[size_t(gi)] || side_of[size_t(gi)] >= 0 || g.k_h != 1 || g.k_w != 1 || g.pads[0] || g.pads[1] || g.pads[2] ||
+                g.pads[3] || g.act != k::ACT_NONE || g.residual >= 0 || g.c_out != f.c_out)
+                continue;
+            k::ConvTcProblem q = conv_problem(f, {});
+            side_fields(q, g);
+            q.side_x = reinterpret_cast<const __half*>(uintptr_t(16));  // shape query only: any non-null pointer
+            if (!k::conv_tc_side_supported(q, num_sms)) continue;
+            side_of[fi] = gi;
+            absorbed[size_t(gi)] = 1;
+        }
+    }
+
+    // last use of every root value (filter index); the output value lives forever.  An absorbed shortcut's input is read by the
+    // convolution that absorbed it.
+    std::vector<int> last_use(values_.size(), -1);
+    for (size_t fi = 0; fi < filters_.size(); ++fi) {
+        const Filter& f = filters_[fi];
+        if (f.removed || absorbed[fi]) continue;
+        for (int i : f.in) last_use[size_t(root_of(i))] = int(fi);
+        if (f.residual >= 0 && side_of[fi] < 0) last_use[size_t(root_of(f.residual))] = int(fi);
+        if (side_of[fi] >= 0) last_use[size_t(root_of(filters_[size_t(side_of[fi])].in[0]))] = int(fi);
+    }
+    last_use[size_t(out_root)] = int(filters_.size()) + 1;
+
     // ---- offsets (two passes: first compute offsets, then allocate, then bind pointers) ----
     ArenaAlloc arena;
     std::vector<size_t> off(values_.size(), size_t(-1));
@@ -538,8 +585,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     std::vector<std::vector<size_t>> runs;
     // Opt-in (SMELTER_MEGA=1): on ResNet-50 / batch 32 the persistent kernel currently ties with per-layer launches (the
     // ~6.5 us store -> fence -> counter -> poll -> load dependency hop costs what a PDL kernel boundary costs).
-    const char* mega_env = getenv("SMELTER_MEGA");
-    if (mega_env && atoi(mega_env) != 0) {
+    if (mega_on) {
         std::vector<size_t> cur;
         auto flush_run = [&]() {
             if (cur.size() >= 2) {
@@ -575,7 +621,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     for (int v : input_values_) off[size_t(v)] = arena.alloc(input_bytes(v));
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
-        if (f.removed) continue;
+        if (f.removed || absorbed[fi]) continue;
         // temporaries first (live only during this filter)
         if (f.kind == FilterKind::Conv && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) &&
             stem_of[size_t(root_of(f.in[0]))] != &f) {
@@ -588,7 +634,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             scratch[fi].bytes = size_t(N) * tq.h * tq.w * tq.c_in_pitch * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
-        if (f.kind == FilterKind::Conv && f.conv_mode != 4) {
+        if (f.kind == FilterKind::Conv && f.conv_mode != 4 && side_of[fi] < 0) {
             const k::ConvTcPlanInfo info = k::conv_tc_plan(conv_problem(f, stem_of), num_sms);
             if (info.splits > 1) {
                 scratch2[fi].bytes = info.ws_bytes;
@@ -617,7 +663,8 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         // release inputs whose last use is this filter
         std::vector<int> roots;
         for (int i : f.in) roots.push_back(root_of(i));
-        if (f.residual >= 0) roots.push_back(root_of(f.residual));
+        if (f.residual >= 0 && side_of[fi] < 0) roots.push_back(root_of(f.residual));
+        if (side_of[fi] >= 0) roots.push_back(root_of(filters_[size_t(side_of[fi])].in[0]));
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
@@ -688,7 +735,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     void* mega_identity = nullptr;
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
-        if (f.removed) continue;
+        if (f.removed || absorbed[fi]) continue;
         const ImageShape is = values_[size_t(f.in[0])].shape;
         const ImageShape osz = values_[size_t(f.out)].shape;
         const int icp = round_up(is.c, 8), ocp = round_up(osz.c, 8);
@@ -700,9 +747,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             case FilterKind::Conv: {
                 const float* bias = reinterpret_cast<const float*>(wbase + f.bias_off);
                 const __half* w = reinterpret_cast<const __half*>(wbase + f.w_off);
-                const __half* res = f.residual >= 0 ? ptr_of(f.residual) : nullptr;
+                const Filter* side = side_of[fi] >= 0 ? &filters_[size_t(side_of[fi])] : nullptr;
+                const __half* res = f.residual >= 0 && !side ? ptr_of(f.residual) : nullptr;
                 std::string suffix = f.act == k::ACT_RELU ? "+relu" : f.act == k::ACT_CLIP ? "+clip" : f.act == k::ACT_SIGMOID ? "+sigmoid" : "";
                 if (res) suffix = "+add" + suffix;
+                if (side) suffix = "+conv1x1(" + values_[size_t(side->in[0])].name + ")" + suffix;
                 const double flops = f.transposed ? 2.0 * N * is.h * is.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w
                                                   : 2.0 * N * osz.h * osz.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w;
                 if (f.conv_mode == 4) {
@@ -715,6 +764,15 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 }
                 k::ConvTcProblem q = conv_problem(f, stem_of);
                 q.x = x; q.w_packed = w; q.bias = bias; q.residual = res; q.y = y;
+                double side_bytes = 0, side_flops = 0;
+                if (side) {
+                    side_fields(q, *side);
+                    q.side_x = ptr_of(side->in[0]);
+                    q.side_w_packed = reinterpret_cast<const __half*>(wbase + side->w_off);
+                    q.side_bias = reinterpret_cast<const float*>(wbase + side->bias_off);
+                    side_flops = 2.0 * N * osz.h * osz.w * double(f.c_out) * q.side_c_in;
+                    side_bytes = double(N) * q.side_h * q.side_w * q.side_c_in_pitch * 2 / (q.side_stride_h * q.side_stride_w) + double(f.c_out) * q.side_c_in * 2;
+                }
                 // L2 eviction priority (measured on ResNet-50 / batch 32, same-box A/B: ~1 % of the step): a residual operand read for
                 // the last time is marked evict_first so it does not push the freshly written block output out of L2.  (Writing
                 // skip tensors evict_last as well measured slightly worse.)
@@ -784,8 +842,8 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                 const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
-                         [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops,
-                         io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0));
+                         [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops + side_flops,
+                         io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0) + side_bytes);
                 plan->steps.back().tensor = true;
                 break;
             }

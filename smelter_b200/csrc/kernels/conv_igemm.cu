@@ -748,7 +748,8 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
     const int m_tiles = int((M + kBlockM - 1) / kBlockM);
     const int kc = q.mode == CONV_MODE_PACKED_ROW ? S * q.c_in_pitch : q.c_in_pitch;
     const int taps = q.mode == CONV_MODE_TILED ? 1 : (q.mode == CONV_MODE_PACKED_ROW ? R : R * S);
-    const int num_kb = taps * ((kc + kBlockK - 1) / kBlockK);
+    const int side_kb = q.side_x ? (q.side_c_in_pitch + kBlockK - 1) / kBlockK : 0;
+    const int num_kb = taps * ((kc + kBlockK - 1) / kBlockK) + side_kb;
     ConvTcPlanInfo best{};
     best.block_n = q.block_n ? q.block_n : conv_tc_pick_block_n(q.c_out, m_tiles, num_sms);
     best.splits = 1;
@@ -774,7 +775,7 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
         const int v = atoi(force);
         if (v == 32 || v == 64 || v == 128 || v == 256) best.block_n = v;
     }
-    const bool forced = q.block_n != 0 || q.splits == 1 || getenv("SMELTER_FORCE_BN") || getenv("SMELTER_NO_SPLITK");
+    const bool forced = q.block_n != 0 || q.splits == 1 || q.side_x || getenv("SMELTER_FORCE_BN") || getenv("SMELTER_NO_SPLITK");
     if (q.splits > 1) {
         best.splits = q.splits;
     } else if (!forced && q.c_out > 32) {
@@ -814,6 +815,103 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
     best.counter_bytes = best.splits > 1 ? size_t(tiles) * sizeof(unsigned int) : 0;
     return best;
 }
+
+bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms) {
+    if (!q.side_x || q.pair < 0 || (q.pair == 0 && getenv("SMELTER_NO_PAIR")) || num_sms < 2 || q.splits > 1) return false;
+    if (q.side_c_in_pitch % 8 || q.side_stride_h > 8 || q.side_stride_w > 8) return false;
+    auto pairable = [&](const ConvTcProblem& pq) {
+        const ConvTcPlanInfo info = conv_tc_plan(pq, num_sms);
+        return info.splits == 1 && (info.block_n == 64 || info.block_n == 128 || info.block_n == 256);
+    };
+    ConvTcProblem alone = q;
+    alone.side_x = nullptr;
+    return pairable(alone) && pairable(q);
+}
+
+namespace {
+
+// A-operand map of a TILED / IM2COL / PACKED_ROW problem: [128 pixels x 64 channels] boxes, 128-byte swizzle.
+bool encode_a_map(CUtensorMap* tm, int mode, const __half* x, int n, int h, int w, int c_in_pitch, int kc, long M, int R, int S, int Q,
+                  int stride_h, int stride_w, int dil_h, int dil_w, int pad_t, int pad_l, int pad_b, int pad_r, std::string* err) {
+    if (mode == CONV_MODE_TILED) {
+        cuuint64_t dims[2] = {cuuint64_t(kc), cuuint64_t(M)};
+        cuuint64_t strides[1] = {cuuint64_t(kc) * 2};
+        cuuint32_t box[2] = {kBlockK, kBlockM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(x), dims, strides, box, estr,
+                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) {
+            if (err) *err = "cuTensorMapEncodeTiled(activations) failed: " + std::to_string(int(r));
+            return false;
+        }
+        return true;
+    }
+    cuuint64_t dims[4];
+    cuuint64_t strides[3];
+    int lower[2], upper[2];       // {W, H}
+    cuuint32_t estr[4];
+    if (mode == CONV_MODE_IM2COL) {
+        dims[0] = cuuint64_t(kc); dims[1] = cuuint64_t(w); dims[2] = cuuint64_t(h); dims[3] = cuuint64_t(n);
+        strides[0] = cuuint64_t(kc) * 2;
+        strides[1] = strides[0] * w;
+        strides[2] = strides[1] * h;
+        lower[0] = -pad_l; lower[1] = -pad_t;
+        upper[0] = pad_r - (S - 1) * dil_w;
+        upper[1] = pad_b - (R - 1) * dil_h;
+        estr[0] = 1; estr[1] = cuuint32_t(stride_w); estr[2] = cuuint32_t(stride_h); estr[3] = 1;
+    } else {  // packed row: virtual tensor {S*8, Q, H, N}, overlapping W stride
+        // When the last window of a row can read a full 64-element (128-byte) run without leaving the image row, expose
+        // 64 "channels": the extra elements are the next pixel's data and meet zero weights (the B box zero-fills past
+        // S*8), and the TMA no longer has to zero-fill the tail of every 112-byte row.
+        const long last_window_end = long(Q - 1) * stride_w * c_in_pitch + kBlockK;
+        const int kc_a = (kc < kBlockK && last_window_end <= long(w) * c_in_pitch) ? kBlockK : kc;
+        dims[0] = cuuint64_t(kc_a); dims[1] = cuuint64_t(Q); dims[2] = cuuint64_t(h); dims[3] = cuuint64_t(n);
+        strides[0] = cuuint64_t(stride_w) * c_in_pitch * 2;
+        strides[1] = cuuint64_t(w) * c_in_pitch * 2;
+        strides[2] = strides[1] * h;
+        lower[0] = 0; lower[1] = 0;
+        upper[0] = 0; upper[1] = -(R - 1) * dil_h;
+        estr[0] = 1; estr[1] = 1; estr[2] = cuuint32_t(stride_h); estr[3] = 1;
+    }
+    if (lower[0] < -128 || lower[1] < -128 || upper[0] < -128 || upper[1] < -128 || upper[0] > 127 || upper[1] > 127 ||
+        estr[1] > 8 || estr[2] > 8) {
+        if (err) *err = "conv: padding/stride outside the im2col TMA range";
+        return false;
+    }
+    CUresult r = g_encode_im2col(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(x), dims, strides, lower, upper,
+                                 kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeIm2col failed: " + std::to_string(int(r));
+        return false;
+    }
+    // Driver quirk (drivers <= CUDA 13.1): im2col descriptors of tensors smaller than 128 KiB get a flag bit
+    // that must be cleared, otherwise loads fault.  Same workaround NVIDIA's CUTLASS applies.
+    if (g_driver_version <= 13010) {
+        const size_t bytes = size_t(strides[2]) * n;
+        if (bytes < 131072) reinterpret_cast<uint64_t*>(tm)[1] &= ~(1ull << 21);
+    }
+    return true;
+}
+
+// Weight map [Cout][taps][kc] with [box_rows x 1 x 64] boxes.
+bool encode_b_map(CUtensorMap* tm, const __half* w_packed, int kc, int taps, int c_out, int box_rows, std::string* err) {
+    cuuint64_t dims[3] = {cuuint64_t(kc), cuuint64_t(taps), cuuint64_t(c_out)};
+    cuuint64_t strides[2] = {cuuint64_t(kc) * 2, cuuint64_t(kc) * 2 * taps};
+    cuuint32_t box[3] = {kBlockK, 1, cuuint32_t(box_rows)};
+    cuuint32_t estr[3] = {1, 1, 1};
+    CUresult r = g_encode_tiled(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(w_packed), dims, strides, box, estr,
+                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        if (err) *err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r));
+        return false;
+    }
+    return true;
+}
+
+}  // namespace
 
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err) {
     if (!load_driver_entry_points(err)) return false;
@@ -898,24 +996,11 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     L->splits = plan.splits;
     L->flops = 2.0 * double(M) * q.c_out * double(q.c_in) * R * S;
 
-    // ---- B: packed weights [Cout][taps][kc] ----
-    {
-        cuuint64_t dims[3] = {cuuint64_t(kc), cuuint64_t(taps), cuuint64_t(q.c_out)};
-        cuuint64_t strides[2] = {cuuint64_t(kc) * 2, cuuint64_t(kc) * 2 * taps};
-        // two-CTA clusters (conv_pair.cu): each CTA loads half of the weight tile
-        const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
-        L->pair = want_pair ? 1 : 0;
-        L->num_sms = num_sms;
-        cuuint32_t box[3] = {kBlockK, 1, cuuint32_t(want_pair ? block_n / 2 : block_n)};
-        cuuint32_t estr[3] = {1, 1, 1};
-        CUresult r = g_encode_tiled(&L->tm_b, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 3, const_cast<__half*>(q.w_packed), dims, strides,
-                                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            if (err) *err = "cuTensorMapEncodeTiled(weights) failed: " + std::to_string(int(r));
-            return false;
-        }
-    }
+    // ---- B: packed weights [Cout][taps][kc]; two-CTA clusters (conv_pair.cu): each CTA loads half of the weight tile ----
+    const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
+    L->pair = want_pair ? 1 : 0;
+    L->num_sms = num_sms;
+    if (!encode_b_map(&L->tm_b, q.w_packed, kc, taps, q.c_out, want_pair ? block_n / 2 : block_n, err)) return false;
     // ---- D (and the residual, same geometry): [M, out_pitch] fp16, stored / loaded as [32 rows x 64 cols] swizzled boxes ----
     for (int which = 0; which < 2; ++which) {
         const __half* base = which == 0 ? q.y : (q.residual ? q.residual : q.y);
@@ -932,64 +1017,25 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
         }
     }
     // ---- A ----
-    if (mode == CONV_MODE_TILED) {
-        cuuint64_t dims[2] = {cuuint64_t(kc), cuuint64_t(M)};
-        cuuint64_t strides[1] = {cuuint64_t(kc) * 2};
-        cuuint32_t box[2] = {kBlockK, kBlockM};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = g_encode_tiled(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(q.x), dims, strides, box, estr,
-                                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            if (err) *err = "cuTensorMapEncodeTiled(activations) failed: " + std::to_string(int(r));
+    if (!encode_a_map(&L->tm_a, mode, q.x, q.n, q.h, q.w, q.c_in_pitch, kc, M, R, S, Q, q.stride_h, q.stride_w, q.dil_h, q.dil_w, q.pad_t, q.pad_l,
+                      q.pad_b, q.pad_r, err))
+        return false;
+    // ---- projection shortcut: 1x1 / no padding over side_x, sampled with the shortcut's stride onto the same P x Q grid ----
+    if (q.side_x) {
+        if (!want_pair) { if (err) *err = "conv: a projection shortcut needs the two-CTA kernel (see conv_tc_side_supported)"; return false; }
+        const int sp = (q.side_h - 1) / q.side_stride_h + 1, sq = (q.side_w - 1) / q.side_stride_w + 1;
+        if (sp != P || sq != Q || !q.side_w_packed) { if (err) *err = "conv: projection shortcut does not produce the output's shape"; return false; }
+        const bool unit = q.side_stride_h == 1 && q.side_stride_w == 1;
+        p.side_mode = unit ? CONV_MODE_TILED : CONV_MODE_IM2COL;
+        p.side_kb = (q.side_c_in_pitch + kBlockK - 1) / kBlockK;
+        p.side_stride_h = q.side_stride_h;
+        p.side_stride_w = q.side_stride_w;
+        p.bias2 = q.side_bias;
+        if (!encode_a_map(&L->tm_a2, p.side_mode, q.side_x, q.n, q.side_h, q.side_w, q.side_c_in_pitch, q.side_c_in_pitch, M, 1, 1, Q, q.side_stride_h,
+                          q.side_stride_w, 1, 1, 0, 0, 0, 0, err))
             return false;
-        }
-    } else {
-        cuuint64_t dims[4];
-        cuuint64_t strides[3];
-        int lower[2], upper[2];       // {W, H}
-        cuuint32_t estr[4];
-        if (mode == CONV_MODE_IM2COL) {
-            dims[0] = cuuint64_t(kc); dims[1] = cuuint64_t(q.w); dims[2] = cuuint64_t(q.h); dims[3] = cuuint64_t(q.n);
-            strides[0] = cuuint64_t(kc) * 2;
-            strides[1] = strides[0] * q.w;
-            strides[2] = strides[1] * q.h;
-            lower[0] = -q.pad_l; lower[1] = -q.pad_t;
-            upper[0] = q.pad_r - (S - 1) * q.dil_w;
-            upper[1] = q.pad_b - (R - 1) * q.dil_h;
-            estr[0] = 1; estr[1] = cuuint32_t(q.stride_w); estr[2] = cuuint32_t(q.stride_h); estr[3] = 1;
-        } else {  // packed row: virtual tensor {S*8, Q, H, N}, overlapping W stride
-            // When the last window of a row can read a full 64-element (128-byte) run without leaving the image row, expose
-            // 64 "channels": the extra elements are the next pixel's data and meet zero weights (the B box zero-fills past
-            // S*8), and the TMA no longer has to zero-fill the tail of every 112-byte row.
-            const long last_window_end = long(Q - 1) * q.stride_w * q.c_in_pitch + kBlockK;
-            const int kc_a = (kc < kBlockK && last_window_end <= long(q.w) * q.c_in_pitch) ? kBlockK : kc;
-            dims[0] = cuuint64_t(kc_a); dims[1] = cuuint64_t(Q); dims[2] = cuuint64_t(q.h); dims[3] = cuuint64_t(q.n);
-            strides[0] = cuuint64_t(q.stride_w) * q.c_in_pitch * 2;
-            strides[1] = cuuint64_t(q.w) * q.c_in_pitch * 2;
-            strides[2] = strides[1] * q.h;
-            lower[0] = 0; lower[1] = 0;
-            upper[0] = 0; upper[1] = -(R - 1) * q.dil_h;
-            estr[0] = 1; estr[1] = 1; estr[2] = cuuint32_t(q.stride_h); estr[3] = 1;
-        }
-        if (lower[0] < -128 || lower[1] < -128 || upper[0] < -128 || upper[1] < -128 || upper[0] > 127 || upper[1] > 127 ||
-            estr[1] > 8 || estr[2] > 8) {
-            if (err) *err = "conv: padding/stride outside the im2col TMA range";
-            return false;
-        }
-        CUresult r = g_encode_im2col(&L->tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4, const_cast<__half*>(q.x), dims, strides, lower, upper,
-                                     kBlockK, kBlockM, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) {
-            if (err) *err = "cuTensorMapEncodeIm2col failed: " + std::to_string(int(r));
-            return false;
-        }
-        // Driver quirk (drivers <= CUDA 13.1): im2col descriptors of tensors smaller than 128 KiB get a flag bit
-        // that must be cleared, otherwise loads fault.  Same workaround NVIDIA's CUTLASS applies.
-        if (g_driver_version <= 13010) {
-            const size_t bytes = size_t(strides[2]) * q.n;
-            if (bytes < 131072) reinterpret_cast<uint64_t*>(&L->tm_a)[1] &= ~(1ull << 21);
-        }
+        if (!encode_b_map(&L->tm_b2, q.side_w_packed, q.side_c_in_pitch, 1, q.c_out, block_n / 2, err)) return false;
+        L->flops += 2.0 * double(M) * q.c_out * double(q.side_c_in);
     }
     return true;
 }

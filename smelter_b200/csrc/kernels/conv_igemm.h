@@ -38,6 +38,12 @@ struct ConvKernelParams {
     int debug_flags;         // perf experiments only (env SMELTER_CONV_DEBUG): 16 = producers skip the TMA loads (results wrong)
     int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
     int l2_hints;            // 1 = output stores evict_last (tensor re-read by later layers), 2 = residual loads evict_first (last use)
+    // Projection shortcut folded into the k-loop (conv_pair.cu only): after the main k-blocks, `side_kb` more k-blocks read a
+    // second activation tensor (tm_a2: 1x1, stride side_stride_*, no padding, same P x Q) against a second weight matrix (tm_b2).
+    int side_kb;             // 0 = none
+    int side_mode;           // CONV_MODE_TILED (stride 1) or CONV_MODE_IM2COL
+    int side_stride_h, side_stride_w;
+    const float* bias2;      // the shortcut's bias, added to `bias` in the epilogue (nullptr = none)
 };
 
 struct ConvTcProblem {
@@ -56,6 +62,12 @@ struct ConvTcProblem {
     int act;
     float clip_lo, clip_hi;
     int block_n;            // 0 = auto
+    // Optional projection shortcut y += conv1x1(side_x) + side_bias, accumulated in the same TMEM tile ahead of the activation
+    // (the 1x1 "downsample" convolution of a residual block: no separate launch, no round trip of its output through HBM).
+    const __half* side_x;   // NHWC [n, side_h, side_w, side_c_in_pitch]; nullptr = none
+    const __half* side_w_packed;  // [Cout][1][side_c_in_pitch]
+    const float* side_bias;
+    int side_h, side_w, side_c_in, side_c_in_pitch, side_stride_h, side_stride_w;
     int l2_hints;           // ConvKernelParams::l2_hints
     int pair;               // 1 = two-CTA clusters with cta_group::2 MMAs (conv_pair.cu); 0 = single-CTA kernel
     int splits;             // 0 = auto (conv_tc_plan), 1 = no split-K
@@ -69,9 +81,13 @@ struct ConvTcPlanInfo {
 };
 // Tile width and k-split choice for a problem (pure function of the shapes).
 ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms);
+// Whether a problem with a projection shortcut (side_*) can run as one launch: the two-CTA kernel without split-K must be the
+// choice for the problem both with and without the extra k-blocks.
+bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms);
 
 struct ConvTcLaunch {
     CUtensorMap tm_a, tm_b, tm_out, tm_res;
+    CUtensorMap tm_a2, tm_b2;  // projection shortcut operands (p.side_kb > 0)
     ConvKernelParams p;
     int block_n;
     int splits;

@@ -166,8 +166,8 @@ enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
 // One elected thread per producer warp (see conv_igemm.cu produce()).  Work items are (m-pair, n-tile): cluster c visits items
 // c, c + #clusters, ...; this CTA's rows are m-tile 2 * pair + rank, its weight half is rows n0 + rank * BLOCK_N / 2.
 template <int KIND, int BLOCK_N, bool HAS_RES>
-__device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelParams& p, uint32_t smem_base, uint32_t bar_base, int me, int n_prod,
-                                        int num_items, int total_kb, uint32_t rank) {
+__device__ __forceinline__ void produce(const CUtensorMap* tm, const CUtensorMap* tm_side, const ConvKernelParams& p, uint32_t smem_base, uint32_t bar_base,
+                                        int me, int n_prod, int num_items, int main_kb, uint32_t rank) {
     using C = Cfg<BLOCK_N, HAS_RES>;
     constexpr uint32_t kTxBytes = KIND == PROD_B ? C::kBBytes : kABytes;
     const int n_clusters = int(gridDim.x) >> 1;
@@ -176,8 +176,20 @@ __device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelP
     uint32_t full_addr = bar_base + 8u * stage;  // local address of full[stage]; the leader's copy is full_addr & kPeerMask
     uint32_t dst = smem_base + stage * C::kStageBytes + (KIND == PROD_B ? kABytes : 0u);
     int kb = me;
+    const int side_kb = p.side_kb;
+    const int num_kb = main_kb + side_kb;
+    auto advance = [&]() {
+        stage += uint32_t(n_prod);
+        full_addr += 8u * uint32_t(n_prod);
+        dst += uint32_t(n_prod) * C::kStageBytes;
+        if (stage >= uint32_t(C::kStages)) {
+            stage -= uint32_t(C::kStages);
+            phase ^= 1u;
+            full_addr -= 8u * uint32_t(C::kStages);
+            dst -= uint32_t(C::kStages) * C::kStageBytes;
+        }
+    };
     for (int item = int(blockIdx.x) >> 1; item < num_items; item += n_clusters) {
-        const int num_kb = total_kb;
         if (kb < num_kb) {
             const int pair = item / nn, n_tile = item - pair * nn;
             const int m0 = (2 * pair + int(rank)) * kBlockM;
@@ -203,7 +215,7 @@ __device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelP
                 base_w = p.corner_w + oq * p.stride_w;
             }
 #pragma unroll 1
-            for (; kb < num_kb; kb += n_prod) {
+            for (; kb < main_kb; kb += n_prod) {
                 mbar_wait_bounded(full_addr + 8u * C::kStages, phase ^ 1u);  // local empty[stage]: the pair's MMAs have consumed it
                 // The leader's producer announces the bytes of BOTH CTAs' loads of this operand; the peer only issues its loads (their
                 // complete_tx lands on the leader's barrier, possibly before the announcement: the count may go negative inside a phase).
@@ -212,19 +224,34 @@ __device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelP
                 if (KIND == PROD_A_TILED) tma2_load_2d(tm, leader_full, dst, kb * kBlockK, m0);
                 else if (KIND == PROD_A_IM2COL) tma2_load_im2col_4d(tm, leader_full, dst, cblk * kBlockK, base_w, base_h, img, uint16_t(fs * p.dil_w), uint16_t(fr * p.dil_h));
                 else tma2_load_3d(tm, leader_full, dst, cblk * kBlockK, tap, n0);
-                stage += uint32_t(n_prod);
-                full_addr += 8u * uint32_t(n_prod);
-                dst += uint32_t(n_prod) * C::kStageBytes;
-                if (stage >= uint32_t(C::kStages)) {
-                    stage -= uint32_t(C::kStages);
-                    phase ^= 1u;
-                    full_addr -= 8u * uint32_t(C::kStages);
-                    dst -= uint32_t(C::kStages) * C::kStageBytes;
-                }
+                advance();
                 if (KIND != PROD_A_TILED) {
                     cblk += n_prod;
                     while (cblk >= kpt) { cblk -= kpt; ++tap; ++fs; }
                     while (fs >= taps_w) { fs -= taps_w; ++fr; }
+                }
+            }
+            if (side_kb > 0 && kb < num_kb) {
+                // ---- projection shortcut: k-blocks main_kb.. read the block's input (1x1, own stride) and the shortcut's weights ----
+                const bool side_im2col = KIND != PROD_B && p.side_mode == CONV_MODE_IM2COL;
+                if (side_im2col) {
+                    img = m0 / p.PQ;
+                    const int rem = m0 - img * p.PQ;
+                    const int op = rem / p.Q;
+                    const int oq = rem - op * p.Q;
+                    base_h = op * p.side_stride_h;
+                    base_w = oq * p.side_stride_w;
+                }
+#pragma unroll 1
+                for (; kb < num_kb; kb += n_prod) {
+                    mbar_wait_bounded(full_addr + 8u * C::kStages, phase ^ 1u);
+                    const uint32_t leader_full = full_addr & kPeerMask;
+                    if (rank == 0) mbar_expect_tx(full_addr, 2u * kTxBytes);
+                    const int c0 = (kb - main_kb) * kBlockK;
+                    if (KIND == PROD_B) tma2_load_3d(tm_side, leader_full, dst, c0, 0, n0);
+                    else if (side_im2col) tma2_load_im2col_4d(tm_side, leader_full, dst, c0, base_w, base_h, img, uint16_t(0), uint16_t(0));
+                    else tma2_load_2d(tm_side, leader_full, dst, c0, m0);
+                    advance();
                 }
             }
         }
@@ -235,7 +262,8 @@ __device__ __forceinline__ void produce(const CUtensorMap* tm, const ConvKernelP
 template <int BLOCK_N, bool HAS_RES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
-                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res, const ConvKernelParams p) {
+                 const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
+                 const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b2, const ConvKernelParams p) {
     using C = Cfg<BLOCK_N, HAS_RES>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
@@ -262,7 +290,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int cluster_id = int(blockIdx.x) >> 1;
     const int num_pairs = (p.num_m_tiles + 1) / 2;
     const int num_items = num_pairs * p.num_n_tiles;
-    const int total_kb = p.num_taps * p.kblocks_per_tap;
+    const int main_kb = p.num_taps * p.kblocks_per_tap;
+    const int total_kb = main_kb + p.side_kb;
     const int my_tiles = cluster_id < num_items ? (num_items - 1 - cluster_id) / n_clusters + 1 : 0;
     constexpr bool kSplit = C::kChunks >= 2;  // both epilogue groups share every tile (see conv_igemm.cu)
 
@@ -271,6 +300,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         prefetch_tensormap(&tm_b);
         prefetch_tensormap(&tm_out);
         if (HAS_RES) prefetch_tensormap(&tm_res);
+        if (p.side_kb) {
+            prefetch_tensormap(&tm_a2);
+            prefetch_tensormap(&tm_b2);
+        }
     }
     if (warp == 1) {
         if (lane < C::kStages) {
@@ -301,10 +334,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (elect_one() && me < n_prod) {
             if (is_a) {
                 if (p.use_pdl) grid_dep_wait();
-                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
-                else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
+                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
+                else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
             } else {
-                produce<PROD_B, BLOCK_N, HAS_RES>(&tm_b, p, smem_base, bar_base, me, n_prod, num_items, total_kb, rank);
+                produce<PROD_B, BLOCK_N, HAS_RES>(&tm_b, &tm_b2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
             }
         }
     } else if (warp == kMmaWarp) {
@@ -386,11 +419,20 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             else tma_load_2d(&tm_res, res_bar(ewarp, b), buf0 + uint32_t(b) * kEpiBufBytes, col0, m_row0);
         };
         if (HAS_RES && n_items > 0 && lane == 0) prefetch_res(0);
+        auto load_bias = [&](int col0) {
+            float2 b = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
+            if (p.bias2) {  // projection shortcut: its bias joins before the activation
+                const float2 b2 = __ldg(reinterpret_cast<const float2*>(p.bias2 + col0) + lane);
+                b.x += b2.x;
+                b.y += b2.y;
+            }
+            return b;
+        };
         float2 bias_next = make_float2(0.f, 0.f);
         if (n_items > 0) {
             int m_row0, col0;
             item_coords(0, &m_row0, &col0);
-            bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + col0) + lane);
+            bias_next = load_bias(col0);
         }
         uint32_t res_phase = 0;
         int item = 0;
@@ -414,7 +456,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 if (item + 1 < n_items) {
                     int nm, ncol0;
                     item_coords(item + 1, &nm, &ncol0);
-                    bias_next = __ldg(reinterpret_cast<const float2*>(p.bias + ncol0) + lane);
+                    bias_next = load_bias(ncol0);
                 }
                 uint32_t v[kChunkN];
                 tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
@@ -480,8 +522,8 @@ cudaError_t launch_t(const ConvTcLaunch& L, int grid, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = L.use_pdl ? 2 : 1;
-    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, true>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
-    return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, false>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.p);
+    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, true>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, false>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
 }
 
 }  // namespace

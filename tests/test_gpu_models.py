@@ -20,6 +20,7 @@ def _run(ctx, model: bytes, x: np.ndarray, **cfg):
     nn = g.metalGraph()
     out = nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
     launches = nn.numLaunches(x.shape[0])
+    _run.folded = nn.planDump(x.shape[0]).count("+conv1x1(")  # projection shortcuts that run inside their block's last conv
     g.close()
     return out, launches
 
@@ -77,7 +78,8 @@ def test_resnet50_batch4_matches_oracle(ctx):
     out = out.reshape(4, 1000)
     assert np.abs(out - want).max() <= TOL
     assert (out.argmax(1) == want.argmax(1)).all()
-    assert launches == 1 + 53 + 1 + 1 + 1  # boundary + conv (all ReLU/Add fused) + maxpool + gap + fc (logits are a view)
+    # boundary + conv (all ReLU/Add fused) + maxpool + gap + fc (logits are a view), minus the folded 1x1 shortcuts
+    assert 0 <= _run.folded <= 4 and launches == 1 + 53 + 1 + 1 + 1 - _run.folded
 
 
 def test_resnet50_batch32_properties(ctx, monkeypatch):
@@ -125,7 +127,7 @@ def test_persistent_multi_layer_kernel_matches_per_layer_launches(ctx, monkeypat
         g = ONNXGraph(model, context=ctx)
         nn = g.metalGraph()
         outs = [nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(8, 1000).copy() for _ in range(3)]
-        n = nn.numLaunches(8)
+        n = nn.numLaunches(8) + nn.planDump(8).count("+conv1x1(")
         g.close()
         return outs, n
 
@@ -138,6 +140,35 @@ def test_persistent_multi_layer_kernel_matches_per_layer_launches(ctx, monkeypat
     assert np.abs(mega[0].astype(np.float32) - base[0].astype(np.float32)).max() <= 4e-3
     want = _oracle(model, x[:2])
     assert np.abs(mega[0][:2].astype(np.float32) - want).max() <= TOL
+
+
+def test_projection_shortcut_runs_inside_the_block_output_conv(ctx, monkeypatch):
+    """The four 1x1 "downsample" convolutions of ResNet-50 are extra k-blocks of their block's last convolution (one GEMM over
+    the concatenated K axis, kernels/conv_pair.cu): four launches fewer, the shortcut tensor never exists, and the sum is
+    taken in fp32 before the single fp16 rounding -- so results agree with the two-launch form to fp16 rounding only."""
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Image, ONNXGraph
+
+    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    x = np.random.default_rng(7).random((32, 3, 224, 224), dtype=np.float32).astype(np.float16)
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(32, 1000).copy() for _ in range(2)]
+        dump, n = nn.planDump(32), nn.numLaunches(32)
+        g.close()
+        assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
+        return outs[0], dump, n
+
+    folded, dump, n = run()
+    monkeypatch.setenv("SMELTER_NO_SIDE", "1")  # read when a plan is made
+    plain, dump0, n0 = run()
+    assert dump.count("+conv1x1(") == 4 and dump0.count("+conv1x1(") == 0 and n0 - n == 4
+    assert np.abs(folded.astype(np.float32) - plain.astype(np.float32)).max() <= 4e-3
+    want = _oracle(model, x[:2])
+    assert np.abs(folded[:2].astype(np.float32) - want).max() <= TOL
+    assert np.abs(plain[:2].astype(np.float32) - want).max() <= TOL
 
 
 def test_mobilenet_v2_batch1(ctx):

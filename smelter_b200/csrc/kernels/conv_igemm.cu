@@ -818,7 +818,10 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
 
 bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms) {
     if (!q.side_x || q.pair < 0 || (q.pair == 0 && getenv("SMELTER_NO_PAIR")) || num_sms < 2 || q.splits > 1) return false;
-    if (q.side_c_in_pitch % 8 || q.side_stride_h > 8 || q.side_stride_w > 8) return false;
+    if (q.side_c_in_pitch % 8 || q.side_stride_h < 1 || q.side_stride_w < 1 || q.side_stride_h > 8 || q.side_stride_w > 8) return false;
+    const int P = (q.h + q.pad_t + q.pad_b - q.dil_h * (q.k_h - 1) - 1) / q.stride_h + 1;
+    const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (q.k_w - 1) - 1) / q.stride_w + 1;
+    if ((q.side_h - 1) / q.side_stride_h + 1 != P || (q.side_w - 1) / q.side_stride_w + 1 != Q) return false;
     auto pairable = [&](const ConvTcProblem& pq) {
         const ConvTcPlanInfo info = conv_tc_plan(pq, num_sms);
         return info.splits == 1 && (info.block_n == 64 || info.block_n == 128 || info.block_n == 256);

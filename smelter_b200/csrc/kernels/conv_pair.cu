@@ -11,6 +11,9 @@
 //   tmem_full[a]  one per CTA, same multicast commit; each CTA's epilogue drains its own 128 TMEM lanes.
 //   tmem_empty[a] lives in the leader: arrivals from the epilogue threads of both CTAs (remote arrive from the peer).
 //   Only the leader's MMA warp issues MMAs; the peer's takes part in the cta_group::2 TMEM allocation only.
+// Projection shortcut (ConvKernelParams::side_kb): after the main k-blocks of a tile, `side_kb` more k-blocks read a second activation
+// tensor (tm_a2: 1x1, own stride, same output grid) against a second weight matrix (tm_b2) into the same accumulator -- the 1x1
+// "downsample" convolution of a residual block is part of its block's last GEMM instead of a launch of its own.
 // Everything else (operand modes, epilogue, fusion, PDL) is conv_igemm.cu's.  Default for 64/128/256-column tiles without split-K
 // (same-box A/B on ResNet-50: -1.2 % step time at batch 32, +6..8 % images/s at batch 128/256); SMELTER_NO_PAIR=1 turns it off.
 #include <cstdio>

@@ -171,6 +171,21 @@ def test_projection_shortcut_runs_inside_the_block_output_conv(ctx, monkeypatch)
     assert np.abs(plain[:2].astype(np.float32) - want).max() <= TOL
 
 
+@pytest.mark.parametrize("batch,hw", [(3, 40), (1, 64), (5, 32)])
+def test_folded_projection_shortcut_on_ragged_tiles(ctx, monkeypatch, batch, hw):
+    """Small, odd-sized bottleneck stacks: the last m-tile pair is partly (or wholly) out of range, stride-2 shortcuts sample odd
+    image sizes, and every shortcut is folded (split-K off so that the two-CTA kernel is the plan for these tiny layers)."""
+    from smelter_b200 import modelzoo
+
+    monkeypatch.setenv("SMELTER_NO_SPLITK", "1")  # read when a plan is made
+    model = modelzoo.resnet50(seed=batch, fold_bn=True, num_classes=24, hw=hw, depths=(1, 2, 1, 1)).serialize()
+    x = np.random.default_rng(batch).random((batch, 3, hw, hw), dtype=np.float32).astype(np.float16)
+    out, launches = _run(ctx, model, x)
+    assert _run.folded == 4
+    want = _oracle(model, x)
+    assert np.abs(out.reshape(want.shape) - want).max() <= TOL
+
+
 def test_mobilenet_v2_batch1(ctx):
     from smelter_b200 import modelzoo, onnx2mps
 

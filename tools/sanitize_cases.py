@@ -42,7 +42,7 @@ def model(bytes_, x, tol, what, **env):
     out = nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toFloatArray()
     ref = Interpreter(bytes_).run(torch.from_numpy(x.astype(np.float32))).numpy().reshape(out.shape)
     err = float(np.abs(out - ref).max())
-    print(f"model {what}: launches {nn.numLaunches(x.shape[0])} max_abs_err {err:.3e}", flush=True)
+    print(f"model {what}: launches {nn.numLaunches(x.shape[0])} folded shortcuts {nn.planDump(x.shape[0]).count('+conv1x1(')} max_abs_err {err:.3e}", flush=True)
     assert err <= tol
     gph.close()
     for k_ in env:
@@ -54,6 +54,8 @@ small = modelzoo.resnet50(seed=0, fold_bn=True, num_classes=16, hw=64, depths=(1
 x = rng.random((2, 3, 64, 64), dtype=np.float32).astype(np.float16)
 model(small, x, 1e-2, "resnet bottlenecks (per-layer)")
 model(small, x, 1e-2, "resnet bottlenecks (persistent kernel)", SMELTER_MEGA="1")
+ragged = modelzoo.resnet50(seed=1, fold_bn=True, num_classes=16, hw=40, depths=(1, 1, 1, 1)).serialize()
+model(ragged, rng.random((3, 3, 40, 40), dtype=np.float32).astype(np.float16), 1e-2, "resnet bottlenecks, ragged tiles, shortcuts folded", SMELTER_NO_SPLITK="1")
 model(modelzoo.decoder_ops(seed=3).serialize(), rng.standard_normal((1, 32, 10, 10)).astype(np.float16), 1e-2, "conv_transpose / group_norm / pow")
 model(modelzoo.synthetic_ops(seed=0).serialize(), rng.random((2, 16, 12, 12), dtype=np.float32).astype(np.float16), 1e-2, "sigmoid / concat / avgpool / softmax")
 tn = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=64, width_div=4).serialize(), half=True)

@@ -512,18 +512,18 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
     };
     const char* mega_env = getenv("SMELTER_MEGA");
     const bool mega_on = mega_env && atoi(mega_env) != 0;
+    std::vector<int> reads(values_.size(), 0), producer(values_.size(), -1);
+    for (size_t fi = 0; fi < filters_.size(); ++fi) {
+        const Filter& f = filters_[fi];
+        if (f.removed) continue;
+        for (int i : f.in) ++reads[size_t(root_of(i))];
+        if (f.residual >= 0) ++reads[size_t(root_of(f.residual))];
+        if (f.out >= 0 && values_[size_t(f.out)].alias_of < 0) producer[size_t(f.out)] = int(fi);
+    }
+    auto plain_tc_conv = [&](const Filter& f) {
+        return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
+    };
     if (!getenv("SMELTER_NO_SIDE") && !mega_on) {
-        std::vector<int> reads(values_.size(), 0), producer(values_.size(), -1);
-        for (size_t fi = 0; fi < filters_.size(); ++fi) {
-            const Filter& f = filters_[fi];
-            if (f.removed) continue;
-            for (int i : f.in) ++reads[size_t(root_of(i))];
-            if (f.residual >= 0) ++reads[size_t(root_of(f.residual))];
-            if (f.out >= 0 && values_[size_t(f.out)].alias_of < 0) producer[size_t(f.out)] = int(fi);
-        }
-        auto plain_tc_conv = [&](const Filter& f) {
-            return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
-        };
         for (size_t fi = 0; fi < filters_.size(); ++fi) {
             const Filter& f = filters_[fi];
             if (f.removed || !plain_tc_conv(f) || f.residual < 0) continue;
@@ -543,6 +543,32 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         }
     }
 
+    // ---- back-to-back pairs (opt-in, SMELTER_B2B=1; kernels/conv_b2b.cu): a convolution with 64 / 128 output channels whose only reader
+    // is a 1x1 / stride-1 convolution runs inside that reader's launch; its output tensor never exists.  b2b_first[B] = A.
+    std::vector<int> b2b_first(filters_.size(), -1);
+    auto b2b_problem = [&](const Filter& g, const Filter& h) {
+        k::ConvB2bProblem bq{};
+        bq.first = conv_problem(g, {});
+        bq.c_out2 = h.c_out;
+        bq.c_out2_pitch = round_up(values_[size_t(h.out)].shape.c, 8);
+        bq.act2 = h.act; bq.clip2_lo = h.clip_lo; bq.clip2_hi = h.clip_hi;
+        return bq;
+    };
+    if (const char* b2b_env = getenv("SMELTER_B2B"); b2b_env && atoi(b2b_env) != 0 && !mega_on) {
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& h = filters_[fi];
+            if (h.removed || absorbed[fi] || side_of[fi] >= 0 || !plain_tc_conv(h) || h.conv_mode != k::CONV_MODE_TILED) continue;
+            const int mid = root_of(h.in[0]);
+            const int gi = producer[size_t(mid)];
+            if (gi < 0 || gi >= int(fi) || mid == out_root || reads[size_t(mid)] != 1 || values_[size_t(mid)].is_input) continue;
+            const Filter& g = filters_[size_t(gi)];
+            if (!plain_tc_conv(g) || absorbed[size_t(gi)] || side_of[size_t(gi)] >= 0 || b2b_first[size_t(gi)] >= 0 || g.residual >= 0 || h.c_in_g != g.c_out) continue;
+            if (!k::conv_b2b_supported(b2b_problem(g, h), num_sms)) continue;
+            b2b_first[fi] = gi;
+            absorbed[size_t(gi)] = 1;
+        }
+    }
+
     // last use of every root value (filter index); the output value lives forever.  An absorbed shortcut's input is read by the
     // convolution that absorbed it.
     std::vector<int> last_use(values_.size(), -1);
@@ -552,6 +578,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         for (int i : f.in) last_use[size_t(root_of(i))] = int(fi);
         if (f.residual >= 0 && side_of[fi] < 0) last_use[size_t(root_of(f.residual))] = int(fi);
         if (side_of[fi] >= 0) last_use[size_t(root_of(filters_[size_t(side_of[fi])].in[0]))] = int(fi);
+        if (b2b_first[fi] >= 0) last_use[size_t(root_of(filters_[size_t(b2b_first[fi])].in[0]))] = int(fi);
     }
     last_use[size_t(out_root)] = int(filters_.size()) + 1;
 
@@ -634,7 +661,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             scratch[fi].bytes = size_t(N) * tq.h * tq.w * tq.c_in_pitch * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
-        if (f.kind == FilterKind::Conv && f.conv_mode != 4 && side_of[fi] < 0) {
+        if (f.kind == FilterKind::Conv && f.conv_mode != 4 && side_of[fi] < 0 && b2b_first[fi] < 0) {
             const k::ConvTcPlanInfo info = k::conv_tc_plan(conv_problem(f, stem_of), num_sms);
             if (info.splits > 1) {
                 scratch2[fi].bytes = info.ws_bytes;
@@ -665,6 +692,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         for (int i : f.in) roots.push_back(root_of(i));
         if (f.residual >= 0 && side_of[fi] < 0) roots.push_back(root_of(f.residual));
         if (side_of[fi] >= 0) roots.push_back(root_of(filters_[size_t(side_of[fi])].in[0]));
+        if (b2b_first[fi] >= 0) roots.push_back(root_of(filters_[size_t(b2b_first[fi])].in[0]));
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
@@ -760,6 +788,27 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
                         return k::depthwise_conv(x, w, bias, y, N, is.h, is.w, icp, osz.h, osz.w, fp->k_h, fp->k_w, fp->stride_h, fp->stride_w, fp->dil_h,
                                                  fp->dil_w, fp->pads[0], fp->pads[1], fp->act, fp->clip_lo, fp->clip_hi, st);
                     }, flops, io_bytes);
+                    break;
+                }
+                if (b2b_first[fi] >= 0) {
+                    const Filter& g = filters_[size_t(b2b_first[fi])];
+                    k::ConvB2bProblem bq = b2b_problem(g, f);
+                    bq.first.x = ptr_of(g.in[0]);
+                    bq.first.w_packed = reinterpret_cast<const __half*>(wbase + g.w_off);
+                    bq.first.bias = reinterpret_cast<const float*>(wbase + g.bias_off);
+                    bq.w2_packed = w; bq.bias2 = bias; bq.residual = res; bq.y = y;
+                    if (res && last_use[size_t(root_of(f.residual))] == int(fi)) bq.l2_hints |= 2;
+                    auto BL = std::make_shared<k::ConvB2bLaunch>();
+                    std::string cerr;
+                    if (!k::conv_b2b_prepare(BL.get(), bq, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
+                    const ImageShape gs = values_[size_t(g.in[0])].shape;
+                    const std::string mid_act = g.act == k::ACT_RELU ? "+relu" : g.act == k::ACT_CLIP ? "+clip" : "";
+                    add_step("conv_b2b[" + std::string(g.conv_mode == k::CONV_MODE_TILED ? "tiled" : "im2col") + ",n1=" + std::to_string(g.c_out) + mid_act + " -> 1x1]" +
+                                 suffix + " Conv " + values_[size_t(g.out)].name + " -> " + values_[size_t(f.out)].name,
+                             [BL](cudaStream_t st) { return k::conv_b2b_launch(*BL, st); }, BL->flops,
+                             double(N) * (double(gs.h) * gs.w * round_up(gs.c, 8) + double(osz.h) * osz.w * ocp * (res ? 2 : 1)) * 2 +
+                                 double(g.c_out) * g.c_in_g * g.k_h * g.k_w * 2 + double(f.c_out) * f.c_in_g * 2);
+                    plan->steps.back().tensor = true;
                     break;
                 }
                 k::ConvTcProblem q = conv_problem(f, stem_of);

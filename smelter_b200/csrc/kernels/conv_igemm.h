@@ -108,6 +108,37 @@ void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only
 bool conv_pair_supported(const ConvTcLaunch& L);
 cudaError_t conv_pair_set_attr(int block_n);
 cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
+// ---- back-to-back pair (conv_b2b.cu, opt-in): a convolution with 64 / 128 output channels and the 1x1 convolution that consumes
+//      it run as one launch; the intermediate tile stays in shared memory ----
+struct ConvB2bProblem {
+    ConvTcProblem first;      // conv A: x, w_packed, bias, act (the activation between the two); y / residual / side_* unused
+    const __half* w2_packed;  // conv B weights [c_out2][c_out of A]
+    const float* bias2;
+    int c_out2, c_out2_pitch;
+    const __half* residual;   // [M, c_out2_pitch] added before conv B's activation, or nullptr
+    __half* y;                // [M, c_out2_pitch]
+    int act2;
+    float clip2_lo, clip2_hi;
+    int l2_hints;
+};
+struct ConvB2bParams {
+    const float* bias2;
+    int act2;
+    float clip2_lo, clip2_hi;
+    int subtiles;             // 128-column accumulators of conv B per tile
+    int has_residual;
+    int l2_hints;
+};
+struct ConvB2bLaunch {
+    CUtensorMap tm_a, tm_b1, tm_b2, tm_out, tm_res;
+    ConvKernelParams p;       // conv A geometry
+    ConvB2bParams p2;
+    int n1, grid, use_pdl;
+    double flops;
+};
+bool conv_b2b_supported(const ConvB2bProblem& q, int num_sms);
+bool conv_b2b_prepare(ConvB2bLaunch* L, const ConvB2bProblem& q, int num_sms, std::string* err);
+cudaError_t conv_b2b_launch(const ConvB2bLaunch& L, cudaStream_t stream);
 // benchmark only: TMA load rate of [128 x 64] fp16 boxes; mode 0 = 2-D tiled over [N*H*W, C], 1 = im2col (3x3, pad 1)
 int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
                std::string* err);

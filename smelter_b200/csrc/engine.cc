@@ -719,7 +719,11 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         SM_CUDA(cudaMemset(plan->counters, 0, counter_total));
     }
     char* abase = static_cast<char*>(plan->arena);
-    auto ptr_of = [&](int v) { return reinterpret_cast<__half*>(abase + off[size_t(root_of(v))]); };
+    // values without a buffer (outputs of convolutions that run inside their consumer's launch) have no address
+    auto ptr_of = [&](int v) -> __half* {
+        const size_t o = off[size_t(root_of(v))];
+        return o == size_t(-1) ? nullptr : reinterpret_cast<__half*>(abase + o);
+    };
 
     // ---- steps ----
     auto add_step = [&](std::string desc, std::function<cudaError_t(cudaStream_t)> fn, double flops = 0, double bytes = 0) {

@@ -967,7 +967,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     p.timeline = nullptr;
     if (getenv("SMELTER_CONV_TIMELINE")) {
         static unsigned long long* buf = nullptr;
-        if (!buf) cudaMalloc(&buf, 64 * sizeof(unsigned long long));
+        if (!buf && cudaMalloc(&buf, 64 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(buf, 0, 64 * sizeof(unsigned long long));
         p.timeline = buf;
     }
     {
@@ -1333,8 +1333,19 @@ int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iter
 
 void conv_tc_dump_timeline(const ConvTcLaunch& L) {
     if (!L.p.timeline) return;
-    unsigned long long h[16];
+    unsigned long long h[64];
     cudaMemcpy(h, L.p.timeline, sizeof h, cudaMemcpyDeviceToHost);
+    if (L.pair) {  // conv_pair.cu: six stamps per work item of the first epilogue warp (see epi_stamp)
+        fprintf(stderr, "pair epilogue timeline (ns since the first stamp; acc_ready, store_read+res_prefetch, tmem_loaded, residual_landed, staged, store_issued):\n");
+        for (int item = 0; item < 8; ++item) {
+            if (!h[16 + 6 * item]) break;
+            fprintf(stderr, "  item %d:", item);
+            for (int pt = 0; pt < 6; ++pt) fprintf(stderr, " %lld", (long long)(h[16 + 6 * item + pt] - h[16]));
+            fprintf(stderr, "\n");
+        }
+        cudaMemset(L.p.timeline, 0, sizeof h);
+        return;
+    }
     const char* names[9] = {"entry", "prologue_done", "deps_resolved", "first_operands", "mma_issued", "acc_ready", "last_store_issued", "stores_read", "exit"};
     fprintf(stderr, "timeline(ns since entry):");
     for (int i = 0; i < 9; ++i) fprintf(stderr, " %s=%lld", names[i], (long long)(h[i] - h[0]));

@@ -63,6 +63,20 @@ struct Cfg {
     static constexpr size_t kSmemBytes = size_t(kStages) * kStageBytes + kEpiBytes + kBarrierBytes;
 };
 
+// Epilogue timeline stamps (perf experiments only, -DSMELTER_CONV_INSTRUMENT=1 builds with SMELTER_CONV_TIMELINE set): lane 0 of the
+// first epilogue warp of CTA 0 writes %globaltimer at six points of its first eight work items into p.timeline[16 + 6 * item + point].
+#ifndef SMELTER_CONV_INSTRUMENT
+#define SMELTER_CONV_INSTRUMENT 0
+#endif
+constexpr bool kInstr = SMELTER_CONV_INSTRUMENT != 0;
+__device__ __forceinline__ void epi_stamp(const ConvKernelParams& p, bool who, int item, int point) {
+    if (kInstr && p.timeline && who && item < 8) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        p.timeline[16 + 6 * item + point] = t;
+    }
+}
+
 enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
 
 // One elected thread per producer warp (see conv_igemm.cu produce()).  Work items are (m-pair, n-tile): cluster c visits items
@@ -343,6 +357,8 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             const uint32_t acc_parity = uint32_t(kSplit ? (gt >> 1) : gt) & 1u;
             mbar_wait_bounded(tmem_full_bar(acc), acc_parity);
             tc_fence_after();
+            const bool stamper = kInstr && blockIdx.x == 0 && ewarp == 0 && lane == 0;
+            epi_stamp(p, stamper, item, 0);
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
 #pragma unroll 1
             for (int j = 0; j < kCPW; ++j, ++item) {
@@ -354,6 +370,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tma_store_wait_read<0>();
                     prefetch_res(item + 1);
                 }
+                epi_stamp(p, stamper, item, 1);
                 asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(bias_slot + uint32_t(lane) * 8u), "f"(bias_next.x), "f"(bias_next.y) : "memory");
                 if (item + 1 < n_items) {
                     int nm, ncol0;
@@ -364,6 +381,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 tmem_ld_32(taddr + uint32_t(c * kChunkN), v);
                 tmem_ld_32(taddr + uint32_t(c * kChunkN + 32), v + 32);
                 tmem_ld_wait();
+                epi_stamp(p, stamper, item, 2);
                 if (j == kCPW - 1) {  // hand the accumulator back to the leader's MMA warp (remote arrive from the peer CTA)
                     tc_fence_before();
                     mbar_arrive_cluster(tmem_empty_bar(acc) & kPeerMask);
@@ -372,6 +390,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     mbar_wait_bounded(res_bar(ewarp, b), (res_phase >> b) & 1u);
                     res_phase ^= 1u << b;
                 }
+                epi_stamp(p, stamper, item, 3);
                 __syncwarp();
                 const uint32_t buf = buf0 + uint32_t(b) * kEpiBufBytes;
                 uint4 out[kChunkN / 8];
@@ -384,10 +403,12 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 for (int g = 0; g < kChunkN / 8; ++g) st_shared_v4(buf + row_off + ((uint32_t(g) ^ sw) << 4), out[g]);
                 fence_proxy_async_smem();
                 __syncwarp();
+                epi_stamp(p, stamper, item, 4);
                 if (lane == 0) {
                     tma_store_2d(&tm_out, buf, col0, m_row0);
                     tma_store_commit();
                 }
+                epi_stamp(p, stamper, item, 5);
             }
         }
         if (lane == 0) tma_store_wait_read<0>();

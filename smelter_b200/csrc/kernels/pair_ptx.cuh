@@ -75,9 +75,9 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {  // arrives on `bar
 
 static __device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
 
-template <int kCols, bool HAS_RES>
-__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
-                                              bool is_sigmoid, __half2 lo2, __half2 hi2) {
+template <int kCols, bool HAS_RES, bool SIGMOID>
+__device__ __forceinline__ void epilogue_math_t(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
+                                                __half2 lo2, __half2 hi2) {
     constexpr int kGroups = kCols / 8;
     uint4 nb0 = ld_shared_v4(bias_slot), nb1 = ld_shared_v4(bias_slot + 16u);
     uint4 nrv = make_uint4(0u, 0u, 0u, 0u);
@@ -104,7 +104,7 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 
                 f[2 * i + 1] += r2.y;
             }
         }
-        if (is_sigmoid) {
+        if (SIGMOID) {
 #pragma unroll
             for (int i = 0; i < 8; ++i) f[i] = sigmoid1(f[i]);
         }
@@ -112,6 +112,16 @@ __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 
 #pragma unroll
         for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
     }
+}
+
+// The sigmoid test is made once per chunk, not once per 8 columns: a branch around the out-of-line calls inside the unrolled loop
+// cuts it into eight scheduling regions, each a serial LDS -> FADD -> F2FP -> HMNMX2 chain, and the epilogue's arithmetic
+// (measured with the timeline stamps: 0.55-0.7 us of a 1.2 us work item) cannot overlap across column groups.
+template <int kCols, bool HAS_RES>
+__device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
+                                              bool is_sigmoid, __half2 lo2, __half2 hi2) {
+    if (is_sigmoid) epilogue_math_t<kCols, HAS_RES, true>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
+    else epilogue_math_t<kCols, HAS_RES, false>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
 }
 
 }  // namespace pairptx

@@ -75,7 +75,8 @@ __device__ __forceinline__ void umma2_commit(uint32_t bar) {  // arrives on `bar
 
 static __device__ __noinline__ float sigmoid1(float v) { return 1.f / (1.f + __expf(-v)); }
 
-template <int kCols, bool HAS_RES, bool SIGMOID>
+// CLAMP: 0 = no activation clamp, 1 = lower bound only (ReLU), 2 = both bounds (Clip)
+template <int kCols, bool HAS_RES, bool SIGMOID, int CLAMP>
 __device__ __forceinline__ void epilogue_math_t(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
                                                 __half2 lo2, __half2 hi2) {
     constexpr int kGroups = kCols / 8;
@@ -110,7 +111,12 @@ __device__ __forceinline__ void epilogue_math_t(const uint32_t (&v)[kCols], uint
         }
         __half2* oh = reinterpret_cast<__half2*>(&out[g]);
 #pragma unroll
-        for (int i = 0; i < 4; ++i) oh[i] = __hmin2(__hmax2(__floats2half2_rn(f[2 * i], f[2 * i + 1]), lo2), hi2);
+        for (int i = 0; i < 4; ++i) {
+            __half2 h = __floats2half2_rn(f[2 * i], f[2 * i + 1]);
+            if (CLAMP >= 1) h = __hmax2(h, lo2);
+            if (CLAMP >= 2) h = __hmin2(h, hi2);
+            oh[i] = h;
+        }
     }
 }
 
@@ -120,8 +126,12 @@ __device__ __forceinline__ void epilogue_math_t(const uint32_t (&v)[kCols], uint
 template <int kCols, bool HAS_RES>
 __device__ __forceinline__ void epilogue_math(const uint32_t (&v)[kCols], uint4 (&out)[kCols / 8], uint32_t rowbuf, uint32_t sw, uint32_t bias_slot,
                                               bool is_sigmoid, __half2 lo2, __half2 hi2) {
-    if (is_sigmoid) epilogue_math_t<kCols, HAS_RES, true>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
-    else epilogue_math_t<kCols, HAS_RES, false>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
+    // lo2 / hi2 are -inf / +inf where the activation has no bound; the bounded forms are picked by comparing against those
+    const bool has_lo = __hgt(__low2half(lo2), __float2half_rn(-INFINITY)), has_hi = __hlt(__low2half(hi2), __float2half_rn(INFINITY));
+    if (is_sigmoid) epilogue_math_t<kCols, HAS_RES, true, 0>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
+    else if (has_hi) epilogue_math_t<kCols, HAS_RES, false, 2>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
+    else if (has_lo) epilogue_math_t<kCols, HAS_RES, false, 1>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
+    else epilogue_math_t<kCols, HAS_RES, false, 0>(v, out, rowbuf, sw, bias_slot, lo2, hi2);
 }
 
 }  // namespace pairptx

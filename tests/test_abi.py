@@ -48,3 +48,24 @@ def test_no_cpu_fallback_without_a_device(native_lib):
     rc = native_lib.smelter_context_create(0, None, C.byref(h))
     assert rc == 102  # SMELTER_ERR_CUDA
     assert b"no CPU fallback" in native_lib.smelter_last_error()
+
+
+def test_environment_switches_are_documented():
+    """Every SMELTER_* variable the native code reads appears in INTEGRATION.md's table (or, for the MEGA_* / build-time ones, by
+    prefix), and the table names no switch the code does not read."""
+    import glob
+    import os
+    import re
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    read = set()
+    for path in glob.glob(os.path.join(root, "smelter_b200", "csrc", "**", "*.c*"), recursive=True):
+        read |= set(re.findall(r'getenv\("(SMELTER_[A-Z0-9_]+)"\)', open(path).read()))
+    doc = open(os.path.join(root, "INTEGRATION.md")).read()
+    table = doc[doc.index("## Environment switches"):]
+    named = set(re.findall(r"`(SMELTER_[A-Z0-9_]+\*?)", table))
+    prefixes = [n[:-1] for n in named if n.endswith("*")]
+    for var in sorted(read):
+        assert var in named or any(var.startswith(p) for p in prefixes), var
+    for var in sorted(n for n in named if not n.endswith("*")):
+        assert var in read or var == "SMELTER_CONV_INSTRUMENT", var

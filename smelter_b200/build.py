@@ -26,7 +26,7 @@ SOURCES = [
     "nccl_shim.cc",
     "kernels/conv_igemm.cu",
     "kernels/conv_mega.cu",
-    "kernels/conv_pair.cu", "kernels/conv_b2b.cu",
+    "kernels/conv_pair.cu", "kernels/conv_duo.cu", "kernels/conv_b2b.cu",
     "kernels/elementwise.cu",
     "kernels/pool_norm.cu",
 ]

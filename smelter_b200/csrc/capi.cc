@@ -855,8 +855,8 @@ int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* 
     __half* yo = static_cast<__half*>(B.yo);
     auto launch = [&]() -> cudaError_t {
         switch (p->op) {
-            case SMELTER_EW_UNARY: return k::unary(xi, yo, in_elems, p->sub, p->alpha, p->beta, s);
-            case SMELTER_EW_BINARY: return k::binary(xi, x2i, yo, in_elems, p->sub, p->act, s);
+            case SMELTER_EW_UNARY: return k::unary(xi, yo, in_elems, p->sub, p->alpha, p->beta, s, Cc, cp);
+            case SMELTER_EW_BINARY: return k::binary(xi, x2i, yo, in_elems, p->sub, p->act, s, Cc, cp);
             case SMELTER_EW_SCALE_SHIFT:
                 return k::scale_shift(xi, yo, size_t(N) * H * W, cp, static_cast<const float*>(B.q0), static_cast<const float*>(B.q1), p->act, s);
             case SMELTER_EW_POOL: return k::pool2d(xi, yo, N, H, W, cp, oh, ow, p->k_h, p->k_w, p->stride_h, p->stride_w, p->pad_h, p->pad_w, p->sub, s);

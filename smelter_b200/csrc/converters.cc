@@ -100,10 +100,12 @@ int convert_conv(ONNXGraph& g, int ni) {
             reformat_conv_weight(wv.data(), f.w.data(), 4, o, i, kh, kw, is_transpose);  // :94-120 (ConvTranspose: IOHW -> OHWI + 180 degree flip)
         }
     }
-    if (in_shape->c != f.c_in_g * f.groups) {
-        if (!(is_gemm && in_shape->c * in_shape->h * in_shape->w == f.c_in_g))
-            return err(SMELTER_ERR_INCONSISTENT_STATE, node, "input channels disagree with the weight dims");
-    }
+    if (in_shape->c != f.c_in_g * f.groups) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "input channels disagree with the weight dims");
+    // Gemm runs as a 1x1 fully-connected layer over [N, C, 1, 1] (:228-232).  An un-flattened image (H*W > 1) would need the NCHW
+    // flatten order the weights were trained with; Flatten / Reshape produce exactly that [N, C*H*W, 1, 1] value, so demand it
+    // instead of silently reading NHWC memory in the wrong order.
+    if (is_gemm && in_shape->h * in_shape->w != 1)
+        return err(SMELTER_ERR_UNSUPPORTED, node, "Gemm input must be flattened to [N, C, 1, 1] (insert Flatten / Reshape)");
     f.bias.assign(size_t(f.c_out), 0.f);
     if (bias) {  // :126-135 bias always widened to fp32
         std::vector<float> bv;

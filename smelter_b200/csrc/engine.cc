@@ -923,13 +923,13 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
             case FilterKind::Unary: {
                 const int kind = f.sub;
                 const float a = f.alpha, b = f.beta;
-                add_step("unary " + name, [=](cudaStream_t st) { return k::unary(x, y, size_t(N) * is.h * is.w * icp, kind, a, b, st); }, 0, io_bytes);
+                add_step("unary " + name, [=](cudaStream_t st) { return k::unary(x, y, size_t(N) * is.h * is.w * icp, kind, a, b, st, is.c, icp); }, 0, io_bytes);
                 break;
             }
             case FilterKind::Binary: {
                 const __half* x2 = ptr_of(f.in[1]);
                 const int kind = f.sub, act = f.act;
-                add_step("binary " + name, [=](cudaStream_t st) { return k::binary(x, x2, y, size_t(N) * is.h * is.w * icp, kind, act, st); }, 0,
+                add_step("binary " + name, [=](cudaStream_t st) { return k::binary(x, x2, y, size_t(N) * is.h * is.w * icp, kind, act, st, is.c, icp); }, 0,
                          io_bytes + double(N) * is.h * is.w * icp * 2);
                 break;
             }

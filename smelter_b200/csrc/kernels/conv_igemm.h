@@ -44,6 +44,9 @@ struct ConvKernelParams {
     int side_mode;           // CONV_MODE_TILED (stride 1) or CONV_MODE_IM2COL
     int side_stride_h, side_stride_w;
     const float* bias2;      // the shortcut's bias, added to `bias` in the epilogue (nullptr = none)
+    // Residual add on the tensor core (conv_duo.cu only): after the main and shortcut k-blocks, `res_kb` = BLOCK_N / 64 k-blocks take
+    // the residual tile as the A operand (tm_res, [128 x 64] boxes) against 64 columns of an identity matrix (tm_ident).
+    int res_kb;              // 0 = none
 };
 
 struct ConvTcProblem {
@@ -88,12 +91,14 @@ bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms);
 struct ConvTcLaunch {
     CUtensorMap tm_a, tm_b, tm_out, tm_res;
     CUtensorMap tm_a2, tm_b2;  // projection shortcut operands (p.side_kb > 0)
+    CUtensorMap tm_ident;      // conv_duo.cu: [BLOCK_N / 2 rows x 64 cols] boxes of the identity matrix (p.res_kb > 0)
     ConvKernelParams p;
     int block_n;
     int splits;
     int grid;
     int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
     int pair;      // launched as conv_pair_kernel (two-CTA clusters): tm_b boxes hold BLOCK_N / 2 rows
+    int duo;       // launched as conv_duo_kernel (two-CTA clusters, two CTAs per SM); implies pair-style tm_b
     int num_sms;
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
 };
@@ -108,6 +113,11 @@ void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only
 bool conv_pair_supported(const ConvTcLaunch& L);
 cudaError_t conv_pair_set_attr(int block_n);
 cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
+// half-footprint two-CTA variant, two CTAs per SM, residual add as identity k-blocks (conv_duo.cu)
+bool conv_duo_supported(int block_n, int splits);
+cudaError_t conv_duo_set_attr(int block_n);
+cudaError_t conv_duo_identity(const __half** out);
+cudaError_t conv_duo_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
 // ---- back-to-back pair (conv_b2b.cu, opt-in): a convolution with 64 / 128 output channels and the 1x1 convolution that consumes
 //      it run as one launch; the intermediate tile stays in shared memory ----
 struct ConvB2bProblem {

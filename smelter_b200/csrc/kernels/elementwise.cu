@@ -78,8 +78,19 @@ __device__ __forceinline__ float unary_op(float x, int kind, float a, float b) {
 // thread per iteration these kernels sat at 55-68 % of the HBM copy rate, the two-input add (two loads in flight) at 97 %.
 constexpr int kUnroll = 4;
 
+// Channel pitches are multiples of 8; when the logical channel count is not (`tail` = c % 8 != 0), the lanes >= tail of a pixel's
+// last vector are padding.  They are written as zeros whatever f(0) is: Log / Div / Pow would otherwise leave inf or NaN there and
+// the next convolution multiplies every lane (by zero weights) inside the MMA -- inf * 0 = NaN in every output of that layer.
+__device__ __forceinline__ void zero_tail(float (&f)[8], size_t vec, int cp8, int tail) {
+    if (tail && int(vec % size_t(cp8)) == cp8 - 1) {
+#pragma unroll
+        for (int j = 1; j < 8; ++j)
+            if (j >= tail) f[j] = 0.f;
+    }
+}
+
 __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t n8, int kind,
-                                                        float a, float b) {
+                                                        float a, float b, int cp8, int tail) {
     const size_t stride = size_t(gridDim.x) * blockDim.x;
     for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < n8; i0 += stride * kUnroll) {
         Half8 v[kUnroll];
@@ -100,6 +111,7 @@ __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restric
             } else {
 #pragma unroll
                 for (int j = 0; j < 8; ++j) f[j] = unary_op(f[j], kind, a, b);
+                zero_tail(f, i0 + u * stride, cp8, tail);
             }
             st8(y + (i0 + u * stride) * 8, pack(f));
         }
@@ -107,7 +119,7 @@ __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restric
 }
 
 __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restrict__ pa, const __half* __restrict__ pb,
-                                                         __half* __restrict__ y, size_t n8, int kind, int act) {
+                                                         __half* __restrict__ y, size_t n8, int kind, int act, int cp8, int tail) {
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
         float a[8], b[8];
         unpack(ld8(pa + i * 8), a);
@@ -123,6 +135,7 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restri
             }
             a[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
         }
+        zero_tail(a, i, cp8, tail);
         st8(y + i * 8, pack(a));
     }
 }
@@ -476,14 +489,16 @@ __global__ void __launch_bounds__(kThreads) checksum_kernel(const uint32_t* __re
 
 }  // namespace
 
-cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s) {
+cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
-    unary_kernel<<<grid_for(n8), kThreads, 0, s>>>(x, y, n8, kind, alpha, beta);
+    const int tail = cp > 0 ? (c & 7) : 0;
+    unary_kernel<<<grid_for(n8), kThreads, 0, s>>>(x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
-cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s) {
+cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
-    binary_kernel<<<grid_for(n8), kThreads, 0, s>>>(a, b, y, n8, kind, act);
+    const int tail = cp > 0 ? (c & 7) : 0;
+    binary_kernel<<<grid_for(n8), kThreads, 0, s>>>(a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
 cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act, cudaStream_t s) {

@@ -64,20 +64,29 @@ def test_asymmetric_padding_and_sigmoid_epilogue(ctx):
     assert np.abs(y.toFloatArray() - ref).max() <= 2e-3
 
 
-def test_every_block_n_gives_the_same_answer(ctx):
-    """The N-tile width is a scheduling choice; results must not depend on it (same fp32 accumulation order per output)."""
-    import ctypes as C
-
-    from smelter_b200 import _lib as L
+@pytest.mark.parametrize("res", [False, True], ids=["plain", "residual"])
+def test_every_block_n_gives_the_same_answer(ctx, monkeypatch, res):
+    """The N-tile width is a scheduling choice; results must not depend on it (same k order and fp32 accumulation per output).
+    SMELTER_FORCE_BN (read when a launch is prepared) forces 64 / 128 / 256-column tiles of the two-CTA kernel."""
     from smelter_b200.api import Image, run_conv
 
     rng = np.random.default_rng(9)
     x = rng.standard_normal((2, 96, 14, 14)).astype(np.float16)
     wt = (rng.standard_normal((200, 96, 3, 3)) * 0.04).astype(np.float16)
+    b = rng.standard_normal(200).astype(np.float32)
+    r = rng.standard_normal((2, 200, 14, 14)).astype(np.float16) if res else None
     xi = Image.fromArray(ctx, x)
-    base = run_conv(ctx, xi, wt, None, pads=(1, 1, 1, 1))[0].toHalfArray()
-    again = run_conv(ctx, xi, wt, None, pads=(1, 1, 1, 1))[0].toHalfArray()
+
+    def run():
+        return run_conv(ctx, xi, wt, b, pads=(1, 1, 1, 1), act=1, residual=Image.fromArray(ctx, r) if res else None)[0].toHalfArray()
+
+    base = run()
+    again = run()
     assert np.array_equal(base.view(np.uint16), again.view(np.uint16))  # deterministic
+    for bn in (64, 128, 256):
+        monkeypatch.setenv("SMELTER_FORCE_BN", str(bn))
+        forced = run()
+        assert np.array_equal(base.view(np.uint16), forced.view(np.uint16)), f"BLOCK_N={bn} changes the result"
 
 
 def test_linearity_at_full_size(ctx):
@@ -109,7 +118,8 @@ _SINGLE_CTA = [c for c in CONV_CASES if c[0] in ("tiled_64_256_56", "tiled_256_6
 @pytest.mark.parametrize("case", _SINGLE_CTA, ids=[c[0] for c in _SINGLE_CTA])
 def test_single_cta_kernel_matches_the_two_cta_default(ctx, case, monkeypatch):
     """The default for 64/128/256-column tiles is the two-CTA cluster kernel (conv_pair.cu, tcgen05.mma.cta_group::2); the single-CTA
-    kernel behind SMELTER_NO_PAIR=1 must give bit-identical results (same k order, same fp32 accumulation, same epilogue)."""
+    kernel (SMELTER_NO_PAIR=1) and the half-footprint two-CTA kernel (conv_duo.cu, SMELTER_DUO=1) must give the same results: bit
+    for bit without a residual (same k order, same fp32 accumulation, same epilogue)."""
     from smelter_b200.api import Image, run_conv
 
     name, shape, co, k, s, p, d, g, act, has_bias, has_res, force = case
@@ -128,6 +138,17 @@ def test_single_cta_kernel_matches_the_two_cta_default(ctx, case, monkeypatch):
         return y.toHalfArray()
 
     pair = run()
-    monkeypatch.setenv("SMELTER_NO_PAIR", "1")  # read when the launch is prepared
+    monkeypatch.setenv("SMELTER_DUO", "1")  # read when the launch is prepared: conv_duo.cu (two 113 KiB CTAs per SM)
+    duo = run()
+    monkeypatch.delenv("SMELTER_DUO")
+    monkeypatch.setenv("SMELTER_NO_PAIR", "1")
     single = run()
     assert np.array_equal(pair.view(np.uint16), single.view(np.uint16))
+    if not has_res:
+        assert np.array_equal(duo.view(np.uint16), pair.view(np.uint16))
+    else:
+        # conv_duo.cu adds the residual inside the fp32 accumulator (identity k-blocks) and the bias after it; the other kernels add
+        # bias first, residual second: the fp32 sums may differ in the last bit, i.e. by at most one fp16 ulp after rounding
+        d = np.abs(duo.astype(np.float32) - pair.astype(np.float32))
+        ulp = np.spacing(np.maximum(np.abs(pair), np.abs(duo)).astype(np.float16)).astype(np.float32)
+        assert (d <= ulp).all()

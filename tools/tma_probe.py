@@ -21,3 +21,8 @@ if which in ("all", "overlap"):
     # rows of 64 elements (128 B) at a pitch of 16 elements (32 B): the stem's packed-row operand
     for pitch in (16, 32, 64, 128):
         run(f"tiled noswizzle {{64,128}}, row pitch {pitch*2} B", 2, pitch, 4, 400, 148, 64 * 1000 + 128, 16)
+if which in ("sweep",):
+    # per-SM ingest ceiling: does the delivered rate per SM change with the number of SMs pulling?  (port limit vs chip limit)
+    for grid in (8, 37, 74, 148):
+        for n, st in ((4, 2), (6, 2), (7, 2)):
+            run(f"{n} issuer warps x 16KiB", 5, 256, st, 400, grid, n, 16 * n)

@@ -4,8 +4,11 @@
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl native|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
-A "step" is one `encode` of one batch of 32 synthetic images per GPU (BASELINE.json configs[2]; weak scaling: every
-rank runs its own batch of 32, the only collective is the one-time NCCL weight-arena broadcast).  The model is the
+A "step" is one `encode` of one batch of synthetic images per GPU.  One GPU: batch 32 (BASELINE.json configs[2]).  N > 1 GPUs:
+BASELINE.json configs[4] as written — GLOBAL batch 256 split 256 / N per rank (strong scaling; the 32-per-GPU weak-scaling figure,
+the one-GPU batch-256 base and a bit-exact shard-parity check are measured next to it); the only collective is the one-time NCCL
+weight-arena broadcast.  `--in-flight S` (default 2) keeps S encodes in flight per GPU, each on its own stream with its own
+activation arena, the way Metal command buffers overlap; `one_in_flight` reports the strictly serial figure.  The model is the
 repo's seeded ResNet-50 (random weights: no network for checkpoints) with its 53 BatchNormalization nodes still in the
 graph, taken through the ONNX2MPS restatement with --half (BN fold, fp16, OHWI, producer stamp) exactly as the
 reference intends (README.md:54), then built and run by libsmelter_b200.so.
@@ -30,7 +33,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-PER_GPU_BATCH = 32
+PER_GPU_BATCH = 32      # BASELINE.json configs[2]
+GLOBAL_BATCH = 256      # BASELINE.json configs[4]: split 256 / N over N GPUs
 IMAGE = (3, 224, 224)
 FLOPS_PER_IMAGE = 2 * 4_089_184_256  # 53 conv + FC, algorithmic
 N_INPUT_SETS = 16                    # 16 x 9.6 MB = 154 MB of distinct inputs > 126 MB L2
@@ -52,19 +56,24 @@ def peaks() -> dict:
 
 
 def ncu_conv_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of the conv kernels of one encode, summed over the launches of a step, from
-    the committed `ncu --set full` capture of this same command (profiles/r1_encode_full.csv; cold-cache replay).  None when the
-    capture is absent."""
-    path = os.path.join(ROOT, "profiles", "r1_encode_full.csv")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the conv kernels of one encode, summed over the launches of a step, from the
+    newest committed `ncu --set full` capture of this same command (profiles/r*_encode_full.csv; cold-cache replay, so an upper
+    bound on the in-situ traffic).  Returns (bytes, source file) or (None, reason)."""
+    import csv
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_encode_full.csv")))
+    if not files:
+        return None, "no committed ncu capture"
+    path = files[-1]
     try:
-        import csv
         with open(path) as f:
             rows = list(csv.reader(f))
         head = rows[0]
         ir, iw, ik = head.index("dram_read"), head.index("dram_write"), head.index("kernel")
-        return sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_igemm" in r[ik] or "conv_mega" in r[ik] or "conv_pair" in r[ik])
-    except (OSError, ValueError):
-        return None
+        total = sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_" in r[ik])
+        return total, os.path.relpath(path, ROOT) + " (committed capture of an earlier build of this command, not this run)"
+    except (OSError, ValueError) as e:
+        return None, f"unreadable capture: {e}"
 
 
 class stdout_to_stderr:
@@ -177,6 +186,90 @@ def run_reference(args) -> int:
     return 0
 
 
+def _sets_for(batch: int) -> int:
+    """Distinct resident input batches so that the rotation is larger than the 126 MB L2 (at least two)."""
+    per = batch * IMAGE[0] * IMAGE[1] * IMAGE[2] * 2
+    return max(2, min(N_INPUT_SETS, -(-160_000_000 // per)))
+
+
+class Runner:
+    """One graph on one context; `encodes(K, S)` times K back-to-back encodes with S of them in flight (one stream each)."""
+
+    def __init__(self, torch, ctx, nn, dev, batch, seed, max_in_flight):
+        import numpy as np
+        from smelter_b200.api import Image
+
+        self.torch, self.ctx, self.nn, self.B = torch, ctx, nn, batch
+        self.sets = _sets_for(batch)
+        self.n_in = batch * IMAGE[0] * IMAGE[1] * IMAGE[2]
+        rng = np.random.default_rng(seed)
+        self.host_in = torch.empty((self.sets, batch) + IMAGE, dtype=torch.float16).pin_memory()
+        self.host_in.numpy()[...] = rng.random(self.host_in.shape, dtype=np.float32).astype(np.float16)
+        self.streams = [torch.cuda.Stream(device=dev) for _ in range(max_in_flight)]
+        self.images = [Image(ctx, batch, *IMAGE) for _ in range(self.sets)]
+        for i, img in enumerate(self.images):
+            img.copyFromPointer(self.host_in[i].data_ptr(), self.n_in, self.streams[0].cuda_stream)
+        torch.cuda.synchronize()
+
+    def encodes(self, K: int, S: int, e0=None, e1=None):
+        """K encodes round-robin over S streams.  With events: e0 is recorded before the first encode can start on any stream, e1
+        after the last encode of every stream has finished (fork / join through events on stream 0)."""
+        torch = self.torch
+        st = self.streams[:S]
+        if e0 is not None:
+            e0.record(st[0])
+            for s in st[1:]:
+                s.wait_event(e0)
+        for i in range(K):
+            self.nn.encode(to=st[i % S].cuda_stream, sourceImages=[self.images[i % self.sets]])
+        if e1 is not None:
+            for s in st[1:]:
+                ev = torch.cuda.Event()
+                ev.record(s)
+                st[0].wait_event(ev)
+            e1.record(st[0])
+
+    def timed(self, K: int, W: int, S: int, barrier, max_over_ranks) -> float:
+        torch = self.torch
+        self.encodes(max(W, S), S)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        torch.cuda.synchronize()
+        self.encodes(K, S, e0, e1)
+        torch.cuda.synchronize()
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
+
+def other_configs(torch, ctx, stream) -> dict:
+    """BASELINE.json configs[1] and configs[3] at their named shapes, timed the same way (resident input, CUDA events, graph replay)."""
+    import numpy as np
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Configuration, Image, ONNXGraph
+
+    out = {}
+    for name, model, shape, iters, gflop in (
+            ("MobileNetV2 fp16 1x3x224x224 (configs[1])", modelzoo.mobilenet_v2(seed=0, fold_bn=False), (1, 3, 224, 224), 300, 0.6015),
+            ("TransformerNet fp16 1x3x512x512 (configs[3])", modelzoo.transformer_net(seed=0, hw=512), (1, 3, 512, 512), 100, 80.63)):
+        g = ONNXGraph(onnx2mps.convert_bytes(model.serialize(), half=True), Configuration(), context=ctx)
+        nn = g.metalGraph()
+        img = Image.fromArray(ctx, np.random.default_rng(1).random(shape, dtype=np.float32).astype(np.float16))
+        for _ in range(5):
+            nn.encode(to=stream.cuda_stream, sourceImages=[img])
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(iters):
+            nn.encode(to=stream.cuda_stream, sourceImages=[img])
+        e1.record(stream)
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        out[name] = {"ms_per_encode": ms, "images_per_s": shape[0] / ms * 1e3, "launches": nn.numLaunches(shape[0]), "tflops": gflop * shape[0] / ms}
+        g.close()
+    return out
+
+
 def run_native(args) -> int:
     import numpy as np
     import torch
@@ -191,6 +284,7 @@ def run_native(args) -> int:
     dev = torch.device("cuda", local_rank)
     quiet = stdout_to_stderr()
     quiet.__enter__()  # until the weight replicas are in place (below)
+    t_init = time.perf_counter()
     if world > 1:
         sdist.init_process_group("nccl")
     import torch.distributed as dist
@@ -199,20 +293,37 @@ def run_native(args) -> int:
         if world > 1:
             dist.barrier(device_ids=[local_rank])
 
-    K, W, B = args.steps, max(args.warmup, 3), args.batch
+    def max_over_ranks(v: float) -> float:
+        return sdist.max_over_ranks(v, dev) if world > 1 else v
+
+    # Workload: one GPU = BASELINE.json configs[2] (batch 32); N > 1 = configs[4]: ResNet-50, GLOBAL batch 256 split 256 / N per rank
+    # (strong scaling; the 32-per-GPU weak-scaling figure is measured next to it).
+    K, W, S = args.steps, max(args.warmup, 3), max(1, args.in_flight)
+    G = args.global_batch or (PER_GPU_BATCH if world == 1 else GLOBAL_BATCH)
+    if args.batch:
+        G = args.batch * world
+    if G % world:
+        raise SystemExit(f"global batch {G} does not split over {world} ranks")
+    B = G // world
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank, stream=stream.cuda_stream)
     data = model_bytes()
     graph = ONNXGraph(data, Configuration(deferWeights=(world > 1 and rank != 0)), context=ctx)
     assert graph.modelFormat == Format.mpsFlavor
     nn = graph.metalGraph()
-    bcast_ms = None
+    comm_ms = bcast_ms = None
     if world > 1:  # one-time weight replica over NVLink
         uid = sdist.share_bytes(Context.ncclUniqueId() if rank == 0 else b"", 0)
-        ctx.initNCCL(uid, rank, world)
         barrier()
         t0 = time.perf_counter()
-        nn.broadcastWeights(0)
+        ctx.initNCCL(uid, rank, world)
+        nn.broadcastWeights(0)          # first collective on the engine's communicator: includes its bring-up (channels, NVLS setup)
+        ctx.synchronize()
+        comm_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        t0 = time.perf_counter()
+        nn.broadcastWeights(0)          # the 51 MB broadcast by itself
+        ctx.synchronize()
         bcast_ms = (time.perf_counter() - t0) * 1e3
         checksum, _ = nn.weightChecksum()
         if not sdist.all_equal(checksum, dev):
@@ -220,90 +331,119 @@ def run_native(args) -> int:
     barrier()
     quiet.__exit__()
 
-    rng = np.random.default_rng(1 + rank)
-    host_in = torch.empty((N_INPUT_SETS, B) + IMAGE, dtype=torch.float16).pin_memory()
-    host_in.numpy()[...] = rng.random(host_in.shape, dtype=np.float32).astype(np.float16)
-    images = [Image(ctx, B, *IMAGE) for _ in range(N_INPUT_SETS)]
-    n_in = B * IMAGE[0] * IMAGE[1] * IMAGE[2]
-    for i, img in enumerate(images):
-        img.copyFromPointer(host_in[i].data_ptr(), n_in, stream.cuda_stream)
-    ctx.synchronize()
-
-    # ---- device-resident throughput -------------------------------------------------------------------------------
-    for i in range(W):
-        nn.encode(sourceImages=[images[i % N_INPUT_SETS]])
-    ctx.synchronize()
+    run = Runner(torch, ctx, nn, dev, B, 1 + rank, max(S, 2))
+    # ---- device-resident throughput: K encodes, S in flight (each on its own stream / activation arena) -----------------------
     sampler = ClockSampler(local_rank)
     time.sleep(0.3)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    torch.cuda.synchronize()
     lo = sampler.mark()
-    with torch.cuda.stream(stream):
-        e0.record(stream)
-        for i in range(K):
-            nn.encode(sourceImages=[images[i % N_INPUT_SETS]])
-        e1.record(stream)
-    torch.cuda.synchronize()
-    barrier()
+    elapsed_ms = run.timed(K, W, S, barrier, max_over_ranks)
     hi = sampler.mark()
-    elapsed_ms = e0.elapsed_time(e1)
-    if world > 1:
-        elapsed_ms = sdist.max_over_ranks(elapsed_ms, dev)
     value = world * B * K / (elapsed_ms * 1e-3)
     launches = nn.numLaunches(B) * K
+    # latency of one encode with nothing else in flight (what round 1 reported as the step)
+    K1 = min(K, 300)
+    one_ms = run.timed(K1, W, 1, barrier, max_over_ranks) / K1
 
-    # ---- end to end through the public API with host buffers --------------------------------------------------------
+    # ---- end to end through the public API with host buffers, S batches in flight ----------------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
-    dev_in = [Image(ctx, B, *IMAGE), Image(ctx, B, *IMAGE)]
-    copied = [torch.cuda.Event(), torch.cuda.Event()]
-    host_out = torch.empty((2, B, 1000), dtype=torch.float32).pin_memory()  # double-buffered results
-    out_np = [host_out[0].numpy(), host_out[1].numpy()]
-    landed = [torch.cuda.Event(), torch.cuda.Event()]
+    n_in = run.n_in
+    slots = max(4, 2 * S)   # uploads run this many steps ahead of the host's read-back
+    dev_in = [Image(ctx, B, *IMAGE) for _ in range(slots)]
+    copied = [torch.cuda.Event() for _ in range(slots)]
+    landed = [torch.cuda.Event() for _ in range(slots)]
+    host_out = torch.empty((slots, B, 1000), dtype=torch.float32).pin_memory()
+    out_np = [host_out[i].numpy() for i in range(slots)]
     checksum = [0.0]
 
     def e2e_loop(n_steps: int) -> float:
-        """Every step: H2D of its input batch (copy stream), encode, D2H of its logits into pinned host memory; the host reads
-        step i-1's logits while step i runs (one step of queue depth, like committing the next Metal command buffer before
-        waiting on the previous one), and the last step's logits before the clock stops."""
+        """Every step: H2D of its input batch (copy stream) into the slot's source image, encode on the slot's stream, D2H of its fp32
+        logits into pinned host memory.  `slots` batches are in flight: before a slot is reused the host waits for that slot's
+        previous logits and reads them (committing the next Metal command buffers before waiting on an earlier one); the last
+        steps' logits are read before the clock stops."""
         t0 = time.perf_counter()
-        dev_in[0].copyFromPointer(host_in[0].data_ptr(), n_in, copy_stream.cuda_stream)  # step 0's upload, inside the timed region
-        copied[0].record(copy_stream)
         for i in range(n_steps):
-            cur, nxt = i % 2, (i + 1) % 2
-            if i + 1 < n_steps:  # overlap the next batch's upload with this batch's compute (double-buffered source images)
-                if i > 0:
-                    copy_stream.wait_event(landed[nxt])  # step i-1 read dev_in[nxt]: do not overwrite it before that encode is done
-                dev_in[nxt].copyFromPointer(host_in[(i + 1) % N_INPUT_SETS].data_ptr(), n_in, copy_stream.cuda_stream)
-                copied[nxt].record(copy_stream)
-            stream.wait_event(copied[cur])
-            res = nn.encode(sourceImages=[dev_in[cur]])
-            res.toFloatArrayAsync(out_np[cur])   # fp32 logits -> pinned host buffer, enqueued behind the encode
-            landed[cur].record(stream)
-            if i > 0:
-                landed[nxt].synchronize()         # step i-1's logits are on the host: use them
-                checksum[0] += float(out_np[nxt][0, 0])
-        landed[(n_steps - 1) % 2].synchronize()
-        checksum[0] += float(out_np[(n_steps - 1) % 2][0, 0])
+            s = i % slots
+            if i >= slots:
+                landed[s].synchronize()          # step i - slots is complete: its logits are on the host, its source image is free
+                checksum[0] += float(out_np[s][0, 0])
+            dev_in[s].copyFromPointer(run.host_in[i % run.sets].data_ptr(), n_in, copy_stream.cuda_stream)
+            copied[s].record(copy_stream)
+            st = run.streams[s % S]
+            st.wait_event(copied[s])
+            res = nn.encode(to=st.cuda_stream, sourceImages=[dev_in[s]])
+            res.toFloatArrayAsync(out_np[s], stream=st.cuda_stream)  # fp32 logits -> pinned host buffer, enqueued behind the encode
+            landed[s].record(st)
+        for i in range(max(0, n_steps - slots), n_steps):
+            landed[i % slots].synchronize()
+            checksum[0] += float(out_np[i % slots][0, 0])
         return time.perf_counter() - t0
 
-    e2e_loop(W)
+    e2e_loop(W + slots)
     barrier()
     torch.cuda.synchronize()
     e2e_s = e2e_loop(K)
     torch.cuda.synchronize()
     barrier()
-    if world > 1:
-        e2e_s = sdist.max_over_ranks(e2e_s, dev)
+    e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * B * K / e2e_s
     clocks = sampler.stop(lo, hi)
+
+    # ---- multi-GPU: weak-scaling figure, 1-GPU batch-256 base, shard parity ----------------------------------------------------
+    extra = {}
+    if world > 1:
+        if B == PER_GPU_BATCH:
+            weak_value = value
+        else:
+            weak = Runner(torch, ctx, nn, dev, PER_GPU_BATCH, 101 + rank, max(S, 2))
+            weak_value = world * PER_GPU_BATCH * K / (weak.timed(K, W, S, barrier, max_over_ranks) * 1e-3)
+            del weak
+        extra["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "value": weak_value, "unit": "images/s"}
+        # strong-scaling base: the whole global batch on ONE GPU (every rank times it on its own GPU; they do not share anything)
+        if B == G:
+            base_value = value
+        else:
+            k256 = max(20, min(K, 100))
+            full = Runner(torch, ctx, nn, dev, G, 201, max(S, 2))
+            base_value = G * k256 / (full.timed(k256, W, S, barrier, max_over_ranks) * 1e-3)
+        extra["strong_scaling"] = {"global_batch": G, "one_gpu_value": base_value, "efficiency_vs_one_gpu": value / (world * base_value),
+                                   "note": "value / (N x the same global batch on one GPU, measured in this run)"}
+        # shard parity: every rank holds the SAME seeded global batch, encodes its contiguous slice, rank 0 compares the gathered
+        # logits with its own one-GPU encode of the whole batch.  Bit-exact with one k-reduction order per layer (SMELTER_NO_SPLITK=1:
+        # the default plans may split K for some batch sizes, which only re-associates fp32 sums; that difference is reported too).
+        xg = np.random.default_rng(7).random((G,) + IMAGE, dtype=np.float32).astype(np.float16)
+        lo_i, hi_i = sdist.shard_range(G, rank, world)
+
+        def logits(nn_, x):
+            r = nn_.encode(sourceImages=[Image.fromArray(ctx, x)])
+            return torch.from_numpy(r.toHalfArray().reshape(x.shape[0], -1).copy()).to(dev)  # fp16: all_gather moves the bits
+
+        def gathered(nn_):
+            mine = logits(nn_, xg[lo_i:hi_i])
+            parts = [torch.empty_like(mine) for _ in range(world)]
+            dist.all_gather(parts, mine)
+            return torch.cat(parts).cpu().numpy()
+
+        g_default = gathered(nn)
+        os.environ["SMELTER_NO_SPLITK"] = "1"   # read when a plan is made: fresh graph, same weights
+        graph2 = ONNXGraph(data, Configuration(), context=ctx)
+        nn2 = graph2.metalGraph()
+        g_exact = gathered(nn2)
+        if rank == 0:
+            full_exact = logits(nn2, xg).cpu().numpy()
+            full_default = logits(nn, xg).cpu().numpy()
+            extra["shard_parity"] = bool(np.array_equal(g_exact.view(np.uint16), full_exact.view(np.uint16)))
+            extra["shard_parity_how"] = {"bit_exact_with_one_k_order_per_layer": extra["shard_parity"],
+                                         "default_plans_max_abs_diff": float(np.abs(g_default.astype(np.float32) - full_default.astype(np.float32)).max()),
+                                         "images": G, "gathered_over": "torch.distributed all_gather of fp16 logits"}
+        del os.environ["SMELTER_NO_SPLITK"]
+        graph2.close()
 
     # ---- roofline of the dominant kernel (tcgen05 implicit-GEMM conv), measured live with CUDA events --------------------
     # Every kernel of one encode is bracketed by CUDA-event record nodes inside a captured graph (smelter_graph_profile), which
     # gives each kernel's duration in situ.  The event nodes themselves cost a few us per kernel and defeat PDL overlap, so the
     # per-kernel numbers are used for the conv kernels' SHARE of the step; the absolute duration is pinned to the event-timed
     # step above: conv_ms = ms_per_step x share.  Both the raw and the pinned figures are reported.
-    prof = nn.profile([images[0]], iters=5, stream=stream.cuda_stream)
+    prof = nn.profile([run.images[0]], iters=5, stream=stream.cuda_stream)
     conv = [p for p in prof if p["tensor"]]
     conv_ms_raw = sum(p["ms"] for p in conv)
     conv_flops = sum(p["flops"] for p in conv)
@@ -313,13 +453,18 @@ def run_native(args) -> int:
     conv_ms = step_ms * share
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
+    traffic, traffic_src = ncu_conv_traffic()
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
-                "traffic": ncu_conv_traffic(), "kernel": f"conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> ({len(conv)} conv/gemm launches per step, aggregated; "
+                "frac_of_burst_peak": achieved / pk["tflops_burst"], "burst_peak": pk["tflops_burst"],
+                "traffic": traffic, "traffic_source": traffic_src,
+                "kernel": f"conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> ({len(conv)} conv/gemm launches per step, aggregated; "
                           f"{sum('+conv1x1(' in p['desc'] for p in conv)} of them carry a folded 1x1 projection shortcut)",
-                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json)", "kernel_share_of_step": share,
+                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json); frac_of_burst_peak uses bf16_tflops", "kernel_share_of_step": share,
                 "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
                 "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,
-                "how": "algorithmic FLOPs (2*M*N*K, SURVEY 8d) / (event-timed step x conv share from in-graph per-kernel events)",
+                "achieved_one_in_flight": conv_flops / (one_ms * share * 1e-3) / 1e12 if one_ms > 0 else 0.0,
+                "how": "algorithmic FLOPs (2*M*N*K, SURVEY 8d) / (event-timed step x conv share from in-graph per-kernel events); "
+                       f"step = elapsed / steps with {S} encodes in flight",
                 "step_frac_of_conv_roofline": value / world / (pk["tflops_sustained"] * 1e12 / FLOPS_PER_IMAGE)}
     if rank == 0:
         outdir = os.path.join(ROOT, "gpurun_out")
@@ -331,19 +476,31 @@ def run_native(args) -> int:
             pass
 
     line = {"metric": "ResNet-50 fp16 224x224 images/sec", "value": value, "unit": "images/s", "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
-            "config": {"workload": "ResNet-50 fp16 224x224 batch=32 per GPU (BASELINE.json configs[2]; N GPUs = configs[4] weak-scaled)",
-                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": world * B,
+            "ms_per_step": elapsed_ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f16",
+            "data": "synthetic",
+            "config": {"workload": ("ResNet-50 fp16 224x224 batch=32 on one GPU (BASELINE.json configs[2])" if world == 1 and G == PER_GPU_BATCH else
+                                    f"ResNet-50 fp16 224x224 global batch={G} batch-sharded {B} per GPU over {world} GPU(s) (BASELINE.json configs[4])"),
+                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": G,
                        "per_gpu_batch": B, "parallelism": f"batch-sharded dp{world}, one NCCL weight broadcast, no steady-state collective",
-                       "l2": f"inputs larger than L2: {N_INPUT_SETS} distinct resident batches (154 MB) rotated, no flush",
+                       "in_flight": S, "in_flight_note": f"{S} encodes in flight per GPU, each on its own stream with its own activation arena "
+                       "(the reference's encode(to: commandBuffer) is asynchronous in the same way); ms_per_step = elapsed / steps",
+                       "l2": f"inputs larger than L2: {run.sets} distinct resident batches ({run.sets * run.n_in * 2 / 1e6:.0f} MB) rotated, no flush",
                        "cuda_graph": True, "accumulate": "fp32 (TMEM)"},
+            "one_in_flight": {"ms_per_step": one_ms, "value": world * B / (one_ms * 1e-3), "unit": "images/s", "steps": K1},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": n_in * 2, "d2h_bytes_per_step": B * 1000 * 4,
-                    "ms_per_step": e2e_s / K * 1e3, "how": "pinned host fp16 batch -> Image.copyFromPointer (copy stream, double-buffered) -> encode -> "
-                    "toFloatArrayAsync (fp32 logits into pinned host memory every step; the host consumes step i-1's logits while step i runs, "
-                    "the last step's before the clock stops); wall clock"},
+                    "ms_per_step": e2e_s / K * 1e3, "how": "pinned host fp16 batch -> Image.copyFromPointer (copy stream) -> encode -> "
+                    f"toFloatArrayAsync (fp32 logits into pinned host memory every step), {slots} batches in flight: the host reads a slot's logits "
+                    "before it reuses the slot, the last steps' before the clock stops; wall clock"},
             "gpu_launches": launches, "launches_per_step": nn.numLaunches(B), "clocks": clocks, "roofline": roofline}
-    if bcast_ms is not None:
+    line.update(extra)
+    if comm_ms is not None:
         line["weight_broadcast_ms"] = bcast_ms
+        line["weight_broadcast"] = {"communicator_bring_up_plus_first_broadcast_ms": comm_ms, "broadcast_ms": bcast_ms, "bytes": nn.weightChecksum()[1]}
+    if world == 1 and not args.no_extra:
+        try:
+            line["other_configs"] = other_configs(torch, ctx, stream)
+        except Exception as e:  # never lose the headline line to an extra
+            line["other_configs"] = {"error": str(e)[:200]}
     if world == 1 and not args.no_cpu:
         base = cpu_reference(steps=3, warmup=1, budget_s=20.0)
         line["cpu_baseline"] = {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -360,8 +517,11 @@ def main() -> int:
     ap.add_argument("--steps", type=int, default=1000)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU per step (the metric is quoted at 32)")
+    ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 32 on one GPU, 256 / N on N GPUs)")
+    ap.add_argument("--global-batch", type=int, default=0, help="global batch split over the ranks (default: 32 for one GPU, 256 for N > 1)")
+    ap.add_argument("--in-flight", type=int, default=2, help="encodes in flight per GPU, each on its own stream (1 = strictly one at a time)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] / configs[3] latency fields")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

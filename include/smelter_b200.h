@@ -152,7 +152,10 @@ int32_t smelter_graph_profile(smelter_graph* g, void* cuda_stream, const smelter
 
 /* ---- inference ------------------------------------------------------------------------------------------
  * MPSNNGraph.encode(to:sourceImages:) (README.md:43-44): enqueue only, no synchronisation.  `*result` is
- * owned by the graph and valid until the next encode on this graph.  Batch = leading dim of sources[0]. */
+ * owned by the graph and valid until the next encode on this graph with the same `cuda_stream` (NULL = the context's).
+ * Like Metal command buffers, encodes on DIFFERENT streams may be in flight together: each (batch size, stream) owns its
+ * activation arena and captured CUDA graph (at most 8 streams per batch size); on one stream they run in order.
+ * Batch = leading dim of sources[0]. */
 int32_t smelter_graph_encode(smelter_graph* g, void* cuda_stream, const smelter_tensor* const* sources, int32_t n_sources,
                              const smelter_tensor** result);
 

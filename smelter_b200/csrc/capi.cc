@@ -68,6 +68,7 @@ int32_t smelter_context_destroy(smelter_context* ctx) {
     if (!ctx) return SMELTER_OK;
     nccl_destroy(&ctx->c);
     if (ctx->c.flush_buf) cudaFree(ctx->c.flush_buf);
+    for (auto& kv : ctx->c.staging) if (kv.second.ptr) cudaFree(kv.second.ptr);
     if (ctx->c.own_stream) cudaStreamDestroy(ctx->c.stream);
     delete ctx;
     return SMELTER_OK;
@@ -127,15 +128,17 @@ int32_t smelter_tensor_device_ptr(const smelter_tensor* t, void** ptr) {
 }
 
 namespace {
-// staging buffers for fp32<->fp16 conversion at the boundary, one per context/device (grown on demand)
-struct Staging { void* ptr = nullptr; size_t bytes = 0; };
-thread_local Staging g_staging;
-int ensure_staging(size_t bytes) {
-    if (g_staging.bytes >= bytes) return SMELTER_OK;
-    if (g_staging.ptr) cudaFree(g_staging.ptr);
-    g_staging = Staging();
-    SM_CUDA(cudaMalloc(&g_staging.ptr, bytes));
-    g_staging.bytes = bytes;
+// staging buffer for fp32<->fp16 / u8 conversion at the boundary: per (context, stream), see Context::staging
+int ensure_staging(Context* ctx, cudaStream_t s, size_t bytes, void** out) {
+    std::lock_guard<std::mutex> lock(ctx->staging_mu);
+    Context::Staging& st = ctx->staging[s];
+    if (st.bytes < bytes) {
+        if (st.ptr) cudaFree(st.ptr);  // synchronises: nothing in flight still reads the old buffer
+        st = Context::Staging();
+        SM_CUDA(cudaMalloc(&st.ptr, bytes));
+        st.bytes = bytes;
+    }
+    *out = st.ptr;
     return SMELTER_OK;
 }
 }  // namespace
@@ -144,10 +147,11 @@ int32_t smelter_tensor_from_float(smelter_tensor* t, void* cuda_stream, const fl
     ARG(t && host && count == t->t.count());
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
     SM_CUDA(cudaSetDevice(t->t.ctx->device));
-    int rc = ensure_staging(count * 4);
+    void* stage = nullptr;
+    int rc = ensure_staging(t->t.ctx, s, count * 4, &stage);
     if (rc) return rc;
-    SM_CUDA(cudaMemcpyAsync(g_staging.ptr, host, count * 4, cudaMemcpyHostToDevice, s));
-    SM_CUDA(k::f32_to_f16(static_cast<const float*>(g_staging.ptr), t->t.ptr, count, s));
+    SM_CUDA(cudaMemcpyAsync(stage, host, count * 4, cudaMemcpyHostToDevice, s));
+    SM_CUDA(k::f32_to_f16(static_cast<const float*>(stage), t->t.ptr, count, s));
     return SMELTER_OK;
 }
 int32_t smelter_tensor_from_half(smelter_tensor* t, void* cuda_stream, const uint16_t* host, size_t count) {
@@ -162,12 +166,13 @@ int32_t smelter_tensor_from_u8(smelter_tensor* t, void* cuda_stream, const uint8
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
     SM_CUDA(cudaSetDevice(t->t.ctx->device));
     const size_t hw = size_t(t->t.h) * t->t.w, bytes = size_t(t->t.n) * hw * src_channels;
-    int rc = ensure_staging(bytes);
+    void* stage = nullptr;
+    int rc = ensure_staging(t->t.ctx, s, bytes, &stage);
     if (rc) return rc;
     float sc4[4], b4[4];
     for (int i = 0; i < 4; ++i) { sc4[i] = scale && i < t->t.c ? scale[i] : 1.f / 255.f; b4[i] = bias && i < t->t.c ? bias[i] : 0.f; }
-    SM_CUDA(cudaMemcpyAsync(g_staging.ptr, host, bytes, cudaMemcpyHostToDevice, s));
-    SM_CUDA(k::u8_to_nchw_f16(static_cast<const uint8_t*>(g_staging.ptr), t->t.ptr, t->t.n, t->t.c, hw, src_channels, sc4, b4, s));
+    SM_CUDA(cudaMemcpyAsync(stage, host, bytes, cudaMemcpyHostToDevice, s));
+    SM_CUDA(k::u8_to_nchw_f16(static_cast<const uint8_t*>(stage), t->t.ptr, t->t.n, t->t.c, hw, src_channels, sc4, b4, s));
     return SMELTER_OK;
 }
 int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, float* host, size_t capacity) {
@@ -175,10 +180,11 @@ int32_t smelter_tensor_to_float(const smelter_tensor* t, void* cuda_stream, floa
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
     SM_CUDA(cudaSetDevice(t->t.ctx->device));
     const size_t count = t->t.count();
-    int rc = ensure_staging(count * 4);
+    void* stage = nullptr;
+    int rc = ensure_staging(t->t.ctx, s, count * 4, &stage);
     if (rc) return rc;
-    SM_CUDA(k::f16_to_f32(t->t.ptr, static_cast<float*>(g_staging.ptr), count, s));
-    SM_CUDA(cudaMemcpyAsync(host, g_staging.ptr, count * 4, cudaMemcpyDeviceToHost, s));
+    SM_CUDA(k::f16_to_f32(t->t.ptr, static_cast<float*>(stage), count, s));
+    SM_CUDA(cudaMemcpyAsync(host, stage, count * 4, cudaMemcpyDeviceToHost, s));
     SM_CUDA(cudaStreamSynchronize(s));
     return SMELTER_OK;
 }
@@ -207,10 +213,11 @@ int32_t smelter_tensor_to_float_async(const smelter_tensor* t, void* cuda_stream
     cudaStream_t s = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : t->t.ctx->stream;
     SM_CUDA(cudaSetDevice(t->t.ctx->device));
     const size_t count = t->t.count();
-    int rc = ensure_staging(count * 4);  // one staging buffer: uses on the same stream are ordered by the stream
+    void* stage = nullptr;
+    int rc = ensure_staging(t->t.ctx, s, count * 4, &stage);  // per stream: uses on the same stream are ordered by the stream
     if (rc) return rc;
-    SM_CUDA(k::f16_to_f32(t->t.ptr, static_cast<float*>(g_staging.ptr), count, s));
-    SM_CUDA(cudaMemcpyAsync(host, g_staging.ptr, count * 4, cudaMemcpyDeviceToHost, s));
+    SM_CUDA(k::f16_to_f32(t->t.ptr, static_cast<float*>(stage), count, s));
+    SM_CUDA(cudaMemcpyAsync(host, stage, count * 4, cudaMemcpyDeviceToHost, s));
     return SMELTER_OK;
 }
 int32_t smelter_tensor_to_half(const smelter_tensor* t, void* cuda_stream, uint16_t* host, size_t capacity) {

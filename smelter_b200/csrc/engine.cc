@@ -450,10 +450,16 @@ struct ArenaAlloc {
 
 }  // namespace
 
-int ONNXGraph::plan_for(int batch, Plan** out) {
+int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
     if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
-    auto it = plans_.find(batch);
+    const std::pair<int, uintptr_t> key(batch, (stream == nullptr || stream == ctx_->stream) ? uintptr_t(0) : reinterpret_cast<uintptr_t>(stream));
+    auto it = plans_.find(key);
     if (it != plans_.end()) { *out = it->second.get(); return SMELTER_OK; }
+    {   // every stream that encodes this batch size owns an activation arena: bound the number of them
+        int same_batch = 0;
+        for (const auto& kv : plans_) same_batch += kv.first.first == batch;
+        if (same_batch >= 8) return fail(SMELTER_ERR_INCONSISTENT_STATE, "more than 8 streams encode batch " + std::to_string(batch) + " on one graph");
+    }
     SM_CUDA(cudaSetDevice(ctx_->device));
     auto plan = std::make_unique<Plan>();
     plan->batch = batch;
@@ -1018,7 +1024,7 @@ int ONNXGraph::plan_for(int batch, Plan** out) {
         plan->result.ptr = dst;
     }
     *out = plan.get();
-    plans_[batch] = std::move(plan);
+    plans_[key] = std::move(plan);
     return SMELTER_OK;
 }
 
@@ -1031,7 +1037,7 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     const int batch = sources[0]->n;
     if (batch <= 0) return fail(SMELTER_ERR_INVALID_ARGUMENT, "empty batch");
     Plan* plan = nullptr;
-    int rc = plan_for(batch, &plan);
+    int rc = plan_for(batch, &plan, stream);
     if (rc) return rc;
     for (int i = 0; i < n_sources; ++i) {
         const ImageShape& s = plan->src_shapes[size_t(i)];

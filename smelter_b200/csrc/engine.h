@@ -13,6 +13,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -44,6 +45,11 @@ struct Context {
     // benchmark helper: scratch larger than L2, written by smelter_l2_flush
     void* flush_buf = nullptr;
     size_t flush_bytes = 0;
+    // fp32 <-> fp16 / u8 conversion staging at the boundary: one device buffer per stream of this context (uses on one stream are
+    // ordered by the stream; different streams never share a buffer), grown on demand, freed with the context
+    struct Staging { void* ptr = nullptr; size_t bytes = 0; };
+    std::map<cudaStream_t, Staging> staging;
+    std::mutex staging_mu;
 };
 
 struct Tensor {
@@ -146,7 +152,9 @@ class ONNXGraph {
     Context* ctx() const { return ctx_; }
     const std::vector<Value>& values() const { return values_; }
 
-    int plan_for(int batch, Plan** out);
+    // One plan (activation arena, captured CUDA graph, result tensor) per (batch size, stream): encodes on different streams own
+    // different arenas and may be in flight together; on one stream they are ordered by the stream.  stream == nullptr is the context's.
+    int plan_for(int batch, Plan** out, cudaStream_t stream = nullptr);
     int num_launches(int batch, int* n);
     int profile(cudaStream_t stream, const Tensor* const* sources, int n_sources, int iters, std::vector<float>* ms,
                 std::vector<double>* flops, std::vector<double>* bytes, std::vector<int>* is_tensor);
@@ -179,7 +187,7 @@ class ONNXGraph {
 
     void* weight_arena_ = nullptr;
     size_t weight_bytes_ = 0;
-    std::map<int, std::shared_ptr<Plan>> plans_;
+    std::map<std::pair<int, uintptr_t>, std::shared_ptr<Plan>> plans_;
 };
 
 // ---- shared host helpers (also exported through the C ABI) -------------------------------------------------

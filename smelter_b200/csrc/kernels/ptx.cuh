@@ -52,8 +52,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// SMELTER_TRYWAIT_HINT_NS > 0: pass a suspend-time hint, so that a waiting thread sleeps in hardware for up to that long (or until the
+// phase completes) instead of coming back to spin in the caller's loop, where it competes for issue slots with the epilogue warps.
+#ifndef SMELTER_TRYWAIT_HINT_NS
+#define SMELTER_TRYWAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if SMELTER_TRYWAIT_HINT_NS > 0
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(uint32_t(SMELTER_TRYWAIT_HINT_NS))
+        : "memory");
+#else
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
@@ -63,6 +79,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Non-blocking probe (try_wait may suspend the thread up to a hardware time limit): used to look one stage ahead.

@@ -148,7 +148,8 @@ def test_single_cta_kernel_matches_the_two_cta_default(ctx, case, monkeypatch):
         assert np.array_equal(duo.view(np.uint16), pair.view(np.uint16))
     else:
         # conv_duo.cu adds the residual inside the fp32 accumulator (identity k-blocks) and the bias after it; the other kernels add
-        # bias first, residual second: the fp32 sums may differ in the last bit, i.e. by at most one fp16 ulp after rounding
+        # bias first, residual second: the fp32 sums differ by re-association only (~2^-23 of the O(1..10) operands, which can be
+        # several ulps of an output that cancels to almost zero), i.e. by at most one fp16 ulp of the result after rounding
         d = np.abs(duo.astype(np.float32) - pair.astype(np.float32))
         ulp = np.spacing(np.maximum(np.abs(pair), np.abs(duo)).astype(np.float16)).astype(np.float32)
-        assert (d <= ulp).all()
+        assert (d <= np.maximum(ulp, 8e-6)).all()

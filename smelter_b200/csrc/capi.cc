@@ -830,19 +830,29 @@ int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* 
     const int ocp = round_up(oc, 8);
     struct Bufs {
         void *xi = nullptr, *x2i = nullptr, *yo = nullptr, *q0 = nullptr, *q1 = nullptr, *scratch = nullptr;
+        void *raw_x2 = nullptr, *raw_y = nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        ~Bufs() { cudaFree(xi); cudaFree(x2i); cudaFree(yo); cudaFree(q0); cudaFree(q1); cudaFree(scratch); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+        ~Bufs() { cudaFree(xi); cudaFree(raw_x2); cudaFree(raw_y); cudaFree(q0); cudaFree(q1); cudaFree(scratch); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
     } B;
+    // The operands of a streaming kernel advance through their buffers in lock-step.  cudaMalloc hands out 2 MiB-aligned blocks, so
+    // equal offsets of input and output would keep landing on the same DRAM channels / banks (measured: the two-input add fell
+    // from 98 % to 14-32 % of the copy rate depending on what the allocator had handed out before).  The engine's arena places
+    // tensors at arbitrary 256-byte offsets; this harness staggers its buffers by odd multiples of 4 KiB to measure the same thing.
+    // SMELTER_EW_STAGGER = k: offsets of k x 641 x 4 KiB between the buffers (default 1); the benchmark tool tries several placements.
+    const char* stg = getenv("SMELTER_EW_STAGGER");
+    const size_t kStagger = size_t(stg ? std::max(0, atoi(stg)) : 1) * 641 * 4096;
     const size_t in_elems = size_t(N) * H * W * cp, out_elems = size_t(N) * oh * ow * ocp;
     SM_CUDA(cudaMalloc(&B.xi, in_elems * 2));
-    SM_CUDA(cudaMalloc(&B.yo, out_elems * 2));
+    SM_CUDA(cudaMalloc(&B.raw_y, out_elems * 2 + kStagger));
+    B.yo = static_cast<char*>(B.raw_y) + kStagger;
     SM_CUDA(cudaMemsetAsync(B.yo, 0xff, out_elems * 2, s));
     SM_CUDA(k::nchw_to_nhwc(static_cast<const __half*>(x), static_cast<__half*>(B.xi), N, Cc, H, W, cp, 0, 0, 0, 0, s));
     int c2p = 0;
     if (x2) {
         const int c2 = p->op == SMELTER_EW_CONCAT ? p->c2 : Cc;
         c2p = round_up(c2, 8);
-        SM_CUDA(cudaMalloc(&B.x2i, size_t(N) * H * W * c2p * 2));
+        SM_CUDA(cudaMalloc(&B.raw_x2, size_t(N) * H * W * c2p * 2 + 2 * kStagger));
+        B.x2i = static_cast<char*>(B.raw_x2) + 2 * kStagger;
         SM_CUDA(k::nchw_to_nhwc(static_cast<const __half*>(x2), static_cast<__half*>(B.x2i), N, c2, H, W, c2p, 0, 0, 0, 0, s));
     }
     if (p0 && p1) {
@@ -855,7 +865,7 @@ int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* 
         SM_CUDA(cudaMemcpy(B.q1, b.data(), size_t(cp) * 4, cudaMemcpyHostToDevice));
     }
     if (p->op == SMELTER_EW_INSTANCE_NORM)
-        SM_CUDA(cudaMalloc(&B.scratch, size_t(N) * k::instance_norm_splits(H * W, cp) * cp * 2 * sizeof(float)));
+        SM_CUDA(cudaMalloc(&B.scratch, k::instance_norm_scratch_floats(N, H * W, cp) * sizeof(float)));
     if (p->op == SMELTER_EW_CONCAT && ocp != oc) SM_CUDA(cudaMemsetAsync(B.yo, 0, out_elems * 2, s));
     const __half* xi = static_cast<const __half*>(B.xi);
     const __half* x2i = static_cast<const __half*>(B.x2i);

@@ -678,7 +678,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         }
         if (f.kind == FilterKind::InstanceNorm) {
             const ImageShape& s = values_[size_t(f.in[0])].shape;
-            scratch[fi].bytes = size_t(N) * k::instance_norm_splits(s.h * s.w, round_up(s.c, 8)) * round_up(s.c, 8) * 2 * sizeof(float);
+            scratch[fi].bytes = k::instance_norm_scratch_floats(N, s.h * s.w, round_up(s.c, 8)) * sizeof(float);
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
         if (f.kind == FilterKind::Reshape) {
@@ -922,8 +922,8 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c;
                 add_step(std::string(group_size > 1 ? "group_norm " : "instance_norm ") + name,
                          [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels); }, 0,
-                         io_bytes + double(N) * is.h * is.w * icp * 2);
-                plan->steps.back().launches = 2;
+                         io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)
+                plan->steps.back().launches = k::instance_norm_launches(N, is.h * is.w, icp);
                 break;
             }
             case FilterKind::Unary: {

@@ -29,6 +29,13 @@ inline int grid_for(size_t work_items, int per_block = kThreads) {
     return int(blocks);
 }
 
+// one block per kThreads * per_thread work items, no cap (the block-tiled streaming kernels do not loop)
+inline unsigned tiled_grid(size_t work_items, int per_thread) {
+    const size_t per_block = size_t(kThreads) * per_thread;
+    const size_t blocks = (work_items + per_block - 1) / per_block;
+    return unsigned(blocks < 1 ? 1 : blocks);
+}
+
 struct alignas(16) Half8 {
     __half2 v[4];
 };
@@ -74,9 +81,18 @@ __device__ __forceinline__ float unary_op(float x, int kind, float a, float b) {
     }
 }
 
-// Streaming kernels keep kUnroll independent 128-bit loads in flight per thread before the first use: with one load per
-// thread per iteration these kernels sat at 55-68 % of the HBM copy rate, the two-input add (two loads in flight) at 97 %.
-constexpr int kUnroll = 4;
+// Streaming kernels: every block owns a contiguous run of kThreads * U 128-bit vectors; a thread issues its U loads (4 KiB apart, each
+// a fully coalesced warp access) before the first use.  With one load in flight per thread these kernels sat at 55-68 % of the HBM
+// copy rate; 8 in flight per thread (32 KiB per block) reach the copy rate.  Index arithmetic is 32-bit wherever the tensor allows.
+constexpr int kUnroll = 4;   // kernels with per-element index arithmetic (pad, concat)
+constexpr int kU1 = 8;       // one-input streaming kernels
+constexpr int kU2 = 4;       // two-input streaming kernels (8 loads in flight)
+
+__device__ __forceinline__ float tanh_approx(float x) {
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 // Channel pitches are multiples of 8; when the logical channel count is not (`tail` = c % 8 != 0), the lanes >= tail of a pixel's
 // last vector are padding.  They are written as zeros whatever f(0) is: Log / Div / Pow would otherwise leave inf or NaN there and
@@ -91,39 +107,61 @@ __device__ __forceinline__ void zero_tail(float (&f)[8], size_t vec, int cp8, in
 
 __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t n8, int kind,
                                                         float a, float b, int cp8, int tail) {
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < n8; i0 += stride * kUnroll) {
-        Half8 v[kUnroll];
+    constexpr size_t step = kThreads;
+    const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
+    Half8 v[kU1];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (i0 + u * stride < n8) v[u] = ld8(x + (i0 + u * stride) * 8);
+    for (int u = 0; u < kU1; ++u)
+        if (base + u * step < n8) v[u] = ld8(x + (base + u * step) * 8);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            if (i0 + u * stride >= n8) break;
-            float f[8];
-            unpack(v[u], f);
-            if (kind == UN_RELU) {
+    for (int u = 0; u < kU1; ++u) {
+        const size_t i = base + u * step;
+        if (i >= n8) break;
+        if (kind == UN_RELU) {  // max is exact in fp16: no conversion
+            const __half2 z = __float2half2_rn(0.f);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            } else if (kind == UN_CLIP) {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], a), b);
-            } else {
-#pragma unroll
-                for (int j = 0; j < 8; ++j) f[j] = unary_op(f[j], kind, a, b);
-                zero_tail(f, i0 + u * stride, cp8, tail);
-            }
-            st8(y + (i0 + u * stride) * 8, pack(f));
+            for (int j = 0; j < 4; ++j) v[u].v[j] = __hmax2(v[u].v[j], z);
+            st8(y + i * 8, v[u]);
+            continue;
         }
+        float f[8];
+        unpack(v[u], f);
+        if (kind == UN_CLIP) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], a), b);
+        } else if (kind == UN_SIGMOID) {
+            // one MUFU per element (tanh) instead of two (ex2 + rcp): at two the kernel is bound by the special-function unit
+            // (16 results per clock per SM), not by HBM.  |error| <= 2^-12, below the fp16 rounding of the result.
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fmaf(tanh_approx(0.5f * f[j]), 0.5f, 0.5f);
+            zero_tail(f, i, cp8, tail);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = unary_op(f[j], kind, a, b);
+            zero_tail(f, i, cp8, tail);
+        }
+        st8(y + i * 8, pack(f));
     }
 }
 
 __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restrict__ pa, const __half* __restrict__ pb,
                                                          __half* __restrict__ y, size_t n8, int kind, int act, int cp8, int tail) {
-    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < n8; i += size_t(gridDim.x) * blockDim.x) {
+    constexpr size_t step = kThreads;
+    const size_t base = size_t(blockIdx.x) * (kThreads * kU2) + threadIdx.x;
+    Half8 va[kU2], vb[kU2];
+#pragma unroll
+    for (int u = 0; u < kU2; ++u)
+        if (base + u * step < n8) {
+            va[u] = ld8(pa + (base + u * step) * 8);
+            vb[u] = ld8(pb + (base + u * step) * 8);
+        }
+#pragma unroll
+    for (int u = 0; u < kU2; ++u) {
+        const size_t i = base + u * step;
+        if (i >= n8) break;
         float a[8], b[8];
-        unpack(ld8(pa + i * 8), a);
-        unpack(ld8(pb + i * 8), b);
+        unpack(va[u], a);
+        unpack(vb[u], b);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float r;
@@ -140,30 +178,39 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restri
     }
 }
 
+// Un-fused BatchNormalization.  kFixed: kThreads % cp8 == 0, so a thread meets the same 8 channels in every vector it handles and
+// its scale / shift values are loaded once.
+template <bool kFixed>
 __global__ void __launch_bounds__(kThreads) scale_shift_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t n8, int cp8,
                                                               const float* __restrict__ scale, const float* __restrict__ shift, int act) {
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
+    const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
     const float lo = act == ACT_RELU ? 0.f : -INFINITY;
-    for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < n8; i0 += stride * kUnroll) {
-        Half8 v[kUnroll];
+    Half8 v[kU1];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (i0 + u * stride < n8) v[u] = ld8(x + (i0 + u * stride) * 8);
+    for (int u = 0; u < kU1; ++u)
+        if (base + u * kThreads < n8) v[u] = ld8(x + (base + u * kThreads) * 8);
+    float4 s0, s1, h0, h1;
+    if (kFixed) {
+        const int c = int(threadIdx.x % unsigned(cp8)) * 8;
+        s0 = __ldg(reinterpret_cast<const float4*>(scale + c)); s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+        h0 = __ldg(reinterpret_cast<const float4*>(shift + c)); h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
+    }
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i >= n8) break;
-            const int c = int(i % cp8) * 8;
-            const float4 s0 = __ldg(reinterpret_cast<const float4*>(scale + c)), s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
-            const float4 h0 = __ldg(reinterpret_cast<const float4*>(shift + c)), h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
-            float f[8];
-            unpack(v[u], f);
-            f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), lo); f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), lo);
-            f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), lo); f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), lo);
-            f[4] = fmaxf(fmaf(f[4], s1.x, h1.x), lo); f[5] = fmaxf(fmaf(f[5], s1.y, h1.y), lo);
-            f[6] = fmaxf(fmaf(f[6], s1.z, h1.z), lo); f[7] = fmaxf(fmaf(f[7], s1.w, h1.w), lo);
-            st8(y + i * 8, pack(f));
+    for (int u = 0; u < kU1; ++u) {
+        const size_t i = base + u * kThreads;
+        if (i >= n8) break;
+        if (!kFixed) {
+            const int c = int(i % size_t(cp8)) * 8;
+            s0 = __ldg(reinterpret_cast<const float4*>(scale + c)); s1 = __ldg(reinterpret_cast<const float4*>(scale + c + 4));
+            h0 = __ldg(reinterpret_cast<const float4*>(shift + c)); h1 = __ldg(reinterpret_cast<const float4*>(shift + c + 4));
         }
+        float f[8];
+        unpack(v[u], f);
+        f[0] = fmaxf(fmaf(f[0], s0.x, h0.x), lo); f[1] = fmaxf(fmaf(f[1], s0.y, h0.y), lo);
+        f[2] = fmaxf(fmaf(f[2], s0.z, h0.z), lo); f[3] = fmaxf(fmaf(f[3], s0.w, h0.w), lo);
+        f[4] = fmaxf(fmaf(f[4], s1.x, h1.x), lo); f[5] = fmaxf(fmaf(f[5], s1.y, h1.y), lo);
+        f[6] = fmaxf(fmaf(f[6], s1.z, h1.z), lo); f[7] = fmaxf(fmaf(f[7], s1.w, h1.w), lo);
+        st8(y + i * 8, pack(f));
     }
 }
 
@@ -344,27 +391,31 @@ __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const __half* __
     }
 }
 
+// Nearest-neighbour upsampling, input-centric: blockIdx.y = (image, input row); a thread loads U vectors of that row (consecutive
+// threads = consecutive 16-byte vectors) and stores each of them sh * sw times.  Every input byte is read once, every output byte
+// written once, no per-element division beyond one 32-bit divide by the vectors per pixel.
 __global__ void __launch_bounds__(kThreads) upsample_nearest_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h,
                                                                    int w, int cp8, int sh, int sw) {
-    const int ho = h * sh, wo = w * sw;
-    const size_t total = size_t(n) * ho * wo * cp8;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < total; i0 += stride * kUnroll) {
-        Half8 v[kUnroll];
+    const int iy = blockIdx.y % h;
+    const int img = blockIdx.y / h;
+    const unsigned row_items = unsigned(w) * unsigned(cp8);
+    const __half* xr = x + (size_t(img) * h + iy) * row_items * 8;
+    const int wo = w * sw;
+    __half* yr = y + (size_t(img) * h + iy) * size_t(sh) * wo * cp8 * 8;
+    const unsigned base = blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    Half8 v[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i >= total) break;
-            const int g = int(i % cp8);
-            size_t pix = i / cp8;
-            const int ox = int(pix % wo);
-            const int oy = int((pix / wo) % ho);
-            const int img = int(pix / (size_t(wo) * ho));
-            v[u] = ld8(x + (((size_t(img) * h + oy / sh) * w + ox / sw) * cp8 + g) * 8);
+    for (int u = 0; u < kUnroll; ++u)
+        if (base + u * kThreads < row_items) v[u] = ld8(xr + size_t(base + u * kThreads) * 8);
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const unsigned it = base + u * kThreads;
+        if (it >= row_items) break;
+        const unsigned ix = it / unsigned(cp8), g = it - ix * unsigned(cp8);
+        for (int dy = 0; dy < sh; ++dy) {
+            __half* dst = yr + ((size_t(dy) * wo + size_t(ix) * sw) * cp8 + g) * 8;
+            for (int dx = 0; dx < sw; ++dx) st8(dst + size_t(dx) * cp8 * 8, v[u]);
         }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (i0 + u * stride < total) st8(y + (i0 + u * stride) * 8, v[u]);
     }
 }
 
@@ -410,54 +461,58 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
     return i;
 }
 
+// blockIdx.y = (image, output row): the source row is resolved once per block; threads walk (ox, channel group) of the row.
 __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
                                                         int pt, int pl, int ho, int wo, int mode, float value) {
-    const size_t total = size_t(n) * ho * wo * cp8;
+    const int oy = blockIdx.y % ho;
+    const int img = blockIdx.y / ho;
+    int sy = oy - pt;
+    bool row_inside = sy >= 0 && sy < h;
+    if (mode == PAD_REFLECT) { sy = reflect_idx(sy, h); row_inside = true; }
+    else if (mode == PAD_EDGE) { sy = min(max(sy, 0), h - 1); row_inside = true; }
     Half8 fill;
 #pragma unroll
     for (int j = 0; j < 4; ++j) fill.v[j] = __floats2half2_rn(value, value);
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < total; i0 += stride * kUnroll) {
-        Half8 v[kUnroll];
+    const unsigned row_items = unsigned(wo) * unsigned(cp8);
+    const __half* xr = x + (size_t(img) * h + (row_inside ? sy : 0)) * w * cp8 * 8;
+    __half* yr = y + (size_t(img) * ho + oy) * row_items * 8;
+    const unsigned base = blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
+    Half8 v[kUnroll];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i >= total) break;
-            const int g = int(i % cp8);
-            size_t pix = i / cp8;
-            const int ox = int(pix % wo);
-            const int oy = int((pix / wo) % ho);
-            const int img = int(pix / (size_t(wo) * ho));
-            int sx = ox - pl, sy = oy - pt;
-            bool inside = sx >= 0 && sx < w && sy >= 0 && sy < h;
-            if (mode == PAD_REFLECT) {
-                sx = reflect_idx(sx, w); sy = reflect_idx(sy, h); inside = true;
-            } else if (mode == PAD_EDGE) {
-                sx = min(max(sx, 0), w - 1); sy = min(max(sy, 0), h - 1); inside = true;
-            }
-            v[u] = inside ? ld8(x + (((size_t(img) * h + sy) * w + sx) * cp8 + g) * 8) : fill;
-        }
-#pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (i0 + u * stride < total) st8(y + (i0 + u * stride) * 8, v[u]);
+    for (int u = 0; u < kUnroll; ++u) {
+        const unsigned it = base + u * kThreads;
+        if (it >= row_items) break;
+        const unsigned ox = it / unsigned(cp8), g = it - ox * unsigned(cp8);
+        int sx = int(ox) - pl;
+        bool inside = row_inside && sx >= 0 && sx < w;
+        if (mode == PAD_REFLECT) { sx = reflect_idx(sx, w); inside = true; }
+        else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
+        v[u] = inside ? ld8(xr + (size_t(sx) * cp8 + g) * 8) : fill;
     }
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u)
+        if (base + u * kThreads < row_items) st8(yr + size_t(base + u * kThreads) * 8, v[u]);
 }
 
 __global__ void __launch_bounds__(kThreads) concat_vec_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t pixels,
                                                              int src8, int dst_pitch, int c_off) {
     const size_t total = pixels * src8;
-    const size_t stride = size_t(gridDim.x) * blockDim.x;
-    for (size_t i0 = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i0 < total; i0 += stride * kUnroll) {
-        Half8 v[kUnroll];
+    const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
+    Half8 v[kU1];
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u)
-            if (i0 + u * stride < total) v[u] = ld8(src + (i0 + u * stride) * 8);
+    for (int u = 0; u < kU1; ++u)
+        if (base + u * kThreads < total) v[u] = ld8(src + (base + u * kThreads) * 8);
+    // pixel / vector-in-pixel of the first vector once (64-bit), then advance by kThreads vectors with 32-bit arithmetic
+    size_t pix = base / size_t(src8);
+    unsigned g = unsigned(base - pix * size_t(src8));
+    const unsigned step_pix = unsigned(kThreads) / unsigned(src8), step_g = unsigned(kThreads) % unsigned(src8);
 #pragma unroll
-        for (int u = 0; u < kUnroll; ++u) {
-            const size_t i = i0 + u * stride;
-            if (i >= total) break;
-            st8(dst + (i / src8) * dst_pitch + c_off + int(i % src8) * 8, v[u]);
-        }
+    for (int u = 0; u < kU1; ++u) {
+        if (base + u * kThreads >= total) break;
+        st8(dst + pix * dst_pitch + c_off + g * 8, v[u]);
+        pix += step_pix;
+        g += step_g;
+        if (g >= unsigned(src8)) { g -= unsigned(src8); ++pix; }
     }
 }
 __global__ void __launch_bounds__(kThreads) concat_scalar_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t pixels,
@@ -492,18 +547,19 @@ __global__ void __launch_bounds__(kThreads) checksum_kernel(const uint32_t* __re
 cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
     const int tail = cp > 0 ? (c & 7) : 0;
-    unary_kernel<<<grid_for(n8), kThreads, 0, s>>>(x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
+    unary_kernel<<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
 cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
     const int tail = cp > 0 ? (c & 7) : 0;
-    binary_kernel<<<grid_for(n8), kThreads, 0, s>>>(a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
+    binary_kernel<<<tiled_grid(n8, kU2), kThreads, 0, s>>>(a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
 cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act, cudaStream_t s) {
     const size_t n8 = pixels * (cp / 8);
-    scale_shift_kernel<<<grid_for(n8), kThreads, 0, s>>>(x, y, n8, cp / 8, scale, shift, act);
+    if (kThreads % (cp / 8) == 0) scale_shift_kernel<true><<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, cp / 8, scale, shift, act);
+    else scale_shift_kernel<false><<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, cp / 8, scale, shift, act);
     return cudaGetLastError();
 }
 cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, int w, int cp, int pad_t, int pad_l, int pad_b, int pad_r,
@@ -581,20 +637,27 @@ cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, in
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
                        cudaStream_t s) {
     const size_t total = size_t(n) * h * scale_h * w * scale_w * (cp / 8);
-    if (mode == UP_NEAREST) upsample_nearest_kernel<<<grid_for(total), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, scale_h, scale_w);
-    else upsample_bilinear_kernel<<<grid_for(total), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, scale_h, scale_w, align_corners);
+    if (mode == UP_NEAREST) {
+        if (size_t(n) * h > 65535) return cudaErrorInvalidValue;  // grid.y = (image, input row)
+        const unsigned row_items = unsigned(w) * unsigned(cp / 8);
+        upsample_nearest_kernel<<<dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * h)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8,
+                                                                                                                                  scale_h, scale_w);
+    } else upsample_bilinear_kernel<<<grid_for(total), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, scale_h, scale_w, align_corners);
     return cudaGetLastError();
 }
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
                   cudaStream_t s) {
     const int ho = h + pt + pb, wo = w + pl + pr;
-    pad2d_kernel<<<grid_for(size_t(n) * ho * wo * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, pt, pl, ho, wo, mode, value);
+    if (size_t(n) * ho > 65535) return cudaErrorInvalidValue;  // grid.y = (image, output row)
+    const unsigned row_items = unsigned(wo) * unsigned(cp / 8);
+    pad2d_kernel<<<dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, pt, pl, ho, wo,
+                                                                                                                 mode, value);
     return cudaGetLastError();
 }
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s) {
     if (c_off % 8 == 0 && c_src % 8 == 0) {
-        concat_vec_kernel<<<grid_for(pixels * (c_src / 8)), kThreads, 0, s>>>(src, dst, pixels, c_src / 8, c_dst_pitch, c_off);
+        concat_vec_kernel<<<tiled_grid(pixels * (c_src / 8), kU1), kThreads, 0, s>>>(src, dst, pixels, c_src / 8, c_dst_pitch, c_off);
         // vector path assumes src pitch == c_src (true when c_src % 8 == 0)
         (void)c_src_pitch;
     } else {

@@ -240,6 +240,21 @@ def test_transformer_net_256(ctx):
     assert np.abs(out - want).mean() <= 2e-3
 
 
+def test_transformer_net_512_named_shape(ctx):
+    """BASELINE.json configs[3] at its named shape, 1x3x512x512, against the fp32 oracle with the north_star tolerance (1e-2 max-abs)."""
+    from smelter_b200 import modelzoo, onnx2mps
+
+    model = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=512).serialize(), half=True)
+    x = np.random.default_rng(1).random((1, 3, 512, 512), dtype=np.float32).astype(np.float16)
+    out, _ = _run(ctx, model, x)
+    want = _oracle(model, x)
+    assert out.shape == (1, 3, 512, 512)
+    err = np.abs(out - want)
+    print(f"TransformerNet 512x512: max-abs {err.max():.3e}, mean-abs {err.mean():.3e}, |ref| max {np.abs(want).max():.2f}")
+    assert err.max() <= TOL * max(1.0, float(np.abs(want).max()))
+    assert err.mean() <= 2e-3
+
+
 @pytest.mark.parametrize("half", [False, True], ids=["onnx", "onnx2mps-half"])
 def test_conv_transpose_group_norm_pow(ctx, half):
     """The registry entries no BASELINE model uses (ONNXGraph.swift:116,143,154): ConvTranspose (3x3/2 with output_padding,

@@ -2,6 +2,8 @@
 // See engine.h for the reference map.
 #include "engine.h"
 
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -106,6 +108,14 @@ int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride
 }
 
 // ---- ONNXGraph ------------------------------------------------------------------------------------------------
+
+// NVTX range "opType:outputName" around every plan step (the reference's only tracing hook is the node label,
+// Converters.swift:931,1064).  Header-only NVTX v3: a no-op unless a tool (nsys / ncu --nvtx) is attached.  Steps that are replayed
+// from the captured CUDA graph carry their range on the capture pass; SMELTER_DEBUG_SYNC=1 / useCudaGraph=0 give per-launch ranges.
+struct NvtxRange {
+    explicit NvtxRange(const std::string& name) { nvtxRangePushA(name.c_str()); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 struct Step {
     std::function<cudaError_t(cudaStream_t)> run;
@@ -399,8 +409,12 @@ int ONNXGraph::upload_weights() {
         }
     }
     SM_CUDA(cudaMalloc(&weight_arena_, weight_bytes_));
-    if (cfg_.defer_weights) SM_CUDA(cudaMemset(weight_arena_, 0, weight_bytes_));  // filled by broadcast_weights()
-    else SM_CUDA(cudaMemcpy(weight_arena_, host.data(), weight_bytes_, cudaMemcpyHostToDevice));
+    if (cfg_.defer_weights) {
+        SM_CUDA(cudaMemset(weight_arena_, 0, weight_bytes_));  // filled by broadcast_weights()
+        weights_pending_ = true;   // encode refuses to run on the zero arena
+    } else {
+        SM_CUDA(cudaMemcpy(weight_arena_, host.data(), weight_bytes_, cudaMemcpyHostToDevice));
+    }
     return SMELTER_OK;
 }
 
@@ -608,7 +622,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             for (int i : f.in) if (root_of(i) == v) { ++readers; only = &f; }
             if (f.residual >= 0 && root_of(f.residual) == v) ++readers;
         }
-        if (readers == 1 && v != out_root && only->kind == FilterKind::Conv && only->conv_mode == k::CONV_MODE_PACKED_ROW && only->in[0] == v &&
+        if (readers == 1 && v != out_root && only->kind == FilterKind::Conv && only->conv_mode == k::CONV_MODE_PACKED_ROW && root_of(only->in[0]) == v &&
             (only->s2d || only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
             stem_of[size_t(v)] = only;
     }
@@ -1030,6 +1044,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
 
 int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_sources, const Tensor** result) {
     if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "encode before build");
+    if (weights_pending_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "weights were deferred (deferWeights) and never broadcast: call broadcastWeights first");
     if (!sources || n_sources != int(input_values_.size()))
         return fail(SMELTER_ERR_INSUFFICIENT_INPUTS, "graph expects " + std::to_string(input_values_.size()) + " source image(s)");
     for (int i = 0; i < n_sources; ++i)
@@ -1069,6 +1084,7 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     if (cfg_.use_cuda_graph) {
         for (auto& st : plan->steps) {  // source-image conversions run eagerly: their pointers change per call
             if (!st.boundary) continue;
+            NvtxRange range(st.desc);
             cudaError_t e = st.run(stream);
             if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
         }
@@ -1079,6 +1095,7 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
             std::string where;
             for (auto& st : plan->steps) {
                 if (st.boundary) continue;
+                NvtxRange range(st.desc);
                 e = st.run(stream);
                 if (e != cudaSuccess) { where = st.desc; break; }
             }
@@ -1095,6 +1112,7 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     } else {
         static const bool debug_sync = getenv("SMELTER_DEBUG_SYNC") != nullptr;  // fault isolation: sync after every kernel
         for (auto& st : plan->steps) {
+            NvtxRange range(st.desc);
             cudaError_t e = st.run(stream);
             if (e == cudaSuccess && debug_sync) e = cudaStreamSynchronize(stream);
             if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
@@ -1206,7 +1224,11 @@ int ONNXGraph::plan_dump(int batch, std::string* out) {
 
 int ONNXGraph::broadcast_weights(int root) {
     if (!built_) return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph not built");
-    return nccl_broadcast(ctx_, weight_arena_, weight_bytes_, root, ctx_->stream);
+    if (weights_pending_ && !ctx_->nccl_comm)
+        return fail(SMELTER_ERR_INCONSISTENT_STATE, "graph was built with deferWeights but the context has no NCCL communicator: nobody can fill the weight arena");
+    const int rc = nccl_broadcast(ctx_, weight_arena_, weight_bytes_, root, ctx_->stream);
+    if (rc == SMELTER_OK) weights_pending_ = false;
+    return rc;
 }
 
 int ONNXGraph::weight_checksum(uint64_t* sum, uint64_t* bytes) {

@@ -184,6 +184,7 @@ class ONNXGraph {
     std::vector<int> input_values_;        // graph inputs that are not initializers, in file order
     int output_value_ = -1;
     bool built_ = false;
+    bool weights_pending_ = false;  // built with defer_weights and not yet filled by broadcast_weights()
 
     void* weight_arena_ = nullptr;
     size_t weight_bytes_ = 0;

@@ -566,7 +566,17 @@ __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __res
 
 cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int p, int q, int kh, int kw, int sh, int sw, int ph, int pw,
                    int is_max, cudaStream_t s) {
-    if (size_t(n) * p > 65535) return cudaErrorInvalidValue;  // grid.y limit (batch x output rows)
+    // grid.y = (image, output row) is limited to 65535: larger batches go in slices of whole images
+    if (size_t(n) * p > 65535) {
+        const int per = std::max(1, 65535 / p);
+        if (p > 65535) return cudaErrorInvalidValue;
+        for (int i0 = 0; i0 < n; i0 += per) {
+            const int gn = std::min(per, n - i0);
+            cudaError_t e = pool2d(x + size_t(i0) * h * w * cp, y + size_t(i0) * p * q * cp, gn, h, w, cp, p, q, kh, kw, sh, sw, ph, pw, is_max, s);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
     const int row_items = q * (cp / 8);
     dim3 grid(unsigned((row_items + kThreads - 1) / kThreads), unsigned(n * p));
     if (kh == 3 && kw == 3 && is_max && (sh == 1 || sh == 2) && p >= 2) {

@@ -298,19 +298,27 @@ def run_native(args) -> int:
 
     # Workload: one GPU = BASELINE.json configs[2] (batch 32); N > 1 = configs[4]: ResNet-50, GLOBAL batch 256 split 256 / N per rank
     # (strong scaling; the 32-per-GPU weak-scaling figure is measured next to it).
-    K, W, S = args.steps, max(args.warmup, 3), max(1, args.in_flight)
+    K, W = args.steps, max(args.warmup, 3)
     G = args.global_batch or (PER_GPU_BATCH if world == 1 else GLOBAL_BATCH)
     if args.batch:
         G = args.batch * world
     if G % world:
         raise SystemExit(f"global batch {G} does not split over {world} ranks")
     B = G // world
+    # Small batches leave every layer latency-bound (a few tiles per SM between two kernel boundaries): the throughput graph is
+    # planned for half of the SMs (Configuration.smShare = 2) and three encodes are kept in flight, so two of them always co-run
+    # on disjoint halves of the chip.  Large per-GPU batches fill the chip by themselves: whole-chip kernels, two in flight.
+    share = args.sm_share or (2 if B <= 64 else 1)
+    S = max(1, args.in_flight or (3 if share >= 2 else 2))
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank, stream=stream.cuda_stream)
     data = model_bytes()
-    graph = ONNXGraph(data, Configuration(deferWeights=(world > 1 and rank != 0)), context=ctx)
-    assert graph.modelFormat == Format.mpsFlavor
-    nn = graph.metalGraph()
+    # Two plans of the same model: smShare = 2 (kernels sized for half of the SMs; the small-batch throughput plan) and the whole-chip
+    # plan (latency of one encode with nothing else in flight, per-kernel roofline, large batches).  Each holds its own weight replica.
+    graphs = {k: ONNXGraph(data, Configuration(deferWeights=(world > 1 and rank != 0), smShare=k), context=ctx) for k in sorted({1, 2, share})}
+    assert all(g.modelFormat == Format.mpsFlavor for g in graphs.values())
+    nns = {k: g.metalGraph() for k, g in graphs.items()}
+    graph, nn, nn_full = graphs[share], nns[share], nns[1]
     comm_ms = bcast_ms = None
     if world > 1:  # one-time weight replica over NVLink
         uid = sdist.share_bytes(Context.ncclUniqueId() if rank == 0 else b"", 0)
@@ -325,6 +333,10 @@ def run_native(args) -> int:
         nn.broadcastWeights(0)          # the 51 MB broadcast by itself
         ctx.synchronize()
         bcast_ms = (time.perf_counter() - t0) * 1e3
+        for k, other in nns.items():
+            if other is not nn:
+                other.broadcastWeights(0)
+        ctx.synchronize()
         checksum, _ = nn.weightChecksum()
         if not sdist.all_equal(checksum, dev):
             raise SystemExit("weight replicas differ after the broadcast")
@@ -340,9 +352,10 @@ def run_native(args) -> int:
     hi = sampler.mark()
     value = world * B * K / (elapsed_ms * 1e-3)
     launches = nn.numLaunches(B) * K
-    # latency of one encode with nothing else in flight (what round 1 reported as the step)
+    # latency of one encode with nothing else in flight on the whole chip (what round 1 reported as the step)
     K1 = min(K, 300)
-    one_ms = run.timed(K1, W, 1, barrier, max_over_ranks) / K1
+    run_full = run if nn_full is nn else Runner(torch, ctx, nn_full, dev, B, 1 + rank, 2)
+    one_ms = run_full.timed(K1, W, 1, barrier, max_over_ranks) / K1
 
     # ---- end to end through the public API with host buffers, S batches in flight ----------------------------------------------
     copy_stream = torch.cuda.Stream(device=dev)
@@ -394,8 +407,8 @@ def run_native(args) -> int:
         if B == PER_GPU_BATCH:
             weak_value = value
         else:
-            weak = Runner(torch, ctx, nn, dev, PER_GPU_BATCH, 101 + rank, max(S, 2))
-            weak_value = world * PER_GPU_BATCH * K / (weak.timed(K, W, S, barrier, max_over_ranks) * 1e-3)
+            weak = Runner(torch, ctx, nns[2], dev, PER_GPU_BATCH, 101 + rank, 3)   # the small-batch plan: smShare 2, three in flight
+            weak_value = world * PER_GPU_BATCH * K / (weak.timed(K, W, 3, barrier, max_over_ranks) * 1e-3)
             del weak
         extra["weak_scaling"] = {"per_gpu_batch": PER_GPU_BATCH, "global_batch": PER_GPU_BATCH * world, "value": weak_value, "unit": "images/s"}
         # strong-scaling base: the whole global batch on ONE GPU (every rank times it on its own GPU; they do not share anything)
@@ -403,8 +416,8 @@ def run_native(args) -> int:
             base_value = value
         else:
             k256 = max(20, min(K, 100))
-            full = Runner(torch, ctx, nn, dev, G, 201, max(S, 2))
-            base_value = G * k256 / (full.timed(k256, W, S, barrier, max_over_ranks) * 1e-3)
+            full = Runner(torch, ctx, nns[1], dev, G, 201, 2)   # whole-chip plan, two in flight
+            base_value = G * k256 / (full.timed(k256, W, 2, barrier, max_over_ranks) * 1e-3)
         extra["strong_scaling"] = {"global_batch": G, "one_gpu_value": base_value, "efficiency_vs_one_gpu": value / (world * base_value),
                                    "note": "value / (N x the same global batch on one GPU, measured in this run)"}
         # shard parity: every rank holds the SAME seeded global batch, encodes its contiguous slice, rank 0 compares the gathered
@@ -443,7 +456,7 @@ def run_native(args) -> int:
     # gives each kernel's duration in situ.  The event nodes themselves cost a few us per kernel and defeat PDL overlap, so the
     # per-kernel numbers are used for the conv kernels' SHARE of the step; the absolute duration is pinned to the event-timed
     # step above: conv_ms = ms_per_step x share.  Both the raw and the pinned figures are reported.
-    prof = nn.profile([run.images[0]], iters=5, stream=stream.cuda_stream)
+    prof = nn_full.profile([run.images[0]], iters=5, stream=stream.cuda_stream)
     conv = [p for p in prof if p["tensor"]]
     conv_ms_raw = sum(p["ms"] for p in conv)
     conv_flops = sum(p["flops"] for p in conv)
@@ -482,8 +495,11 @@ def run_native(args) -> int:
                                     f"ResNet-50 fp16 224x224 global batch={G} batch-sharded {B} per GPU over {world} GPU(s) (BASELINE.json configs[4])"),
                        "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": G,
                        "per_gpu_batch": B, "parallelism": f"batch-sharded dp{world}, one NCCL weight broadcast, no steady-state collective",
-                       "in_flight": S, "in_flight_note": f"{S} encodes in flight per GPU, each on its own stream with its own activation arena "
-                       "(the reference's encode(to: commandBuffer) is asynchronous in the same way); ms_per_step = elapsed / steps",
+                       "in_flight": S, "sm_share": share,
+                       "in_flight_note": f"{S} encodes in flight per GPU, each on its own stream with its own activation arena "
+                       "(the reference's encode(to: commandBuffer) is asynchronous in the same way)" +
+                       (f", kernels planned for 1/{share} of the SMs (Configuration.smShare) so that {share} encodes co-run" if share > 1 else "") +
+                       "; ms_per_step = elapsed / steps; one_in_flight = one encode at a time on the whole chip",
                        "l2": f"inputs larger than L2: {run.sets} distinct resident batches ({run.sets * run.n_in * 2 / 1e6:.0f} MB) rotated, no flush",
                        "cuda_graph": True, "accumulate": "fp32 (TMEM)"},
             "one_in_flight": {"ms_per_step": one_ms, "value": world * B / (one_ms * 1e-3), "unit": "images/s", "steps": K1},
@@ -519,7 +535,10 @@ def main() -> int:
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 32 on one GPU, 256 / N on N GPUs)")
     ap.add_argument("--global-batch", type=int, default=0, help="global batch split over the ranks (default: 32 for one GPU, 256 for N > 1)")
-    ap.add_argument("--in-flight", type=int, default=2, help="encodes in flight per GPU, each on its own stream (1 = strictly one at a time)")
+    ap.add_argument("--in-flight", type=int, default=0, help="encodes in flight per GPU, each on its own stream (1 = strictly one at a time; "
+                    "default: 3 with --sm-share 2 for per-GPU batches up to 64, else 2 on the whole chip)")
+    ap.add_argument("--sm-share", type=int, default=0, help="Configuration.smShare of the throughput graph: kernels sized for 1/k of the SMs so that "
+                    "encodes in flight co-run (default: see --in-flight)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] / configs[3] latency fields")
     args = ap.parse_args()

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define SMELTER_B200_ABI_VERSION 1
+#define SMELTER_B200_ABI_VERSION 2
 
 /* ---- status codes -----------------------------------------------------------------------------------
  * 1..8 are ONNXGraph.Errors in declaration order (Sources/Smelter/ONNXGraph.swift:38-47). */
@@ -61,6 +61,10 @@ typedef struct smelter_config {
     int32_t use_cuda_graph;          /* 1 (default): replay encode() from a captured CUDA graph */
     int32_t defer_weights;           /* 1: build() leaves the device weight arena zero-filled; the caller must fill it with
                                         smelter_graph_broadcast_weights (non-root ranks of a multi-GPU job). default 0 */
+    int32_t sm_share;                /* k >= 2: plan and launch every kernel of this graph for 1/k of the SMs, so that encodes in
+                                        flight on different streams (the reference's asynchronous command buffers) co-run on
+                                        disjoint parts of the chip instead of taking turns with whole-chip grids; one encode
+                                        is slower, k + 1 in flight are faster.  default 1 (whole chip).  ABI version 2 */
 } smelter_config;
 
 /* Shape (Sources/Smelter/TypeDefinitions.swift:1-33) */

@@ -10,7 +10,8 @@ import os
 import re
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libsmelter_b200.so")
+# SMELTER_LIB_PATH: kernel experiments load a differently compiled build of the same library (tools/build_variant.sh)
+LIB_PATH = os.environ.get("SMELTER_LIB_PATH") or os.path.join(HERE, "libsmelter_b200.so")
 HEADER_PATH = os.path.join(HERE, "..", "include", "smelter_b200.h")
 
 i32, i64, u64, f32 = C.c_int32, C.c_int64, C.c_uint64, C.c_float
@@ -20,7 +21,7 @@ P = C.POINTER
 
 class smelter_config(C.Structure):
     _fields_ = [("input_constraint", i32), ("bilinear_align_corners", i32), ("n_dims", i32), ("dims_axis", i32 * 8),
-                ("dims_value", i64 * 8), ("enable_fusion", i32), ("use_cuda_graph", i32), ("defer_weights", i32)]
+                ("dims_value", i64 * 8), ("enable_fusion", i32), ("use_cuda_graph", i32), ("defer_weights", i32), ("sm_share", i32)]
 
 
 class smelter_shape(C.Structure):

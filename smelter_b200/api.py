@@ -68,6 +68,7 @@ class Configuration:
     enableFusion: bool = True
     useCudaGraph: bool = True
     deferWeights: bool = False
+    smShare: int = 1  # k >= 2: kernels sized for 1/k of the SMs so that encodes in flight on different streams co-run
 
     def _c(self) -> L.smelter_config:
         c = L.smelter_config()
@@ -83,6 +84,7 @@ class Configuration:
         c.enable_fusion = int(self.enableFusion)
         c.use_cuda_graph = int(self.useCudaGraph)
         c.defer_weights = int(self.deferWeights)
+        c.sm_share = int(self.smShare)
         return c
 
 

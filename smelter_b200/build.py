@@ -37,7 +37,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-DSMELTER_BUILDING",
 ]
-for _macro in ("SMELTER_TRYWAIT_HINT_NS", "SMELTER_MMA_LOOKAHEAD"):  # compile-time experiment switches
+for _macro in ("SMELTER_TRYWAIT_HINT_NS", "SMELTER_MMA_LOOKAHEAD", "SMELTER_CLUSTER_RELAXED", "SMELTER_TEARDOWN_FULL_WAIT"):  # compile-time experiment switches
     if os.environ.get(_macro):
         NVCC_FLAGS.append(f"-D{_macro}={os.environ[_macro]}")
 if os.environ.get("SMELTER_CONV_INSTRUMENT"):  # perf experiments: %globaltimer stamps + ablation flags in the conv kernel

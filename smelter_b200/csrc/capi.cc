@@ -34,6 +34,7 @@ void smelter_config_default(smelter_config* cfg) {
     cfg->enable_fusion = 1;
     cfg->use_cuda_graph = 1;
     cfg->defer_weights = 0;
+    cfg->sm_share = 1;
 }
 
 // ---- context ----------------------------------------------------------------------------------------------
@@ -54,6 +55,12 @@ int32_t smelter_context_create(int32_t device, void* cuda_stream, smelter_contex
     if (!ctx) return fail(SMELTER_ERR_GRAPH_INTERNAL, "out of memory");
     ctx->c.device = device;
     ctx->c.num_sms = prop.multiProcessorCount;
+    // SMELTER_SM_LIMIT=n: plan and launch every kernel of this context's graphs for n SMs only (experiments with several encodes in
+    // flight, each confined to a share of the chip so that their kernels co-run instead of time-slicing whole-chip grids)
+    if (const char* lim = getenv("SMELTER_SM_LIMIT")) {
+        const int n = atoi(lim);
+        if (n >= 2 && n < ctx->c.num_sms) ctx->c.num_sms = n & ~1;
+    }
     if (cuda_stream) {
         ctx->c.stream = static_cast<cudaStream_t>(cuda_stream);
     } else {

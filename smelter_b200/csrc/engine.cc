@@ -478,7 +478,8 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
     auto plan = std::make_unique<Plan>();
     plan->batch = batch;
     const int N = batch;
-    const int num_sms = ctx_->num_sms;
+    // Configuration.smShare: this graph's kernels are planned and launched for a 1/k share of the SMs (an even number: CTA pairs)
+    const int num_sms = cfg_.sm_share >= 2 ? std::max(2, (ctx_->num_sms / cfg_.sm_share) & ~1) : ctx_->num_sms;
     const char* wbase = static_cast<const char*>(weight_arena_);
 
     auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
@@ -1081,6 +1082,15 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
     }
     if (!stream) stream = ctx_->stream;
     SM_CUDA(cudaSetDevice(ctx_->device));
+    // perf experiments (instrumented builds): SMELTER_CHAIN_TIMELINE=n prints the launch-chain stamps of the n-th encode of the process
+    static const int chain_at = getenv("SMELTER_CHAIN_TIMELINE") ? atoi(getenv("SMELTER_CHAIN_TIMELINE")) : 0;
+    static int chain_calls = 0;
+    const bool chain_now = chain_at > 0 && ++chain_calls == chain_at;
+    if (chain_now) { cudaStreamSynchronize(stream); k::conv_tc_chain_reset(); }
+    struct ChainDump {
+        bool on; cudaStream_t s;
+        ~ChainDump() { if (on) { cudaStreamSynchronize(s); k::conv_tc_chain_dump(); } }
+    } chain_dump{chain_now, stream};
     if (cfg_.use_cuda_graph) {
         for (auto& st : plan->steps) {  // source-image conversions run eagerly: their pointers change per call
             if (!st.boundary) continue;

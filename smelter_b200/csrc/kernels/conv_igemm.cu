@@ -20,6 +20,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <vector>
 
 #include "ptx.cuh"
 
@@ -84,6 +85,10 @@ struct Cfg {
 #define SMELTER_CONV_INSTRUMENT 0
 #endif
 constexpr bool kInstr = SMELTER_CONV_INSTRUMENT != 0;
+constexpr int kChainLaunches = 256;
+unsigned long long* g_chain_buf = nullptr;
+int g_chain_seq = 0;
+char g_chain_desc[kChainLaunches][96];
 constexpr int kMmaLoopVariant = 1;  // MMA issue loop: 0 = one elected lane, 1 = same unrolled by two, 2 = whole warp + elected issue
 
 __device__ __forceinline__ void stamp(const ConvKernelParams& p, int slot) {
@@ -970,6 +975,15 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
         if (!buf && cudaMalloc(&buf, 64 * sizeof(unsigned long long)) == cudaSuccess) cudaMemset(buf, 0, 64 * sizeof(unsigned long long));
         p.timeline = buf;
     }
+    p.chain = nullptr;
+    if (getenv("SMELTER_CHAIN_TIMELINE")) {
+        if (!g_chain_buf && cudaMalloc(&g_chain_buf, kChainLaunches * 16 * sizeof(unsigned long long)) == cudaSuccess) conv_tc_chain_reset();
+        if (g_chain_buf && g_chain_seq < kChainLaunches) {
+            snprintf(g_chain_desc[g_chain_seq], sizeof g_chain_desc[0], "bn%-3d M=%-6ld Cout=%-4d K=%-5d%s%s", block_n, M, q.c_out, q.c_in * R * S + (q.side_x ? q.side_c_in : 0),
+                     q.residual ? " +res" : "", q.side_x ? " +side" : "");
+            p.chain = g_chain_buf + 16 * g_chain_seq++;
+        }
+    }
     {
         cudaError_t e = set_attr(block_n);
         if (e == cudaSuccess && (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && (block_n == 64 || block_n == 128 || block_n == 256)) {
@@ -1343,6 +1357,34 @@ int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iter
         return 1;
     }
     return 0;
+}
+
+// Whole-encode launch chain (instrumented builds, SMELTER_CHAIN_TIMELINE=1): every conv_pair launch prepared while the switch is set
+// owns 16 words = {min, max} over its CTAs of: 0 entry, 1 griddepcontrol.wait returned (first activation producer), 2 first operands
+// landed (leader MMA thread), 3 last accumulator ready (first epilogue warp), 4 last store issued, 5 exit.
+void conv_tc_chain_reset() {
+    if (!g_chain_buf) return;
+    std::vector<unsigned long long> h(size_t(kChainLaunches) * 16);
+    for (size_t i = 0; i < h.size(); ++i) h[i] = (i & 1) ? 0ull : ~0ull;
+    cudaMemcpy(g_chain_buf, h.data(), h.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice);
+}
+void conv_tc_chain_dump() {
+    if (!g_chain_buf) return;
+    std::vector<unsigned long long> h(size_t(kChainLaunches) * 16);
+    cudaMemcpy(h.data(), g_chain_buf, h.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost);
+    unsigned long long t0 = ~0ull;
+    for (int l = 0; l < g_chain_seq; ++l) if (h[size_t(l) * 16] < t0) t0 = h[size_t(l) * 16];
+    fprintf(stderr, "chain timeline (us since the first entry): launch | entry min..max | go min..max | first_operands min..max | last_acc min..max | last_store min..max | dealloc'd min..max | stores_read min..max | teardown_sync min..max\n");
+    for (int l = 0; l < g_chain_seq; ++l) {
+        const unsigned long long* r = &h[size_t(l) * 16];
+        if (r[0] == ~0ull) continue;
+        fprintf(stderr, "%3d %-44s", l, g_chain_desc[l]);
+        for (int pt = 0; pt < 8; ++pt) {
+            if (r[2 * pt] == ~0ull) fprintf(stderr, " |      -      -");
+            else fprintf(stderr, " | %7.2f %7.2f", double((long long)(r[2 * pt] - t0)) * 1e-3, double((long long)(r[2 * pt + 1] - t0)) * 1e-3);
+        }
+        fprintf(stderr, "\n");
+    }
 }
 
 void conv_tc_dump_timeline(const ConvTcLaunch& L) {

@@ -35,6 +35,7 @@ struct ConvKernelParams {
     float* ws;               // split-K workspace: [tiles * splits][128][BLOCK_N] fp32 partial accumulators
     unsigned int* counters;  // split-K: one arrival counter per tile, zero between launches
     unsigned long long* timeline;  // perf experiments only (env SMELTER_CONV_TIMELINE): CTA 0 writes %globaltimer stamps here
+    unsigned long long* chain;     // perf experiments only (env SMELTER_CHAIN_TIMELINE, instrumented builds): per-launch {min, max} over CTAs of six stamps
     int debug_flags;         // perf experiments only (env SMELTER_CONV_DEBUG): 16 = producers skip the TMA loads (results wrong)
     int use_pdl;             // the launch carries the programmatic-serialization attribute: call griddepcontrol.wait
     int l2_hints;            // 1 = output stores evict_last (tensor re-read by later layers), 2 = residual loads evict_first (last use)
@@ -109,6 +110,8 @@ bool conv_tc_encode_2d(CUtensorMap* tm, const __half* base, long cols, long rows
 bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::string* err);
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream);
 void conv_tc_dump_timeline(const ConvTcLaunch& L);  // perf experiments only
+void conv_tc_chain_reset();                          // perf experiments only: whole-encode launch chain timeline (conv_pair.cu stamps)
+void conv_tc_chain_dump();
 // two-CTA variant (conv_pair.cu)
 bool conv_pair_supported(const ConvTcLaunch& L);
 cudaError_t conv_pair_set_attr(int block_n);

@@ -81,6 +81,16 @@ __device__ __forceinline__ void epi_stamp(const ConvKernelParams& p, bool who, i
     }
 }
 
+// Launch-chain stamps (same builds, SMELTER_CHAIN_TIMELINE): min / max over all CTAs of %globaltimer at point `pt` of this launch.
+__device__ __forceinline__ void chain_stamp(const ConvKernelParams& p, int pt) {
+    if (kInstr && p.chain) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        asm volatile("red.global.min.u64 [%0], %1;" ::"l"(p.chain + 2 * pt), "l"(t) : "memory");
+        asm volatile("red.global.max.u64 [%0], %1;" ::"l"(p.chain + 2 * pt + 1), "l"(t) : "memory");
+    }
+}
+
 enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
 
 // One elected thread per producer warp (see conv_igemm.cu produce()).  Work items are (m-pair, n-tile): cluster c visits items
@@ -215,6 +225,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int my_tiles = cluster_id < num_items ? (num_items - 1 - cluster_id) / n_clusters + 1 : 0;
     constexpr bool kSplit = C::kChunks >= 2;  // both epilogue groups share every tile (see conv_igemm.cu)
 
+    if (threadIdx.x == 0) chain_stamp(p, 0);
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&tm_a);
         prefetch_tensormap(&tm_b);
@@ -242,7 +253,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         tmem2_relinquish();
     }
     tc_fence_before();
-    cluster_sync_all();  // both CTAs' barriers exist before anybody arrives remotely or multicasts
+    cluster_sync_exec();  // both CTAs' barriers exist before anybody arrives remotely or multicasts
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_ptr;
     if (p.use_pdl) grid_dep_launch_dependents();
@@ -254,6 +265,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         if (elect_one() && me < n_prod) {
             if (is_a) {
                 if (p.use_pdl) grid_dep_wait();
+                if (me == 0) chain_stamp(p, 1);
                 if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
                 else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
             } else {
@@ -277,9 +289,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             // them: the probe's latency hides behind the issue slots instead of sitting between two k-blocks' MMAs (measured: the
             // wait -> 4 x MMA -> commit chain of one thread, not the tensor pipe, paced the k-loop at MMA time + ~0.08 us per k-block).
             bool ready = false;
+            bool stamped = false;
             auto kblock = [&](uint32_t tmem_d, uint32_t first_accumulate) {
                 if (!ready) mbar_wait_bounded(full_addr, phase);
                 tc_fence_after();
+                if (kInstr && first_accumulate == 0u && tmem_d == tmem_base && !stamped) { chain_stamp(p, 2); stamped = true; }
                 const uint64_t a_desc = desc_hi | uint64_t(a_lo);
                 const uint64_t b_desc = a_desc + kB16;
                 const uint32_t cur_empty = full_addr + 8u * C::kStages;
@@ -385,6 +399,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             mbar_wait_bounded(tmem_full_bar(acc), acc_parity);
             tc_fence_after();
             const bool stamper = kInstr && blockIdx.x == 0 && ewarp == 0 && lane == 0;
+            if (kInstr && gt == group_tiles - 1 && ew == 0 && lane == 0) chain_stamp(p, 3);
             epi_stamp(p, stamper, item, 0);
             const uint32_t taddr = tmem_base + (uint32_t(ew * 32) << 16) + uint32_t(acc * BLOCK_N);
 #pragma unroll 1
@@ -438,14 +453,22 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 epi_stamp(p, stamper, item, 5);
             }
         }
+        if (kInstr && lane == 0 && group_tiles > 0) chain_stamp(p, 4);
+#ifdef SMELTER_TEARDOWN_FULL_WAIT
+        if (lane == 0) tma_store_wait<0>();
+#else
         if (lane == 0) tma_store_wait_read<0>();
+#endif
+        if (kInstr && lane == 0 && group_tiles > 0) chain_stamp(p, 6);
     }
 
     tc_fence_before();
-    cluster_sync_all();  // nobody exits (or frees TMEM) while the other CTA may still signal its barriers or read its operands
+    cluster_sync_exec();  // nobody exits (or frees TMEM) while the other CTA may still signal its barriers or read its operands
+    if (threadIdx.x == 0) chain_stamp(p, 7);
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem2_dealloc(tmem_base, C::kTmemCols);
+        if (lane == 0) chain_stamp(p, 5);
     }
 }
 

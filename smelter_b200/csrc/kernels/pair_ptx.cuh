@@ -23,6 +23,22 @@ __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
     asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+// Execution-only rendezvous of the two CTAs: `arrive.release` is a cluster-scope memory fence that waits for the CTA's outstanding
+// global writes (measured with the launch-chain stamps: the teardown barrier of conv_pair_kernel returned ~1 us after the last
+// epilogue warp reached it, once per launch).  The hand-shakes around it carry their own ordering: mbarrier inits are published by
+// fence.mbarrier_init.release.cluster, CTA-local shared memory by the bar.sync in front, tcgen05 work by its fences and commits.
+#ifndef SMELTER_CLUSTER_RELAXED
+#define SMELTER_CLUSTER_RELAXED 1
+#endif
+__device__ __forceinline__ void cluster_sync_exec() {
+#if SMELTER_CLUSTER_RELAXED
+    __syncthreads();
+    asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+#else
+    cluster_sync_all();
+#endif
+}
 __device__ __forceinline__ void mbar_expect_tx_cluster(uint32_t bar_cluster_addr, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(bar_cluster_addr), "r"(bytes) : "memory");
 }

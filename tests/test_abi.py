@@ -24,7 +24,7 @@ def test_no_torch_or_python_linkage(native_lib):
 
 
 def test_abi_version_and_defaults(native_lib):
-    assert native_lib.smelter_abi_version() == 1
+    assert native_lib.smelter_abi_version() == 2
     cfg = _lib.smelter_config()
     native_lib.smelter_config_default(C.byref(cfg))
     # Configuration.init defaults, ONNXGraph.swift:20,27-35

@@ -25,8 +25,7 @@ SOURCES = [
     "capi.cc",
     "nccl_shim.cc",
     "kernels/conv_igemm.cu",
-    "kernels/conv_mega.cu",
-    "kernels/conv_pair.cu", "kernels/conv_duo.cu", "kernels/conv_b2b.cu",
+    "kernels/conv_pair.cu",
     "kernels/elementwise.cu",
     "kernels/pool_norm.cu",
 ]
@@ -37,7 +36,7 @@ NVCC_FLAGS = [
     "-Xcompiler", "-fPIC,-Wall,-Wno-unused-function",
     "-DSMELTER_BUILDING",
 ]
-for _macro in ("SMELTER_TRYWAIT_HINT_NS", "SMELTER_MMA_LOOKAHEAD", "SMELTER_CLUSTER_RELAXED", "SMELTER_TEARDOWN_FULL_WAIT"):  # compile-time experiment switches
+for _macro in ("SMELTER_TRYWAIT_HINT_NS", "SMELTER_MMA_LOOKAHEAD", "SMELTER_CLUSTER_RELAXED"):  # compile-time experiment switches
     if os.environ.get(_macro):
         NVCC_FLAGS.append(f"-D{_macro}={os.environ[_macro]}")
 if os.environ.get("SMELTER_CONV_INSTRUMENT"):  # perf experiments: %globaltimer stamps + ablation flags in the conv kernel

@@ -139,7 +139,7 @@ struct Plan {
     cudaGraphExec_t exec = nullptr;
     void* counters = nullptr;  // split-K arrival counters of every conv in the plan (zero between launches)
     std::vector<__half*> resized;  // per graph input: NCHW staging the source is resized into under .forceInputScale (lazily allocated)
-    std::vector<void*> blobs;  // further device allocations owned by the plan (completion counters of persistent conv runs)
+    std::vector<void*> blobs;  // further device allocations owned by the plan (none today)
     ~Plan() {
         if (exec) cudaGraphExecDestroy(exec);
         if (arena) cudaFree(arena);
@@ -531,8 +531,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         q.side_c_in = g.c_in_g; q.side_c_in_pitch = round_up(gs.c, 8);
         q.side_stride_h = g.stride_h; q.side_stride_w = g.stride_w;
     };
-    const char* mega_env = getenv("SMELTER_MEGA");
-    const bool mega_on = mega_env && atoi(mega_env) != 0;
     std::vector<int> reads(values_.size(), 0), producer(values_.size(), -1);
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
@@ -544,7 +542,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
     auto plain_tc_conv = [&](const Filter& f) {
         return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
     };
-    if (!getenv("SMELTER_NO_SIDE") && !mega_on) {
+    if (!getenv("SMELTER_NO_SIDE")) {
         for (size_t fi = 0; fi < filters_.size(); ++fi) {
             const Filter& f = filters_[fi];
             if (f.removed || !plain_tc_conv(f) || f.residual < 0) continue;
@@ -564,32 +562,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         }
     }
 
-    // ---- back-to-back pairs (opt-in, SMELTER_B2B=1; kernels/conv_b2b.cu): a convolution with 64 / 128 output channels whose only reader
-    // is a 1x1 / stride-1 convolution runs inside that reader's launch; its output tensor never exists.  b2b_first[B] = A.
-    std::vector<int> b2b_first(filters_.size(), -1);
-    auto b2b_problem = [&](const Filter& g, const Filter& h) {
-        k::ConvB2bProblem bq{};
-        bq.first = conv_problem(g, {});
-        bq.c_out2 = h.c_out;
-        bq.c_out2_pitch = round_up(values_[size_t(h.out)].shape.c, 8);
-        bq.act2 = h.act; bq.clip2_lo = h.clip_lo; bq.clip2_hi = h.clip_hi;
-        return bq;
-    };
-    if (const char* b2b_env = getenv("SMELTER_B2B"); b2b_env && atoi(b2b_env) != 0 && !mega_on) {
-        for (size_t fi = 0; fi < filters_.size(); ++fi) {
-            const Filter& h = filters_[fi];
-            if (h.removed || absorbed[fi] || side_of[fi] >= 0 || !plain_tc_conv(h) || h.conv_mode != k::CONV_MODE_TILED) continue;
-            const int mid = root_of(h.in[0]);
-            const int gi = producer[size_t(mid)];
-            if (gi < 0 || gi >= int(fi) || mid == out_root || reads[size_t(mid)] != 1 || values_[size_t(mid)].is_input) continue;
-            const Filter& g = filters_[size_t(gi)];
-            if (!plain_tc_conv(g) || absorbed[size_t(gi)] || side_of[size_t(gi)] >= 0 || b2b_first[size_t(gi)] >= 0 || g.residual >= 0 || h.c_in_g != g.c_out) continue;
-            if (!k::conv_b2b_supported(b2b_problem(g, h), num_sms)) continue;
-            b2b_first[fi] = gi;
-            absorbed[size_t(gi)] = 1;
-        }
-    }
-
     // last use of every root value (filter index); the output value lives forever.  An absorbed shortcut's input is read by the
     // convolution that absorbed it.
     std::vector<int> last_use(values_.size(), -1);
@@ -599,7 +571,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         for (int i : f.in) last_use[size_t(root_of(i))] = int(fi);
         if (f.residual >= 0 && side_of[fi] < 0) last_use[size_t(root_of(f.residual))] = int(fi);
         if (side_of[fi] >= 0) last_use[size_t(root_of(filters_[size_t(side_of[fi])].in[0]))] = int(fi);
-        if (b2b_first[fi] >= 0) last_use[size_t(root_of(filters_[size_t(b2b_first[fi])].in[0]))] = int(fi);
     }
     last_use[size_t(out_root)] = int(filters_.size()) + 1;
 
@@ -627,37 +598,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             (only->s2d || only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
             stem_of[size_t(v)] = only;
     }
-    // ---- runs of consecutive tensor-core convolutions: one persistent multi-layer launch each (kernels/conv_mega.cu) ----
-    // Inside a run tiles of different layers are in flight at the same time, so no buffer is recycled until the run ends.
-    std::vector<int> run_of(filters_.size(), -1);
-    std::vector<std::vector<size_t>> runs;
-    // Opt-in (SMELTER_MEGA=1): on ResNet-50 / batch 32 the persistent kernel currently ties with per-layer launches (the
-    // ~6.5 us store -> fence -> counter -> poll -> load dependency hop costs what a PDL kernel boundary costs).
-    if (mega_on) {
-        std::vector<size_t> cur;
-        auto flush_run = [&]() {
-            if (cur.size() >= 2) {
-                for (size_t fi : cur) run_of[fi] = int(runs.size());
-                runs.push_back(cur);
-            }
-            cur.clear();
-        };
-        for (size_t fi = 0; fi < filters_.size(); ++fi) {
-            const Filter& f = filters_[fi];
-            if (f.removed) continue;
-            bool ok = f.kind == FilterKind::Conv && f.conv_mode != 4 && !f.is_gemm && !f.transposed;
-            if (ok && f.conv_mode == k::CONV_MODE_PACKED_ROW && (f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) &&
-                stem_of[size_t(root_of(f.in[0]))] != &f)
-                ok = false;  // needs its own pad pass in front
-            if (!ok) { flush_run(); continue; }
-            if (f.conv_mode == k::CONV_MODE_PACKED_ROW) flush_run();  // reads a tensor laid out by a non-conv step: may only start a run
-            cur.push_back(fi);
-            if (int(cur.size()) == k::kMegaMaxLayers) flush_run();
-        }
-        flush_run();
-    }
-    std::vector<std::pair<size_t, size_t>> deferred_release;
-
     auto input_bytes = [&](int v) {
         const Filter* f = stem_of[size_t(v)];
         if (!f) return bytes_of(v);
@@ -682,7 +622,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             scratch[fi].bytes = size_t(N) * tq.h * tq.w * tq.c_in_pitch * 2;
             scratch[fi].off = arena.alloc(scratch[fi].bytes);
         }
-        if (f.kind == FilterKind::Conv && f.conv_mode != 4 && side_of[fi] < 0 && b2b_first[fi] < 0) {
+        if (f.kind == FilterKind::Conv && f.conv_mode != 4 && side_of[fi] < 0) {
             const k::ConvTcPlanInfo info = k::conv_tc_plan(conv_problem(f, stem_of), num_sms);
             if (info.splits > 1) {
                 scratch2[fi].bytes = info.ws_bytes;
@@ -713,19 +653,13 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         for (int i : f.in) roots.push_back(root_of(i));
         if (f.residual >= 0 && side_of[fi] < 0) roots.push_back(root_of(f.residual));
         if (side_of[fi] >= 0) roots.push_back(root_of(filters_[size_t(side_of[fi])].in[0]));
-        if (b2b_first[fi] >= 0) roots.push_back(root_of(filters_[size_t(b2b_first[fi])].in[0]));
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
             if (last_use[size_t(r)] == int(fi) && off[size_t(r)] != size_t(-1)) {
                 const size_t rb = values_[size_t(r)].is_input ? input_bytes(r) : bytes_of(r);
-                if (run_of[fi] >= 0) deferred_release.push_back({off[size_t(r)], rb});
-                else arena.release(off[size_t(r)], rb);
+                arena.release(off[size_t(r)], rb);
             }
-        if (run_of[fi] >= 0 && runs[size_t(run_of[fi])].back() == fi) {
-            for (const auto& d : deferred_release) arena.release(d.first, d.second);
-            deferred_release.clear();
-        }
     }
     // result tensor (NCHW) unless the output value is already NCHW-compatible
     const ImageShape& os = values_[size_t(output_value_)].shape;
@@ -780,12 +714,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         plan->steps.back().boundary = true;
     }
 
-    std::vector<k::ConvTcProblem> mega_q;
-    std::vector<int> mega_dep, mega_res_dep;
-    std::unordered_map<int, int> mega_producer;  // root value -> layer of the current run that writes it
-    double mega_flops = 0, mega_bytes = 0;
-    std::string mega_desc;
-    void* mega_identity = nullptr;
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
         const Filter& f = filters_[fi];
         if (f.removed || absorbed[fi]) continue;
@@ -813,27 +741,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                         return k::depthwise_conv(x, w, bias, y, N, is.h, is.w, icp, osz.h, osz.w, fp->k_h, fp->k_w, fp->stride_h, fp->stride_w, fp->dil_h,
                                                  fp->dil_w, fp->pads[0], fp->pads[1], fp->act, fp->clip_lo, fp->clip_hi, st);
                     }, flops, io_bytes);
-                    break;
-                }
-                if (b2b_first[fi] >= 0) {
-                    const Filter& g = filters_[size_t(b2b_first[fi])];
-                    k::ConvB2bProblem bq = b2b_problem(g, f);
-                    bq.first.x = ptr_of(g.in[0]);
-                    bq.first.w_packed = reinterpret_cast<const __half*>(wbase + g.w_off);
-                    bq.first.bias = reinterpret_cast<const float*>(wbase + g.bias_off);
-                    bq.w2_packed = w; bq.bias2 = bias; bq.residual = res; bq.y = y;
-                    if (res && last_use[size_t(root_of(f.residual))] == int(fi)) bq.l2_hints |= 2;
-                    auto BL = std::make_shared<k::ConvB2bLaunch>();
-                    std::string cerr;
-                    if (!k::conv_b2b_prepare(BL.get(), bq, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
-                    const ImageShape gs = values_[size_t(g.in[0])].shape;
-                    const std::string mid_act = g.act == k::ACT_RELU ? "+relu" : g.act == k::ACT_CLIP ? "+clip" : "";
-                    add_step("conv_b2b[" + std::string(g.conv_mode == k::CONV_MODE_TILED ? "tiled" : "im2col") + ",n1=" + std::to_string(g.c_out) + mid_act + " -> 1x1]" +
-                                 suffix + " Conv " + values_[size_t(g.out)].name + " -> " + values_[size_t(f.out)].name,
-                             [BL](cudaStream_t st) { return k::conv_b2b_launch(*BL, st); }, BL->flops,
-                             double(N) * (double(gs.h) * gs.w * round_up(gs.c, 8) + double(osz.h) * osz.w * ocp * (res ? 2 : 1)) * 2 +
-                                 double(g.c_out) * g.c_in_g * g.k_h * g.k_w * 2 + double(f.c_out) * f.c_in_g * 2);
-                    plan->steps.back().tensor = true;
                     break;
                 }
                 k::ConvTcProblem q = conv_problem(f, stem_of);
@@ -873,42 +780,6 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                         return k::pad2d(x, padded, N, is.h, is.w, 8, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], k::PAD_CONSTANT, 0.f, st);
                     }, 0, double(scratch[fi].bytes) + double(N) * is.h * is.w * 16);
                     q.x = padded;
-                }
-                if (run_of[fi] >= 0) {
-                    // member of a persistent run: collected here, launched as one step when the run's last layer is reached
-                    const std::vector<size_t>& run = runs[size_t(run_of[fi])];
-                    if (run.front() == fi) { mega_q.clear(); mega_dep.clear(); mega_res_dep.clear(); mega_producer.clear(); mega_flops = mega_bytes = 0; mega_desc.clear(); }
-                    auto producer = [&](int v) { auto itp = mega_producer.find(root_of(v)); return itp == mega_producer.end() ? -1 : itp->second; };
-                    mega_dep.push_back(producer(f.in[0]));
-                    mega_res_dep.push_back(f.residual >= 0 ? producer(f.residual) : -1);
-                    mega_producer[root_of(f.out)] = int(mega_q.size());
-                    mega_q.push_back(q);
-                    mega_flops += flops;
-                    mega_bytes += io_bytes + double(f.c_out) * f.c_in_g * f.k_h * f.k_w * 2 + (res ? double(N) * osz.h * osz.w * ocp * 2 : 0);
-                    if (run.front() == fi) mega_desc = values_[size_t(f.out)].name;
-                    if (run.back() == fi) {
-                        auto ML = std::make_shared<k::MegaLaunch>();
-                        const size_t words = k::conv_mega_sync_words(mega_q);
-                        void* sync = nullptr;
-                        SM_CUDA(cudaMalloc(&sync, words * sizeof(unsigned int)));
-                        plan->blobs.push_back(sync);
-                        if (!mega_identity) {  // 64 x 64 fp16 identity: the B operand of the residual k-blocks
-                            std::vector<uint16_t> eye(64 * 64, 0);
-                            for (int d = 0; d < 64; ++d) eye[size_t(d) * 65] = 0x3C00;
-                            SM_CUDA(cudaMalloc(&mega_identity, eye.size() * 2));
-                            plan->blobs.push_back(mega_identity);
-                            SM_CUDA(cudaMemcpy(mega_identity, eye.data(), eye.size() * 2, cudaMemcpyHostToDevice));
-                        }
-                        std::string cerr;
-                        if (!k::conv_mega_prepare(ML.get(), mega_q, mega_dep, mega_res_dep, num_sms, static_cast<unsigned int*>(sync),
-                                                  static_cast<const __half*>(mega_identity), &cerr))
-                            return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
-                        add_step("conv_mega[" + std::to_string(mega_q.size()) + " layers] Conv " + mega_desc + " .. " + values_[size_t(f.out)].name,
-                                 [ML](cudaStream_t st) { return k::conv_mega_launch(*ML, st); }, mega_flops, mega_bytes);
-                        plan->steps.back().tensor = true;
-                        plan->steps.back().launches = 2;  // counter memset + kernel
-                    }
-                    break;
                 }
                 auto L = std::make_shared<k::ConvTcLaunch>();
                 std::string cerr;

@@ -988,7 +988,6 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
         cudaError_t e = set_attr(block_n);
         if (e == cudaSuccess && (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && (block_n == 64 || block_n == 128 || block_n == 256)) {
             e = conv_pair_set_attr(block_n);
-            if (e == cudaSuccess) e = conv_duo_set_attr(block_n);
         }
         if (e != cudaSuccess) { if (err) *err = std::string("cudaFuncSetAttribute: ") + cudaGetErrorString(e); return false; }
     }
@@ -1019,10 +1018,6 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     // ---- B: packed weights [Cout][taps][kc]; two-CTA clusters (conv_pair.cu): each CTA loads half of the weight tile ----
     const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
     L->pair = want_pair ? 1 : 0;
-    // conv_duo.cu (opt-in, SMELTER_DUO=1): the same tiles with two CTAs per SM and the residual as identity k-blocks.  Measured on
-    // ResNet-50 / batch 32: one encode 0.646 ms vs 0.547 ms (half the ring per CTA), two encodes in flight 0.509 vs 0.501 ms per batch.
-    const bool want_duo = want_pair && conv_duo_supported(block_n, plan.splits) && getenv("SMELTER_DUO") != nullptr;
-    L->duo = want_duo ? 1 : 0;
     L->num_sms = num_sms;
     if (!encode_b_map(&L->tm_b, q.w_packed, kc, taps, q.c_out, want_pair ? block_n / 2 : block_n, err)) return false;
     // ---- D (and the residual, same geometry): [M, out_pitch] fp16, stored / loaded as [32 rows x 64 cols] swizzled boxes ----
@@ -1030,7 +1025,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
         const __half* base = which == 0 ? q.y : (q.residual ? q.residual : q.y);
         cuuint64_t dims[2] = {cuuint64_t(q.c_out_pitch), cuuint64_t(M)};
         cuuint64_t strides[1] = {cuuint64_t(q.c_out_pitch) * 2};
-        cuuint32_t box[2] = {cuuint32_t(kChunkN), cuuint32_t(which == 1 && want_duo ? kBlockM : 32)};  // duo: the residual is an A operand
+        cuuint32_t box[2] = {cuuint32_t(kChunkN), cuuint32_t(32)};
         cuuint32_t estr[2] = {1, 1};
         CUresult r = g_encode_tiled(which == 0 ? &L->tm_out : &L->tm_res, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<__half*>(base), dims, strides,
                                     box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1039,13 +1034,6 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
             if (err) *err = "cuTensorMapEncodeTiled(output) failed: " + std::to_string(int(r));
             return false;
         }
-    }
-    if (want_duo && q.residual) {
-        const __half* ident = nullptr;
-        cudaError_t e = conv_duo_identity(&ident);
-        if (e != cudaSuccess) { if (err) *err = std::string("conv: identity operand: ") + cudaGetErrorString(e); return false; }
-        if (!conv_tc_encode_2d(&L->tm_ident, ident, 256, 256, kBlockK, block_n / 2, err)) return false;
-        p.res_kb = block_n / kBlockK;
     }
     // ---- A ----
     if (!encode_a_map(&L->tm_a, mode, q.x, q.n, q.h, q.w, q.c_in_pitch, kc, M, R, S, Q, q.stride_h, q.stride_w, q.dil_h, q.dil_w, q.pad_t, q.pad_l,
@@ -1409,7 +1397,6 @@ void conv_tc_dump_timeline(const ConvTcLaunch& L) {
 }
 
 cudaError_t conv_tc_launch(const ConvTcLaunch& L, cudaStream_t stream) {
-    if (L.duo) return conv_duo_launch(L, L.num_sms, stream);
     if (L.pair) return conv_pair_launch(L, L.num_sms, stream);
     switch (L.block_n) {
         case 32: return launch_t<32>(L, stream);

@@ -45,9 +45,6 @@ struct ConvKernelParams {
     int side_mode;           // CONV_MODE_TILED (stride 1) or CONV_MODE_IM2COL
     int side_stride_h, side_stride_w;
     const float* bias2;      // the shortcut's bias, added to `bias` in the epilogue (nullptr = none)
-    // Residual add on the tensor core (conv_duo.cu only): after the main and shortcut k-blocks, `res_kb` = BLOCK_N / 64 k-blocks take
-    // the residual tile as the A operand (tm_res, [128 x 64] boxes) against 64 columns of an identity matrix (tm_ident).
-    int res_kb;              // 0 = none
 };
 
 struct ConvTcProblem {
@@ -92,14 +89,12 @@ bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms);
 struct ConvTcLaunch {
     CUtensorMap tm_a, tm_b, tm_out, tm_res;
     CUtensorMap tm_a2, tm_b2;  // projection shortcut operands (p.side_kb > 0)
-    CUtensorMap tm_ident;      // conv_duo.cu: [BLOCK_N / 2 rows x 64 cols] boxes of the identity matrix (p.res_kb > 0)
     ConvKernelParams p;
     int block_n;
     int splits;
     int grid;
     int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
     int pair;      // launched as conv_pair_kernel (two-CTA clusters): tm_b boxes hold BLOCK_N / 2 rows
-    int duo;       // launched as conv_duo_kernel (two-CTA clusters, two CTAs per SM); implies pair-style tm_b
     int num_sms;
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
 };
@@ -116,42 +111,6 @@ void conv_tc_chain_dump();
 bool conv_pair_supported(const ConvTcLaunch& L);
 cudaError_t conv_pair_set_attr(int block_n);
 cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
-// half-footprint two-CTA variant, two CTAs per SM, residual add as identity k-blocks (conv_duo.cu)
-bool conv_duo_supported(int block_n, int splits);
-cudaError_t conv_duo_set_attr(int block_n);
-cudaError_t conv_duo_identity(const __half** out);
-cudaError_t conv_duo_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream);
-// ---- back-to-back pair (conv_b2b.cu, opt-in): a convolution with 64 / 128 output channels and the 1x1 convolution that consumes
-//      it run as one launch; the intermediate tile stays in shared memory ----
-struct ConvB2bProblem {
-    ConvTcProblem first;      // conv A: x, w_packed, bias, act (the activation between the two); y / residual / side_* unused
-    const __half* w2_packed;  // conv B weights [c_out2][c_out of A]
-    const float* bias2;
-    int c_out2, c_out2_pitch;
-    const __half* residual;   // [M, c_out2_pitch] added before conv B's activation, or nullptr
-    __half* y;                // [M, c_out2_pitch]
-    int act2;
-    float clip2_lo, clip2_hi;
-    int l2_hints;
-};
-struct ConvB2bParams {
-    const float* bias2;
-    int act2;
-    float clip2_lo, clip2_hi;
-    int subtiles;             // 128-column accumulators of conv B per tile
-    int has_residual;
-    int l2_hints;
-};
-struct ConvB2bLaunch {
-    CUtensorMap tm_a, tm_b1, tm_b2, tm_out, tm_res;
-    ConvKernelParams p;       // conv A geometry
-    ConvB2bParams p2;
-    int n1, grid, use_pdl;
-    double flops;
-};
-bool conv_b2b_supported(const ConvB2bProblem& q, int num_sms);
-bool conv_b2b_prepare(ConvB2bLaunch* L, const ConvB2bProblem& q, int num_sms, std::string* err);
-cudaError_t conv_b2b_launch(const ConvB2bLaunch& L, cudaStream_t stream);
 // benchmark only: TMA load rate of [128 x 64] fp16 boxes; mode 0 = 2-D tiled over [N*H*W, C], 1 = im2col (3x3, pad 1)
 int tma_probe3(int mode, int c, long rows_total, int slabs, int stages, int iters, int grid, const __half* x, cudaStream_t stream, float* ms,
                std::string* err);

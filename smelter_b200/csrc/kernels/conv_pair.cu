@@ -454,11 +454,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
         if (kInstr && lane == 0 && group_tiles > 0) chain_stamp(p, 4);
-#ifdef SMELTER_TEARDOWN_FULL_WAIT
-        if (lane == 0) tma_store_wait<0>();
-#else
         if (lane == 0) tma_store_wait_read<0>();
-#endif
         if (kInstr && lane == 0 && group_tiles > 0) chain_stamp(p, 6);
     }
 

@@ -7,7 +7,6 @@
 #include <stdint.h>
 
 #include "conv_igemm.h"
-#include "conv_mega.h"
 
 namespace smelter {
 namespace k {

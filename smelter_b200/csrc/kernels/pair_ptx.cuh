@@ -1,5 +1,5 @@
 // cta_group::2 / cluster forms of the PTX wrappers and the epilogue arithmetic shared by the two-CTA convolution kernels
-// (conv_pair.cu, conv_b2b.cu).
+// (conv_pair.cu).
 #pragma once
 #include <cuda_fp16.h>
 

@@ -113,35 +113,6 @@ def test_resnet50_batch32_properties(ctx, monkeypatch):
     assert np.abs(full1[:2].astype(np.float32) - want).max() <= TOL
 
 
-def test_persistent_multi_layer_kernel_matches_per_layer_launches(ctx, monkeypatch):
-    """SMELTER_MEGA=1 runs the 52 bottleneck convolutions of ResNet-50 as ONE persistent launch with per-tile dataflow
-    dependencies (kernels/conv_mega.cu); the residual add moves into the tensor-core accumulator, so results agree with the
-    per-layer path to fp16 rounding, and with the oracle within the stated tolerance."""
-    from smelter_b200 import modelzoo, onnx2mps
-    from smelter_b200.api import Image, ONNXGraph
-
-    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
-    x = np.random.default_rng(5).random((8, 3, 224, 224), dtype=np.float32).astype(np.float16)
-
-    def run():
-        g = ONNXGraph(model, context=ctx)
-        nn = g.metalGraph()
-        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(8, 1000).copy() for _ in range(3)]
-        n = nn.numLaunches(8) + nn.planDump(8).count("+conv1x1(")
-        g.close()
-        return outs, n
-
-    base, n_base = run()
-    monkeypatch.setenv("SMELTER_MEGA", "1")  # read when a plan is made
-    mega, n_mega = run()
-    assert n_base == 57 and n_mega == 1 + 1 + 1 + 2 + 1 + 1  # boundary, stem, maxpool, [counter memset + persistent kernel], gap, fc
-    for o in mega[1:]:
-        assert np.array_equal(o.view(np.uint16), mega[0].view(np.uint16))  # replay determinism despite the dynamic tile timing
-    assert np.abs(mega[0].astype(np.float32) - base[0].astype(np.float32)).max() <= 4e-3
-    want = _oracle(model, x[:2])
-    assert np.abs(mega[0][:2].astype(np.float32) - want).max() <= TOL
-
-
 def test_projection_shortcut_runs_inside_the_block_output_conv(ctx, monkeypatch):
     """The four 1x1 "downsample" convolutions of ResNet-50 are extra k-blocks of their block's last convolution (one GEMM over
     the concatenated K axis, kernels/conv_pair.cu): four launches fewer, the shortcut tensor never exists, and the sum is
@@ -184,36 +155,6 @@ def test_folded_projection_shortcut_on_ragged_tiles(ctx, monkeypatch, batch, hw)
     assert _run.folded == 4
     want = _oracle(model, x)
     assert np.abs(out.reshape(want.shape) - want).max() <= TOL
-
-
-@pytest.mark.parametrize("batch,hw,depths", [(2, 64, (2, 2, 1, 1)), (3, 40, (2, 3, 1, 1)), (32, 224, (3, 4, 6, 3))])
-def test_back_to_back_conv_pairs_keep_the_intermediate_on_chip(ctx, monkeypatch, batch, hw, depths):
-    """SMELTER_B2B=1 (opt-in, kernels/conv_b2b.cu): the 3x3 of a stage-1/2 bottleneck and the 1x1 that consumes it are one launch; the
-    3x3's output is rounded to fp16 exactly as when it is stored, so results equal the two-launch form bit for bit."""
-    from smelter_b200 import modelzoo
-    from smelter_b200.api import Image, ONNXGraph
-
-    model = modelzoo.resnet50(seed=3, fold_bn=True, num_classes=40, hw=hw, depths=depths).serialize()
-    x = np.random.default_rng(batch).random((batch, 3, hw, hw), dtype=np.float32).astype(np.float16)
-
-    def run():
-        g = ONNXGraph(model, context=ctx)
-        nn = g.metalGraph()
-        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(batch, -1).copy() for _ in range(2)]
-        dump, n = nn.planDump(batch), nn.numLaunches(batch)
-        g.close()
-        assert np.array_equal(outs[0].view(np.uint16), outs[1].view(np.uint16))
-        return outs[0], dump, n
-
-    monkeypatch.setenv("SMELTER_NO_SPLITK", "1")  # same k-order in both forms whatever the batch
-    base, dump0, n0 = run()
-    monkeypatch.setenv("SMELTER_B2B", "1")  # read when a plan is made
-    fused, dump1, n1 = run()
-    pairs = dump1.count("conv_b2b[")
-    assert dump0.count("conv_b2b[") == 0 and pairs == depths[0] - 1 + depths[1] - 1 and n0 - n1 == pairs  # identity blocks of stages 1 and 2
-    assert np.array_equal(fused.view(np.uint16), base.view(np.uint16))
-    want = _oracle(model, x[:2])
-    assert np.abs(fused[:2].astype(np.float32) - want).max() <= TOL
 
 
 def test_mobilenet_v2_batch1(ctx):

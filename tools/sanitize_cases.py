@@ -53,7 +53,6 @@ rng = np.random.default_rng(0)
 small = modelzoo.resnet50(seed=0, fold_bn=True, num_classes=16, hw=64, depths=(1, 1, 1, 1)).serialize()
 x = rng.random((2, 3, 64, 64), dtype=np.float32).astype(np.float16)
 model(small, x, 1e-2, "resnet bottlenecks (per-layer)")
-model(small, x, 1e-2, "resnet bottlenecks (persistent kernel)", SMELTER_MEGA="1")
 ragged = modelzoo.resnet50(seed=1, fold_bn=True, num_classes=16, hw=40, depths=(1, 1, 1, 1)).serialize()
 model(ragged, rng.random((3, 3, 40, 40), dtype=np.float32).astype(np.float16), 1e-2, "resnet bottlenecks, ragged tiles, shortcuts folded", SMELTER_NO_SPLITK="1")
 model(modelzoo.decoder_ops(seed=3).serialize(), rng.standard_normal((1, 32, 10, 10)).astype(np.float16), 1e-2, "conv_transpose / group_norm / pow")

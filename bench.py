@@ -461,9 +461,9 @@ def run_native(args) -> int:
     conv_ms_raw = sum(p["ms"] for p in conv)
     conv_flops = sum(p["flops"] for p in conv)
     total_ms_raw = sum(p["ms"] for p in prof)
-    share = conv_ms_raw / total_ms_raw if total_ms_raw else 0.0
+    conv_share = conv_ms_raw / total_ms_raw if total_ms_raw else 0.0
     step_ms = elapsed_ms / K
-    conv_ms = step_ms * share
+    conv_ms = step_ms * conv_share
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = ncu_conv_traffic()
@@ -472,10 +472,10 @@ def run_native(args) -> int:
                 "traffic": traffic, "traffic_source": traffic_src,
                 "kernel": f"conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> ({len(conv)} conv/gemm launches per step, aggregated; "
                           f"{sum('+conv1x1(' in p['desc'] for p in conv)} of them carry a folded 1x1 projection shortcut)",
-                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json); frac_of_burst_peak uses bf16_tflops", "kernel_share_of_step": share,
+                "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json); frac_of_burst_peak uses bf16_tflops", "kernel_share_of_step": conv_share,
                 "launch_ms_sum": conv_ms, "launch_ms_sum_raw_with_event_nodes": conv_ms_raw, "flops_per_step": conv_flops,
                 "achieved_raw_with_event_nodes": conv_flops / (conv_ms_raw * 1e-3) / 1e12 if conv_ms_raw > 0 else 0.0,
-                "achieved_one_in_flight": conv_flops / (one_ms * share * 1e-3) / 1e12 if one_ms > 0 else 0.0,
+                "achieved_one_in_flight": conv_flops / (one_ms * conv_share * 1e-3) / 1e12 if one_ms > 0 else 0.0,
                 "how": "algorithmic FLOPs (2*M*N*K, SURVEY 8d) / (event-timed step x conv share from in-graph per-kernel events); "
                        f"step = elapsed / steps with {S} encodes in flight",
                 "step_frac_of_conv_roofline": value / world / (pk["tflops_sustained"] * 1e12 / FLOPS_PER_IMAGE)}

@@ -703,7 +703,6 @@ int32_t smelter_run_conv(smelter_context* ctx, const smelter_conv_problem* p, co
     reformat_conv_weight(w_oihw.data(), w_ohwi.data(), 4, p->c_out, c_in_g, p->k_h, p->k_w, false);
     std::vector<uint16_t> packed;
     if (mode == 4) { packed.resize(size_t(p->k_h) * p->k_w * ocp); pack_weights_depthwise(w_ohwi.data(), p->c_out, p->k_h, p->k_w, ocp, packed.data()); }
-    else if (mode == k::CONV_MODE_PACKED_ROW) { packed.resize(size_t(p->c_out) * p->k_h * p->k_w * 8); pack_weights_rows(w_ohwi.data(), p->c_out, p->c_in, p->k_h, p->k_w, packed.data()); }
     else { packed.resize(size_t(p->c_out) * p->k_h * p->k_w * icp); pack_weights_ohwi(w_ohwi.data(), p->c_out, p->c_in, p->k_h, p->k_w, icp, packed.data()); }
     std::vector<float> bias_pad(size_t(round_up(p->c_out, 256)), 0.f);
     if (p->has_bias) memcpy(bias_pad.data(), bias, size_t(p->c_out) * 4);

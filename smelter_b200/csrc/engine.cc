@@ -66,15 +66,6 @@ void pack_weights_ohwi(const float* w, int c_out, int c_in, int k_h, int k_w, in
             for (int c = c_in; c < c_in_pitch; ++c) d[c] = 0;
         }
 }
-void pack_weights_rows(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst) {
-    for (int o = 0; o < c_out; ++o)
-        for (int r = 0; r < k_h; ++r)
-            for (int s = 0; s < k_w; ++s) {
-                const float* src = w + ((size_t(o) * k_h + r) * k_w + s) * c_in;
-                uint16_t* d = dst + ((size_t(o) * k_h + r) * k_w + s) * 8;
-                for (int c = 0; c < 8; ++c) d[c] = c < c_in ? onnx::float_to_half(src[c]) : uint16_t(0);
-            }
-}
 // Stride-2 stem folded to stride 1 over a 2x2 space-to-depth image (Filter::s2d): w is OHWI [o][r][s][c]; the packed row
 // operand is [o][r2][s2][16] with channel (dy*2+dx)*c_in + c holding w[o][2*r2+dy][2*s2+dx][c] (zero outside the filter).
 void pack_weights_s2d(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst) {
@@ -103,6 +94,13 @@ int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride
         return -1;
     }
     if (c_in <= 8 && dil_w == 1 && k_w * 8 <= 256 && k_h * k_w > 1) return k::CONV_MODE_PACKED_ROW;
+    // Narrow inputs (channel pitch 16..32) without padding of their own (the graph pads explicitly, e.g. reflection padding in front of
+    // every TransformerNet convolution): a filter row of S taps is S x pitch contiguous NHWC elements, so one K block can span several
+    // taps -- R x ceil(S x pitch / 64) dense k-blocks instead of R x S half-empty ones (9x9 on 32 channels: 45 instead of 81).
+    const int pitch = (c_in + 7) / 8 * 8;
+    if (pitch <= 32 && dil_w == 1 && k_w >= 3 && !pads[0] && !pads[1] && !pads[2] && !pads[3] && k_w * pitch <= 1024 &&
+        k_h * ((k_w * pitch + 63) / 64) < k_h * k_w)
+        return k::CONV_MODE_PACKED_ROW;
     if (k_h == 1 && k_w == 1 && stride_h == 1 && stride_w == 1 && !pads[0] && !pads[1] && !pads[2] && !pads[3]) return k::CONV_MODE_TILED;
     return k::CONV_MODE_IM2COL;
 }
@@ -381,7 +379,6 @@ int ONNXGraph::upload_weights() {
             size_t wbytes;
             if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
             else if (f.s2d) wbytes = size_t(f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 16 * 2;
-            else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) wbytes = size_t(f.c_out) * f.k_h * f.k_w * 8 * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
             f.bias_off = total; total = align(total + size_t(round_up(f.c_out, 256)) * 4);
@@ -400,7 +397,6 @@ int ONNXGraph::upload_weights() {
             uint16_t* w = reinterpret_cast<uint16_t*>(host.data() + f.w_off);
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
             else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
-            else if (f.conv_mode == k::CONV_MODE_PACKED_ROW) pack_weights_rows(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
         } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {

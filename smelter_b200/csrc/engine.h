@@ -201,7 +201,6 @@ int pool_output_size(int in, int k, int stride, int pad);
 
 // Weight packers for the conv kernels (w is OHWI fp32 [c_out][k_h][k_w][c_in]).
 void pack_weights_ohwi(const float* w, int c_out, int c_in, int k_h, int k_w, int c_in_pitch, uint16_t* dst);  // [c_out][k_h*k_w][pitch]
-void pack_weights_rows(const float* w, int c_out, int c_in, int k_h, int k_w, uint16_t* dst);                   // [c_out][k_h][k_w*8]
 void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch, uint16_t* dst);               // [k_h*k_w][pitch]
 int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride_h, int stride_w, int dil_w, const int pads[4]);
 

@@ -946,8 +946,8 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     } else if (mode == CONV_MODE_IM2COL) {
         kc = q.c_in_pitch; taps = R * S; taps_w = S;
     } else if (mode == CONV_MODE_PACKED_ROW) {
-        if ((q.c_in_pitch != 8 && q.c_in_pitch != 16) || q.dil_w != 1 || q.pad_t || q.pad_l || q.pad_b || q.pad_r || S * q.c_in_pitch > 256) {
-            if (err) *err = "conv: packed-row mode needs Cin pitch 8 or 16, dilation_w 1 and materialised padding";
+        if (q.c_in_pitch % 8 || q.c_in_pitch > 64 || q.dil_w != 1 || q.pad_t || q.pad_l || q.pad_b || q.pad_r || S * q.c_in_pitch > 1024) {
+            if (err) *err = "conv: packed-row mode needs a Cin pitch of 8..64, dilation_w 1 and materialised padding";
             return false;
         }
         kc = S * q.c_in_pitch; taps = R; taps_w = 1;

@@ -12,6 +12,7 @@
 #include <cstdlib>
 
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace smelter {
 namespace k {
@@ -107,6 +108,7 @@ __device__ __forceinline__ void zero_tail(float (&f)[8], size_t vec, int cp8, in
 
 __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t n8, int kind,
                                                         float a, float b, int cp8, int tail) {
+    pdl_prologue();
     constexpr size_t step = kThreads;
     const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
     Half8 v[kU1];
@@ -146,6 +148,7 @@ __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restric
 
 __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restrict__ pa, const __half* __restrict__ pb,
                                                          __half* __restrict__ y, size_t n8, int kind, int act, int cp8, int tail) {
+    pdl_prologue();
     constexpr size_t step = kThreads;
     const size_t base = size_t(blockIdx.x) * (kThreads * kU2) + threadIdx.x;
     Half8 va[kU2], vb[kU2];
@@ -183,6 +186,7 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restri
 template <bool kFixed>
 __global__ void __launch_bounds__(kThreads) scale_shift_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t n8, int cp8,
                                                               const float* __restrict__ scale, const float* __restrict__ shift, int act) {
+    pdl_prologue();
     const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
     const float lo = act == ACT_RELU ? 0.f : -INFINITY;
     Half8 v[kU1];
@@ -310,6 +314,7 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const __half* __r
 // :266-287).  One thread per destination (pixel, 8 channels): copies the source vector when the pixel sits on the stride lattice.
 __global__ void __launch_bounds__(kThreads) zero_stuff2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
                                                                int hz, int wz, int sh, int sw, int lo_h, int lo_w) {
+    pdl_prologue();
     const size_t total = size_t(n) * hz * wz * cp8;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int g = int(i % cp8);
@@ -374,6 +379,7 @@ __global__ void __launch_bounds__(kThreads) resize_planes_kernel(const __half* _
 // One thread per (pixel, 8-channel group), pixel fastest so plane writes are coalesced along W.
 __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c,
                                                                int hw, int cp, long dst_image_pitch) {
+    pdl_prologue();
     const int groups = cp / 8;
     const size_t total = size_t(n) * groups * hw;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
@@ -396,6 +402,7 @@ __global__ void __launch_bounds__(kThreads) nhwc_to_nchw_kernel(const __half* __
 // written once, no per-element division beyond one 32-bit divide by the vectors per pixel.
 __global__ void __launch_bounds__(kThreads) upsample_nearest_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h,
                                                                    int w, int cp8, int sh, int sw) {
+    pdl_prologue();
     const int iy = blockIdx.y % h;
     const int img = blockIdx.y / h;
     const unsigned row_items = unsigned(w) * unsigned(cp8);
@@ -424,6 +431,7 @@ __global__ void __launch_bounds__(kThreads) upsample_nearest_kernel(const __half
 // (Converters.swift:529-536).
 __global__ void __launch_bounds__(kThreads) upsample_bilinear_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h,
                                                                     int w, int cp8, int sh, int sw, int align) {
+    pdl_prologue();
     const int ho = h * sh, wo = w * sw;
     const size_t total = size_t(n) * ho * wo * cp8;
     const float ry = align ? (ho > 1 ? float(h - 1) / float(ho - 1) : 0.f) : 1.f / float(sh);
@@ -464,6 +472,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 // blockIdx.y = (image, output row): the source row is resolved once per block; threads walk (ox, channel group) of the row.
 __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
                                                         int pt, int pl, int ho, int wo, int mode, float value) {
+    pdl_prologue();
     const int oy = blockIdx.y % ho;
     const int img = blockIdx.y / ho;
     int sy = oy - pt;
@@ -496,6 +505,7 @@ __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restric
 
 __global__ void __launch_bounds__(kThreads) concat_vec_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t pixels,
                                                              int src8, int dst_pitch, int c_off) {
+    pdl_prologue();
     const size_t total = pixels * src8;
     const size_t base = size_t(blockIdx.x) * (kThreads * kU1) + threadIdx.x;
     Half8 v[kU1];
@@ -517,6 +527,7 @@ __global__ void __launch_bounds__(kThreads) concat_vec_kernel(const __half* __re
 }
 __global__ void __launch_bounds__(kThreads) concat_scalar_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t pixels,
                                                                 int c_src, int src_pitch, int dst_pitch, int c_off) {
+    pdl_prologue();
     const size_t total = pixels * c_src;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int ch = int(i % c_src);
@@ -547,19 +558,19 @@ __global__ void __launch_bounds__(kThreads) checksum_kernel(const uint32_t* __re
 cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
     const int tail = cp > 0 ? (c & 7) : 0;
-    unary_kernel<<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
+    (void)launch_pdl(unary_kernel, dim3(tiled_grid(n8, kU1)), dim3(kThreads), s, x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
 cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c, int cp) {
     const size_t n8 = n_elems / 8;
     const int tail = cp > 0 ? (c & 7) : 0;
-    binary_kernel<<<tiled_grid(n8, kU2), kThreads, 0, s>>>(a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
+    (void)launch_pdl(binary_kernel, dim3(tiled_grid(n8, kU2)), dim3(kThreads), s, a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
 cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act, cudaStream_t s) {
     const size_t n8 = pixels * (cp / 8);
-    if (kThreads % (cp / 8) == 0) scale_shift_kernel<true><<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, cp / 8, scale, shift, act);
-    else scale_shift_kernel<false><<<tiled_grid(n8, kU1), kThreads, 0, s>>>(x, y, n8, cp / 8, scale, shift, act);
+    if (kThreads % (cp / 8) == 0) (void)launch_pdl(scale_shift_kernel<true>, dim3(tiled_grid(n8, kU1)), dim3(kThreads), s, x, y, n8, cp / 8, scale, shift, act);
+    else (void)launch_pdl(scale_shift_kernel<false>, dim3(tiled_grid(n8, kU1)), dim3(kThreads), s, x, y, n8, cp / 8, scale, shift, act);
     return cudaGetLastError();
 }
 cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, int w, int cp, int pad_t, int pad_l, int pad_b, int pad_r,
@@ -623,7 +634,7 @@ cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int
 }
 cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
                          cudaStream_t s) {
-    zero_stuff2d_kernel<<<grid_for(size_t(n) * hz * wz * (cp / 8)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, hz, wz, stride_h, stride_w, lo_h, lo_w);
+    (void)launch_pdl(zero_stuff2d_kernel, dim3(grid_for(size_t(n) * hz * wz * (cp / 8))), dim3(kThreads), s, x, y, n, h, w, cp / 8, hz, wz, stride_h, stride_w, lo_h, lo_w);
     return cudaGetLastError();
 }
 cudaError_t resize_planes(const __half* src, __half* dst, int planes, int hs, int ws, int hd, int wd, int mode, cudaStream_t s) {
@@ -631,7 +642,7 @@ cudaError_t resize_planes(const __half* src, __half* dst, int planes, int hs, in
     return cudaGetLastError();
 }
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s) {
-    nhwc_to_nchw_kernel<<<grid_for(size_t(n) * (cp / 8) * h * w), kThreads, 0, s>>>(src, dst, n, c, h * w, cp, dst_image_pitch);
+    (void)launch_pdl(nhwc_to_nchw_kernel, dim3(grid_for(size_t(n) * (cp / 8) * h * w)), dim3(kThreads), s, src, dst, n, c, h * w, cp, dst_image_pitch);
     return cudaGetLastError();
 }
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
@@ -640,9 +651,9 @@ cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, 
     if (mode == UP_NEAREST) {
         if (size_t(n) * h > 65535) return cudaErrorInvalidValue;  // grid.y = (image, input row)
         const unsigned row_items = unsigned(w) * unsigned(cp / 8);
-        upsample_nearest_kernel<<<dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * h)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8,
+        (void)launch_pdl(upsample_nearest_kernel, dim3(dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * h))), dim3(kThreads), s, x, y, n, h, w, cp / 8,
                                                                                                                                   scale_h, scale_w);
-    } else upsample_bilinear_kernel<<<grid_for(total), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, scale_h, scale_w, align_corners);
+    } else (void)launch_pdl(upsample_bilinear_kernel, dim3(grid_for(total)), dim3(kThreads), s, x, y, n, h, w, cp / 8, scale_h, scale_w, align_corners);
     return cudaGetLastError();
 }
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
@@ -650,18 +661,18 @@ cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int p
     const int ho = h + pt + pb, wo = w + pl + pr;
     if (size_t(n) * ho > 65535) return cudaErrorInvalidValue;  // grid.y = (image, output row)
     const unsigned row_items = unsigned(wo) * unsigned(cp / 8);
-    pad2d_kernel<<<dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho)), kThreads, 0, s>>>(x, y, n, h, w, cp / 8, pt, pl, ho, wo,
+    (void)launch_pdl(pad2d_kernel, dim3(dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho))), dim3(kThreads), s, x, y, n, h, w, cp / 8, pt, pl, ho, wo,
                                                                                                                  mode, value);
     return cudaGetLastError();
 }
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s) {
     if (c_off % 8 == 0 && c_src % 8 == 0) {
-        concat_vec_kernel<<<tiled_grid(pixels * (c_src / 8), kU1), kThreads, 0, s>>>(src, dst, pixels, c_src / 8, c_dst_pitch, c_off);
+        (void)launch_pdl(concat_vec_kernel, dim3(tiled_grid(pixels * (c_src / 8), kU1)), dim3(kThreads), s, src, dst, pixels, c_src / 8, c_dst_pitch, c_off);
         // vector path assumes src pitch == c_src (true when c_src % 8 == 0)
         (void)c_src_pitch;
     } else {
-        concat_scalar_kernel<<<grid_for(pixels * c_src), kThreads, 0, s>>>(src, dst, pixels, c_src, c_src_pitch, c_dst_pitch, c_off);
+        (void)launch_pdl(concat_scalar_kernel, dim3(grid_for(pixels * c_src)), dim3(kThreads), s, src, dst, pixels, c_src, c_src_pitch, c_dst_pitch, c_off);
     }
     return cudaGetLastError();
 }

@@ -10,6 +10,7 @@
 #include <cfloat>
 
 #include "kernels.h"
+#include "pdl.cuh"
 
 namespace smelter {
 namespace k {
@@ -25,28 +26,6 @@ inline int grid_for(size_t work_items, int per_block = kThreads) {
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return int(blocks);
-}
-
-// Programmatic dependent launch for the few non-conv kernels that sit between conv kernels of a model (stem pool, global average
-// pool): the kernel may be scheduled while its predecessor drains and tells its successor to do the same; it reads nothing
-// before griddepcontrol.wait.  Saves ~2 us per boundary against a plain stream-ordered launch.
-__device__ __forceinline__ void pdl_prologue() {
-    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
-    asm volatile("griddepcontrol.wait;" ::: "memory");
-}
-template <typename... KArgs, typename... Args>
-cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, cudaStream_t s, Args... args) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = grid;
-    cfg.blockDim = block;
-    cfg.dynamicSmemBytes = 0;
-    cfg.stream = s;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
 }
 
 struct alignas(16) Half8 {
@@ -83,6 +62,7 @@ __device__ __forceinline__ float act_op(float v, int act, float lo, float hi) {
 //      (count_include_pad=1, the MPS/PyTorch default the reference relies on, Converters.swift:609-616).
 __global__ void __launch_bounds__(kThreads) pool2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
                                                          int p, int q, int kh, int kw, int sh, int sw, int ph, int pw, int is_max) {
+    pdl_prologue();
     // grid.y walks output rows (image, op); threads walk (oq, channel group) of that row
     const int op = blockIdx.y % p;
     const int img = blockIdx.y / p;
@@ -220,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) pool_max3x3_rows2_kernel(const __hal
 // ---- global average pool: block = (n, 8-channel group chunk); threads split the pixels, shuffle + smem reduce.
 // grid = (cp8 groups, n); 256 threads over pixels.
 __global__ void __launch_bounds__(kThreads) global_avgpool_kernel(const __half* __restrict__ x, __half* __restrict__ y, int hw, int cp8) {
+    pdl_prologue();
     const int g = blockIdx.x;
     const int img = blockIdx.y;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -314,6 +295,7 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // one FFMA + one MUFU (ex2 of x * log2e - max * log2e), padded lanes are pushed to -65504 once so they contribute exp() = 0.
 __global__ void __launch_bounds__(kThreads, 4) softmax_vec_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int c, int cp,
                                                               int log_softmax) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const size_t warp = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
     const size_t nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
@@ -385,6 +367,7 @@ __global__ void __launch_bounds__(kThreads, 4) softmax_vec_kernel(const __half* 
 // ---- general fallback (rows longer than 1024 channels): one warp per row, three passes.
 __global__ void __launch_bounds__(kThreads) softmax_kernel(const __half* __restrict__ x, __half* __restrict__ y, size_t rows, int c, int cp,
                                                           int log_softmax) {
+    pdl_prologue();
     const int lane = threadIdx.x & 31;
     const size_t warp = (blockIdx.x * size_t(blockDim.x) + threadIdx.x) >> 5;
     const size_t nwarps = (size_t(gridDim.x) * blockDim.x) >> 5;
@@ -416,6 +399,7 @@ __global__ void __launch_bounds__(kThreads) softmax_kernel(const __half* __restr
 //      thread t owns channel group t % cp8 and pixel lane t / cp8.  Deterministic: fixed reduction order.
 __global__ void __launch_bounds__(kThreads) inorm_stats_kernel(const __half* __restrict__ x, float* __restrict__ partials, int hw, int cp8,
                                                               int splits) {
+    pdl_prologue();
     extern __shared__ float sm[];  // [lanes][cp8*8][2]
     const int split = blockIdx.x, img = blockIdx.y;
     const int lanes = blockDim.x / cp8;  // host guarantees cp8 <= blockDim.x
@@ -461,6 +445,7 @@ __global__ void __launch_bounds__(kThreads) inorm_stats_kernel(const __half* __r
 __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* __restrict__ partials, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ params, int hw, int cp, int splits,
                                                                  float eps, int group_size, int channels) {
+    pdl_prologue();
     const int img = blockIdx.x;
     for (int ch = threadIdx.x; ch < cp; ch += blockDim.x) {
         double a = 0.0, b = 0.0;
@@ -486,6 +471,7 @@ __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* _
 // pass 2: y = act(x * scale + shift)
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
                                                               int hw, int cp8, int act) {
+    pdl_prologue();
     const int img = blockIdx.y;
     const float* sm = params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
     // streaming part: block-tiled, eight 128-bit loads in flight per thread; when kThreads % cp8 == 0 a thread meets the same 8
@@ -585,7 +571,7 @@ cudaError_t pool2d(const __half* x, __half* y, int n, int h, int w, int cp, int 
         return launch_pdl(pool_max3x3_rows2_kernel<1>, grid2, dim3(kThreads), s, x, y, h, w, cp / 8, p, q, sw, ph, pw);
     }
     if (kh == 3 && kw == 3 && is_max) return launch_pdl(pool_max3x3_kernel, grid, dim3(kThreads), s, x, y, h, w, cp / 8, p, q, sh, sw, ph, pw);
-    else pool2d_kernel<<<grid, kThreads, 0, s>>>(x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
+    else (void)launch_pdl(pool2d_kernel, dim3(grid), dim3(kThreads), s, x, y, n, h, w, cp / 8, p, q, kh, kw, sh, sw, ph, pw, is_max);
     return cudaGetLastError();
 }
 
@@ -642,15 +628,15 @@ cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cu
         return launch_pdl(global_avgpool_team_kernel, dim3(unsigned(grid_for(teams * 8))), dim3(kThreads), s, x, y, n, hw, cp / 8);
     } else {
         dim3 grid(cp / 8, n);
-        global_avgpool_kernel<<<grid, kThreads, 0, s>>>(x, y, hw, cp / 8);
+        (void)launch_pdl(global_avgpool_kernel, dim3(grid), dim3(kThreads), s, x, y, hw, cp / 8);
     }
     return cudaGetLastError();
 }
 
 cudaError_t softmax_rows(const __half* x, __half* y, size_t rows, int c, int cp, int log_softmax, cudaStream_t s) {
-    if (cp <= 1024) softmax_vec_kernel<<<grid_for(rows * 32), kThreads, 0, s>>>(x, y, rows, c, cp, log_softmax);
+    if (cp <= 1024) (void)launch_pdl(softmax_vec_kernel, dim3(grid_for(rows * 32)), dim3(kThreads), s, x, y, rows, c, cp, log_softmax);
     else
-    softmax_kernel<<<grid_for(rows * 32), kThreads, 0, s>>>(x, y, rows, c, cp, log_softmax);
+    (void)launch_pdl(softmax_kernel, dim3(grid_for(rows * 32)), dim3(kThreads), s, x, y, rows, c, cp, log_softmax);
     return cudaGetLastError();
 }
 
@@ -697,15 +683,15 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         const __half* xg = x + size_t(i0) * n8 * 8;
         __half* yg = y + size_t(i0) * n8 * 8;
         float* pg = partials + size_t(i0) * splits * cp * 2;
-        inorm_stats_kernel<<<dim3(splits, gn), kThreads, smem1, s>>>(xg, pg, hw, cp8, splits);
+        (void)launch_pdl_smem(inorm_stats_kernel, dim3(dim3(splits, gn)), dim3(kThreads), smem1, s, xg, pg, hw, cp8, splits);
         cudaError_t e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         const int chunks = int(std::max<size_t>(1, (n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)));  // one block per 2048 vectors
         float* params = pg + size_t(gn) * splits * cp * 2;  // after this group's partials (see instance_norm_scratch_floats)
-        inorm_finalize_kernel<<<gn, kThreads, 0, s>>>(pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels);
+        (void)launch_pdl(inorm_finalize_kernel, dim3(gn), dim3(kThreads), s, pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        inorm_apply_kernel<<<dim3(chunks, gn), kThreads, 0, s>>>(xg, yg, params, hw, cp8, act);
+        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -30,7 +30,11 @@ CONV_CASES = [
     ("im2col_3x3_dil2", (1, 32, 20, 20), 32, 3, 1, 2, 2, 1, 0, True, False, 0),
     ("im2col_3x3_512_7", (2, 512, 7, 7), 512, 3, 1, 1, 1, 1, 1, True, True, 0),
     ("im2col_3x3_p0_128", (1, 128, 34, 34), 128, 3, 1, 0, 1, 1, 0, True, False, 0),
-    ("im2col_9x9_32_3", (1, 32, 40, 40), 3, 9, 1, 0, 1, 1, 0, True, False, 0),
+    ("im2col_9x9_32_3", (1, 32, 40, 40), 3, 9, 1, 0, 1, 1, 0, True, False, 2),
+    ("rows_9x9_32_3_p0", (1, 32, 40, 40), 3, 9, 1, 0, 1, 1, 0, True, False, 0),
+    ("rows_3x3_s2_c32_p0", (2, 32, 37, 41), 64, 3, 2, 0, 1, 1, 1, True, False, 0),
+    ("rows_5x5_c24_p0", (1, 24, 30, 30), 40, 5, 1, 0, 1, 1, 0, True, False, 0),
+    ("rows_3x3_c16_p0_res", (3, 16, 21, 21), 64, 3, 1, 0, 1, 1, 1, True, True, 0),
     ("im2col_as_1x1", (2, 64, 28, 28), 64, 1, 1, 0, 1, 1, 0, True, False, 2),
     ("rows_7x7_s2_stem", (2, 3, 224, 224), 64, 7, 2, 3, 1, 1, 1, True, False, 0),
     ("rows_3x3_s2_mbv2", (1, 3, 224, 224), 32, 3, 2, 1, 1, 1, 2, True, False, 0),

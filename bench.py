@@ -305,11 +305,12 @@ def run_native(args) -> int:
     if G % world:
         raise SystemExit(f"global batch {G} does not split over {world} ranks")
     B = G // world
-    # Small batches leave every layer latency-bound (a few tiles per SM between two kernel boundaries): the throughput graph is
-    # planned for half of the SMs (Configuration.smShare = 2) and three encodes are kept in flight, so two of them always co-run
-    # on disjoint halves of the chip.  Large per-GPU batches fill the chip by themselves: whole-chip kernels, two in flight.
-    share = args.sm_share or (2 if B <= 64 else 1)
-    S = max(1, args.in_flight or (3 if share >= 2 else 2))
+    # Every layer of the step is latency-bound (a few tiles per SM between two kernel boundaries, ~4 us of hand-over per launch): the
+    # throughput graph is planned for half of the SMs (Configuration.smShare = 2) and three encodes are kept in flight (four from 128
+    # images per GPU), so two of them always co-run on disjoint halves of the chip.  Measured per-GPU batch 16 / 32 / 64 / 128:
+    # 65.7 k / 73.3 k / 77.7 k / 78.2 k images/s against 50.6 k / 60.8 k / 74.4 k / 74.5 k with whole-chip kernels (profiles/r2_batch_share.txt).
+    share = args.sm_share or 2
+    S = max(1, args.in_flight or (4 if B >= 128 else 3))
     stream = torch.cuda.Stream(device=dev)
     ctx = Context(local_rank, stream=stream.cuda_stream)
     data = model_bytes()
@@ -416,8 +417,8 @@ def run_native(args) -> int:
             base_value = value
         else:
             k256 = max(20, min(K, 100))
-            full = Runner(torch, ctx, nns[1], dev, G, 201, 2)   # whole-chip plan, two in flight
-            base_value = G * k256 / (full.timed(k256, W, 2, barrier, max_over_ranks) * 1e-3)
+            full = Runner(torch, ctx, nns[2], dev, G, 201, 4)   # the same kind of plan as the sharded run: smShare 2, four in flight
+            base_value = G * k256 / (full.timed(k256, W, 4, barrier, max_over_ranks) * 1e-3)
         extra["strong_scaling"] = {"global_batch": G, "one_gpu_value": base_value, "efficiency_vs_one_gpu": value / (world * base_value),
                                    "note": "value / (N x the same global batch on one GPU, measured in this run)"}
         # shard parity: every rank holds the SAME seeded global batch, encodes its contiguous slice, rank 0 compares the gathered
@@ -536,9 +537,9 @@ def main() -> int:
     ap.add_argument("--batch", type=int, default=0, help="images per GPU per step (default: 32 on one GPU, 256 / N on N GPUs)")
     ap.add_argument("--global-batch", type=int, default=0, help="global batch split over the ranks (default: 32 for one GPU, 256 for N > 1)")
     ap.add_argument("--in-flight", type=int, default=0, help="encodes in flight per GPU, each on its own stream (1 = strictly one at a time; "
-                    "default: 3 with --sm-share 2 for per-GPU batches up to 64, else 2 on the whole chip)")
+                    "default: 3, or 4 from 128 images per GPU)")
     ap.add_argument("--sm-share", type=int, default=0, help="Configuration.smShare of the throughput graph: kernels sized for 1/k of the SMs so that "
-                    "encodes in flight co-run (default: see --in-flight)")
+                    "encodes in flight co-run (default 2)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[1] / configs[3] latency fields")
     args = ap.parse_args()

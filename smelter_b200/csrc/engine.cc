@@ -805,7 +805,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 add_step(std::string(group_size > 1 ? "group_norm " : "instance_norm ") + name,
                          [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels); }, 0,
                          io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)
-                plan->steps.back().launches = k::instance_norm_launches(N, is.h * is.w, icp);
+                plan->steps.back().launches = k::instance_norm_launches(N, is.h * is.w, icp, group_size);
                 break;
             }
             case FilterKind::Unary: {

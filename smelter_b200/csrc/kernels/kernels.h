@@ -51,7 +51,7 @@ cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int p
 // `partials` holds instance_norm_scratch_floats(n, hw, cp) floats.
 size_t instance_norm_scratch_floats(int n, int hw, int cp);
 int instance_norm_splits(int hw, int cp);
-int instance_norm_launches(int n, int hw, int cp);  // kernels instance_norm() enqueues (images go in L2-sized groups)
+int instance_norm_launches(int n, int hw, int cp, int group_size = 1);  // kernels instance_norm() enqueues: 1 (cluster form) or 3
 // group_size = channels that share one mean / variance: 1 = InstanceNormalization, C / groups = group normalisation
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
                           int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0);

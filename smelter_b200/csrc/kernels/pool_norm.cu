@@ -12,6 +12,8 @@
 #include "kernels.h"
 #include "pdl.cuh"
 
+#include <cooperative_groups.h>
+
 namespace smelter {
 namespace k {
 
@@ -512,6 +514,124 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
     }
 }
 
+// ---- instance norm in ONE launch (thread-block clusters + distributed shared memory).  A cluster of `csz` CTAs owns one
+//      (image, 16-channel slab): every CTA reduces sum / sum of squares over its share of the pixels, publishes them in shared memory,
+//      reads its peers' through the cluster window after one cluster barrier (fixed order: deterministic), and normalises its pixels,
+//      which it finds in L2 again.  Against the three-launch form (partials -> finalize -> apply) that is two kernel boundaries and the
+//      partial / parameter round trips less: the three passes of a 128 x 128 x 128 image took ~16 us, most of it hand-over latency.
+//      Thread t: vector (t & 1) of the slab (8 channels), pixel lane t >> 1; 32 contiguous bytes per pixel.
+__global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
+                                                                const float* __restrict__ beta, int hw, int cp8, float eps, int act, int group_size,
+                                                                int channels) {
+    pdl_prologue();
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int csz = int(cluster.num_blocks());
+    const int rank = int(cluster.block_rank());
+    const int slab = int(blockIdx.x) / csz, img = blockIdx.y;
+    const int g0 = slab * 2;
+    const int ng = min(2, cp8 - g0);
+    const int v = threadIdx.x & 1, pl = threadIdx.x >> 1;
+    constexpr int kLanes = kThreads / 2;
+    constexpr int kU = 8;
+    const int per = (hw + csz - 1) / csz;
+    const int p0 = rank * per, p1 = min(hw, p0 + per);
+    __shared__ float warp_part[kThreads / 32][2][8][2];
+    __shared__ double cta_part[2][8][2];
+    __shared__ float scsh[2][8][2];
+    const bool live = v < ng;
+    const __half* xb = x + (size_t(img) * hw * cp8 + g0 + v) * 8;
+    __half* yb = y + (size_t(img) * hw * cp8 + g0 + v) * 8;
+    float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+        for (int pix = p0 + pl; pix < p1; pix += kU * kLanes) {  // kU independent loads in flight per thread
+            Half8 t[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (pix + u * kLanes < p1) t[u] = ld8(xb + size_t(pix + u * kLanes) * cp8 * 8);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (pix + u * kLanes < p1) {
+                    float f[8];
+                    unpack(t[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) { s1[j] += f[j]; s2[j] += f[j] * f[j]; }
+                }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {  // lanes of equal parity hold the same channels
+#pragma unroll
+        for (int o = 2; o < 32; o <<= 1) {
+            s1[j] += __shfl_xor_sync(0xffffffffu, s1[j], o);
+            s2[j] += __shfl_xor_sync(0xffffffffu, s2[j], o);
+        }
+    }
+    const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane < 2) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { warp_part[wid][lane][j][0] = s1[j]; warp_part[wid][lane][j][1] = s2[j]; }
+    }
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        const int tv = threadIdx.x >> 4, tj = (threadIdx.x >> 1) & 7, tk = threadIdx.x & 1;
+        double a = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) a += double(warp_part[w][tv][tj][tk]);
+        cta_part[tv][tj][tk] = a;
+    }
+    cluster.sync();  // every CTA's partial sums are in its shared memory
+    if (threadIdx.x < 32) {
+        const int tv = threadIdx.x >> 4, tj = (threadIdx.x >> 1) & 7, tk = threadIdx.x & 1;
+        double a = 0.0;
+        for (int r = 0; r < csz; ++r) a += cluster.map_shared_rank(&cta_part[0][0][0], r)[(tv * 8 + tj) * 2 + tk];
+        // custom_group_norm: statistics pooled over the group_size channels of a group (Converters.swift:1273-1300).  group_size is a
+        // power of two <= 16 here (host check), groups are aligned in the slab, consecutive channels sit two lanes apart.
+        double pooled = a;
+        for (int o = 2; o < 2 * group_size; o <<= 1) pooled += __shfl_xor_sync(0xffffffffu, pooled, o);
+        const double a_other = __shfl_xor_sync(0xffffffffu, a, 1);       // tk == 0 lanes: the sum of squares next to their sum
+        const double p_other = __shfl_xor_sync(0xffffffffu, pooled, 1);
+        const int ch = (g0 + tv) * 8 + tj;
+        if (tk == 0 && tv < ng) {
+            const bool real = ch < channels;   // padding lanes of the channel pitch keep statistics of their own (all zero)
+            const int c_lo = real ? (ch / group_size) * group_size : ch;
+            const int c_hi = real ? min(c_lo + group_size, channels) : ch + 1;
+            const double cnt = double(hw) * (c_hi - c_lo);
+            const double mean = (real ? pooled : a) / cnt;
+            double var = (real ? p_other : a_other) / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = float(1.0 / sqrt(var + double(eps)));
+            const float sc = rstd * gamma[ch];
+            scsh[tv][tj][0] = sc;
+            scsh[tv][tj][1] = beta[ch] - float(mean) * sc;
+        }
+    }
+    cluster.sync();  // peers have read this CTA's partials (nobody exits early); scsh is visible to the CTA
+    if (live) {
+        float sc[8], sh[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { sc[j] = scsh[v][j][0]; sh[j] = scsh[v][j][1]; }
+        for (int pix = p0 + pl; pix < p1; pix += kU * kLanes) {
+            Half8 t[kU];
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (pix + u * kLanes < p1) t[u] = ld8(xb + size_t(pix + u * kLanes) * cp8 * 8);
+#pragma unroll
+            for (int u = 0; u < kU; ++u)
+                if (pix + u * kLanes < p1) {
+                    float f[8];
+                    unpack(t[u], f);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float r = fmaf(f[j], sc[j], sh[j]);
+                        f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
+                    }
+                    st8(yb + size_t(pix + u * kLanes) * cp8 * 8, pack(f));
+                }
+        }
+    }
+}
+
 // ---- depthwise conv: one thread per (output pixel, 8 channels); weights [kh*kw][cp].
 __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __restrict__ x, const __half* __restrict__ wt,
                                                             const float* __restrict__ bias, __half* __restrict__ y, int n, int h, int w,
@@ -656,7 +776,20 @@ int inorm_group(int n, int hw, int cp) {
     return n;
 }
 }  // namespace
-int instance_norm_launches(int n, int hw, int cp) {
+// One-launch cluster form (inorm_cluster_kernel): group statistics must pool inside a 16-channel slab, and a CTA's share of the
+// pixels (32 bytes each) should stay small enough to come back from L2 on the second pass.  Returns the cluster size, 0 = three-launch form.
+int inorm_cluster_size(int hw, int group_size) {
+    static const bool off = getenv("SMELTER_NO_CLUSTER_NORM") != nullptr;
+    if (off || group_size < 1 || group_size > 16 || (group_size & (group_size - 1))) return 0;
+    int csz = 8;
+    while (csz > 1 && hw / csz < 512) csz >>= 1;
+    // measured (TransformerNet, one image): 64 KiB per CTA (128 x 128 pixels) 16 -> 10 us against the three-launch form, but 256 KiB /
+    // 1 MiB per CTA (256^2, 512^2 pixels) 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches
+    if (size_t(hw) / csz * 32 > (size_t(128) << 10)) return 0;
+    return csz;
+}
+int instance_norm_launches(int n, int hw, int cp, int group_size) {
+    if (inorm_cluster_size(hw, group_size)) return 1;
     const int group = inorm_group(n, hw, cp);
     return 3 * ((n + group - 1) / group);
 }
@@ -670,6 +803,22 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
     if (channels <= 0) channels = cp;
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
+    if (const int csz = inorm_cluster_size(hw, group_size); csz > 0 && n <= 65535) {
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(unsigned((cp8 + 1) / 2 * csz), unsigned(n));
+        cfg.blockDim = dim3(kThreads);
+        cfg.stream = s;
+        cudaLaunchAttribute attr[2];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = unsigned(csz);
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 2;
+        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels);
+    }
     const int splits = instance_norm_splits(hw, cp);
     const int lanes = kThreads / cp8;
     const size_t smem1 = size_t(lanes) * cp * 2 * sizeof(float);

@@ -71,7 +71,26 @@ def ncu_conv_traffic():
         head = rows[0]
         ir, iw, ik = head.index("dram_read"), head.index("dram_write"), head.index("kernel")
         total = sum(float(r[ir]) + float(r[iw]) for r in rows[1:] if "conv_" in r[ik])
-        return total, os.path.relpath(path, ROOT) + " (committed capture of an earlier build of this command, not this run)"
+        return total, os.path.relpath(path, ROOT) + " (committed `ncu --set full` capture of one whole-chip encode of this workload: cold-cache replay, not this run)"
+    except (OSError, ValueError) as e:
+        return None, f"unreadable capture: {e}"
+
+
+def ncu_conv_traffic_warm():
+    """The same sum from the newest committed warm-cache pass (profiles/r*_dram_insitu.csv: `ncu --cache-control none`, kernels
+    serialised but caches left as the previous kernel left them -- what a kernel moves to and from DRAM inside the step)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_dram_insitu.csv")))
+    if not files:
+        return None, "no committed warm-cache capture"
+    try:
+        import csv
+        total = 0.0
+        with open(files[-1]) as f:
+            for row in csv.reader(line for line in f if not line.startswith("# ")):
+                if len(row) >= 5 and "conv_" in row[1]:
+                    total += float(row[2]) + float(row[3])
+        return total, os.path.relpath(files[-1], ROOT)
     except (OSError, ValueError) as e:
         return None, f"unreadable capture: {e}"
 
@@ -468,9 +487,10 @@ def run_native(args) -> int:
     pk = peaks()
     achieved = conv_flops / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else 0.0
     traffic, traffic_src = ncu_conv_traffic()
+    traffic_warm, traffic_warm_src = ncu_conv_traffic_warm()
     roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tflops_sustained"], "unit": "TFLOP/s", "frac": achieved / pk["tflops_sustained"],
                 "frac_of_burst_peak": achieved / pk["tflops_burst"], "burst_peak": pk["tflops_burst"],
-                "traffic": traffic, "traffic_source": traffic_src,
+                "traffic": traffic, "traffic_source": traffic_src, "traffic_warm_cache": traffic_warm, "traffic_warm_cache_source": traffic_warm_src,
                 "kernel": f"conv_pair_kernel / conv_igemm_kernel <BLOCK_N,HAS_RES> ({len(conv)} conv/gemm launches per step, aggregated; "
                           f"{sum('+conv1x1(' in p['desc'] for p in conv)} of them carry a folded 1x1 projection shortcut)",
                 "peak_source": f"{pk['source']} bf16 sustained (MEASURED_PEAKS.json); frac_of_burst_peak uses bf16_tflops", "kernel_share_of_step": conv_share,

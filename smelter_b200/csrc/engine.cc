@@ -780,6 +780,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 auto L = std::make_shared<k::ConvTcLaunch>();
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
+                L->balanced_grid = cfg_.sm_share >= 2 ? 1 : 0;
                 const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,

@@ -1019,6 +1019,7 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
     L->pair = want_pair ? 1 : 0;
     L->num_sms = num_sms;
+    L->balanced_grid = 0;
     if (!encode_b_map(&L->tm_b, q.w_packed, kc, taps, q.c_out, want_pair ? block_n / 2 : block_n, err)) return false;
     // ---- D (and the residual, same geometry): [M, out_pitch] fp16, stored / loaded as [32 rows x 64 cols] swizzled boxes ----
     for (int which = 0; which < 2; ++which) {

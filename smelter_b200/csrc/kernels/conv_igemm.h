@@ -96,6 +96,7 @@ struct ConvTcLaunch {
     int use_pdl;   // launch with programmatic stream serialization (the kernel calls griddepcontrol.wait itself)
     int pair;      // launched as conv_pair_kernel (two-CTA clusters): tm_b boxes hold BLOCK_N / 2 rows
     int num_sms;
+    int balanced_grid;  // conv_pair_launch: smallest grid that needs the same number of rounds (plans for a share of the chip)
     double flops;  // algorithmic: 2*M*Cout*Cin*R*S
 };
 

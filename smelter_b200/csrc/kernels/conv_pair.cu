@@ -511,7 +511,16 @@ cudaError_t conv_pair_set_attr(int block_n) {
 cudaError_t conv_pair_launch(const ConvTcLaunch& L, int num_sms, cudaStream_t stream) {
     const int pairs = (L.p.num_m_tiles + 1) / 2;
     const long items = long(pairs) * L.p.num_n_tiles;
-    const int grid = 2 * int(std::min<long>(items, num_sms / 2));
+    // Plans for a share of the chip (smShare): as many clusters as it takes to finish in the same number of rounds, not one more --
+    // 50 work items on 37 clusters need two rounds whether 37 or 25 clusters run them, and the SMs left alone are what a kernel of
+    // another encode in flight starts on (+0.8 % images/s with three in flight; a whole-chip plan alone loses 0.8 % by it, because
+    // clusters that finish early leave their L2 bandwidth to the rest).
+    long clusters = std::min<long>(items, num_sms / 2);
+    if (L.balanced_grid) {
+        const long rounds = (items + clusters - 1) / clusters;
+        clusters = (items + rounds - 1) / rounds;
+    }
+    const int grid = 2 * int(clusters);
     switch (L.block_n) {
         case 64: return launch_t<64>(L, grid, stream);
         case 128: return launch_t<128>(L, grid, stream);

@@ -84,6 +84,29 @@ def full(src: str, dst: str) -> None:
         print("not in report:", missing)
 
 
+def insitu(src: str, dst: str) -> None:
+    """`ncu --cache-control none --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --csv` log -> one row per
+    launch: kernels serialised but caches left warm, i.e. the DRAM bytes a kernel moves inside the step."""
+    txt = open(src).read()
+    rows = list(csv.DictReader(io.StringIO(txt[txt.index('"ID"'):])))
+    agg = {}
+    for r in rows:
+        agg.setdefault((int(r["ID"]), r["Kernel Name"]), {})[r["Metric Name"]] = (r["Metric Value"], r["Metric Unit"])
+    with open(dst, "w", newline="") as f:
+        f.write("# ncu --cache-control none --clock-control none: one whole-chip ResNet-50 batch-32 encode, kernels serialised, caches left warm\n")
+        w = csv.writer(f)
+        w.writerow(["#", "kernel", "dram_read_bytes", "dram_write_bytes", "dur_us"])
+        tr = tw = tt = 0.0
+        for (i, name), m in sorted(agg.items()):
+            rd = to_bytes(*m["dram__bytes_read.sum"])
+            wr = to_bytes(*m["dram__bytes_write.sum"])
+            us = to_us(*m["gpu__time_duration.sum"])
+            tr += rd; tw += wr; tt += us
+            w.writerow([i, short(name), int(rd), int(wr), round(us, 2)])
+        w.writerow(["total", "", int(tr), int(tw), round(tt, 2)])
+    print(f"{dst}: {len(agg)} launches, DRAM read {tr / 1e6:.1f} MB, written {tw / 1e6:.1f} MB")
+
+
 def launch_list(src: str, dst: str) -> None:
     with open(src) as f:
         lines = [l for l in f if not l.startswith("==")]
@@ -114,6 +137,9 @@ def launch_list(src: str, dst: str) -> None:
 
 
 if __name__ == "__main__":
+    if len(sys.argv) == 4 and sys.argv[1] == "insitu":
+        insitu(sys.argv[2], sys.argv[3])
+        sys.exit(0)
     if len(sys.argv) != 4 or sys.argv[1] not in ("full", "list"):
         sys.exit(__doc__)
     (full if sys.argv[1] == "full" else launch_list)(sys.argv[2], sys.argv[3])

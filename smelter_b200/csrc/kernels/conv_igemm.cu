@@ -761,18 +761,27 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms) {
     const bool pair_mode = q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"));
     if (pair_mode && !q.block_n && q.c_out > 64) {
         // Two-CTA clusters (conv_pair.cu): work items are (m-tile pair, n-tile) on num_sms / 2 clusters.  Per k-block a pair needs
-        // ~0.125 / 0.15 / 0.26 us for N = 64 / 128 / 256 (N = 256 is bound by its MMAs, the others by bytes in flight), the epilogue
-        // ~0.35 us per 64 columns; pick the width with the shortest span.
+        // ~0.125 / 0.15 / 0.26 us for N = 64 / 128 / 256 (N = 256 is bound by its MMAs, the others by operand delivery).  A [32 x 64]
+        // epilogue item costs a warp ~1 us; 64-column tiles alternate between the two epilogue groups (one tile per 0.5 us), wider ones
+        // are shared by both (1 us per 128 columns), and the last tile's epilogue is not hidden behind anything.  Checked against
+        // every layer of tools/conv_layers.py under SMELTER_FORCE_BN=64/128/256 (profiles/r2_force_bn_layers.txt): same ordering.
+        // That is the model for a plan that has the chip to itself (0.5248 -> 0.5185 ms per ResNet-50 step).  Plans for a share of the
+        // chip run next to other encodes' kernels and compete for L2 bandwidth; there the narrower tiles it prefers (more operand
+        // bytes per FLOP) lose 1.6 % images/s with three in flight, so share plans keep the first model: epilogue 0.35 us per 64
+        // columns, no tail term.
+        const bool alone = num_sms >= 120;
         const long pairs = (m_tiles + 1) / 2;
         double best_span = 1e30;
         const int cands[3] = {64, 128, 256};
         const double t_kb[3] = {0.125, 0.15, 0.26};
+        const double epi_rate[3] = {0.5, 1.0, 2.0}, epi_tail[3] = {1.0, 1.0, 2.0};
         for (int i = 0; i < 3; ++i) {
             const int bn = cands[i];
             if (bn / 2 >= q.c_out) continue;
             const long items = pairs * ((q.c_out + bn - 1) / bn);
             const long waves = (items + num_sms / 2 - 1) / (num_sms / 2);
-            const double span = double(waves) * std::max(num_kb * t_kb[i], 0.35 * (bn / 64));
+            const double span = alone ? double(waves) * std::max(num_kb * t_kb[i], epi_rate[i]) + epi_tail[i]
+                                      : double(waves) * std::max(num_kb * t_kb[i], 0.35 * (bn / 64));
             if (span < best_span * 0.97) { best_span = span; best.block_n = bn; }
         }
     }

@@ -779,7 +779,7 @@ int inorm_group(int n, int hw, int cp) {
 // One-launch cluster form (inorm_cluster_kernel): group statistics must pool inside a 16-channel slab, and a CTA's share of the
 // pixels (32 bytes each) should stay small enough to come back from L2 on the second pass.  Returns the cluster size, 0 = three-launch form.
 int inorm_cluster_size(int hw, int group_size) {
-    static const bool off = getenv("SMELTER_NO_CLUSTER_NORM") != nullptr;
+    const bool off = getenv("SMELTER_NO_CLUSTER_NORM") != nullptr;  // read on every call: tests switch it inside one process
     if (off || group_size < 1 || group_size > 16 || (group_size & (group_size - 1))) return 0;
     int csz = 8;
     while (csz > 1 && hw / csz < 512) csz >>= 1;

@@ -167,6 +167,33 @@ def test_instance_norm(ctx, shape, act):
     _close(y.toFloatArray(), ref, 4e-3)
 
 
+@pytest.mark.parametrize("shape,act", [((2, 128, 128, 128), 1), ((1, 24, 61, 47), 0), ((3, 40, 9, 200), 1), ((1, 32, 300, 300), 0)])
+def test_instance_norm_cluster_form_matches_three_launch_form(ctx, shape, act, monkeypatch):
+    """Small images take the one-launch cluster kernel (partial sums meet through distributed shared memory), large ones and
+    SMELTER_NO_CLUSTER_NORM=1 the partials -> finalize -> apply form: same statistics in a different fixed summation order, so the
+    outputs agree to fp16 rounding (and both with torch); each form is deterministic."""
+    from smelter_b200.api import run_elementwise
+
+    x = (_rand(shape, 21).astype(np.float32) * 3 - 0.25).astype(np.float16)
+    rng = np.random.default_rng(22)
+    g, b = rng.uniform(0.5, 1.5, shape[1]).astype(np.float32), rng.standard_normal(shape[1]).astype(np.float32)
+    ref = F.instance_norm(_t(x), weight=torch.from_numpy(g), bias=torch.from_numpy(b), eps=1e-5)
+    if act:
+        ref = ref.relu()
+
+    def run():
+        y, _ = run_elementwise(ctx, "instance_norm", _img(ctx, x), p0=g, p1=b, out_shape=shape, alpha=1e-5, act=act)
+        return y.toHalfArray()
+
+    one, again = run(), run()
+    assert np.array_equal(one.view(np.uint16), again.view(np.uint16))
+    _close(one.astype(np.float32), ref, 4e-3)
+    monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+    three = run()
+    _close(three.astype(np.float32), ref, 4e-3)
+    assert np.abs(one.astype(np.float32) - three.astype(np.float32)).max() <= 4e-3
+
+
 @pytest.mark.parametrize("shape", SHAPES + [(32, 3, 224, 224)])
 def test_layout_roundtrip_is_exact(ctx, shape):
     from smelter_b200.api import run_elementwise

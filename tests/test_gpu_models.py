@@ -157,6 +157,39 @@ def test_folded_projection_shortcut_on_ragged_tiles(ctx, monkeypatch, batch, hw)
     assert np.abs(out.reshape(want.shape) - want).max() <= TOL
 
 
+def test_sm_share_plans_and_encodes_in_flight(ctx):
+    """Configuration(smShare=2) sizes every kernel for half of the SMs so that encodes on different streams co-run.
+    The plan changes tile widths and grid sizes only: results stay within the tolerance of the oracle and within fp32
+    re-association of the whole-chip plan, and three encodes in flight on three streams (each with its own activation arena and
+    CUDA graph) give exactly what the same encodes give one at a time."""
+    import torch
+
+    from smelter_b200 import modelzoo, onnx2mps
+    from smelter_b200.api import Configuration, Image, ONNXGraph
+
+    model = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    rng = np.random.default_rng(9)
+    xs = [rng.random((8, 3, 224, 224), dtype=np.float32).astype(np.float16) for _ in range(3)]
+    whole = ONNXGraph(model, Configuration(smShare=1), context=ctx)
+    half = ONNXGraph(model, Configuration(smShare=2), context=ctx)
+    nn1, nn2 = whole.metalGraph(), half.metalGraph()
+    base = [nn1.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(8, 1000).copy() for x in xs]
+    serial = [nn2.encode(sourceImages=[Image.fromArray(ctx, x)]).toHalfArray().reshape(8, 1000).copy() for x in xs]
+    for a, b in zip(base, serial):
+        assert np.abs(a.astype(np.float32) - b.astype(np.float32)).max() <= 4e-3
+    assert np.abs(serial[0][:2].astype(np.float32) - _oracle(model, xs[0][:2])).max() <= TOL
+    streams = [torch.cuda.Stream() for _ in xs]
+    images = [Image.fromArray(ctx, x) for x in xs]
+    ctx.synchronize()
+    for _ in range(3):  # several rounds: plans are created on first use of a stream, later rounds replay their graphs concurrently
+        results = [nn2.encode(to=s.cuda_stream, sourceImages=[im]) for s, im in zip(streams, images)]
+        torch.cuda.synchronize()
+        for r, want in zip(results, serial):
+            assert np.array_equal(r.toHalfArray().reshape(8, 1000).view(np.uint16), want.view(np.uint16))
+    whole.close()
+    half.close()
+
+
 def test_mobilenet_v2_batch1(ctx):
     from smelter_b200 import modelzoo, onnx2mps
 

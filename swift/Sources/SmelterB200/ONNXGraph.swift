@@ -90,6 +90,9 @@ public final class ONNXGraph {
         public var inputConstraint: InputConstraint
         public var billinearUpsamplingConfiguration: BillinearUpsampling
         public var dims: [Int: Int]
+        /// Engine option (no reference counterpart, smelter_config.sm_share): k >= 2 sizes every kernel of the graph for 1/k of the
+        /// SMs so that encodes in flight on different streams co-run; 1 = whole chip.
+        public var smShare: Int32 = 1
         public init(inputConstraint: InputConstraint = .none, billinearUpsamplingConfiguration: BillinearUpsampling = .default, dims: [Int: Int] = [:]) {
             self.inputConstraint = inputConstraint
             self.billinearUpsamplingConfiguration = billinearUpsamplingConfiguration
@@ -142,6 +145,7 @@ public final class ONNXGraph {
             }
         }
         cfg.n_dims = n
+        cfg.sm_share = configuration.smShare
         var h: OpaquePointer?
         try data.withUnsafeBytes { bytes in
             try ONNXGraph.check(smelter_graph_create(context.handle, bytes.bindMemory(to: UInt8.self).baseAddress, bytes.count, &cfg, &h))

@@ -92,6 +92,10 @@ class Interpreter:
             if t == "Constant":
                 consts[n.output[0]] = a["value"].t.numpy()
                 continue
+            if t == "Identity" and n.input[0] not in env and (n.input[0] in self.inits or n.input[0] in consts):
+                # torch's exporter de-duplicates equal initializers (e.g. all-zero biases) through Identity nodes: an alias of a weight
+                self.inits[n.output[0]] = host(n.input[0])
+                continue
             x = env[n.input[0]]
             if t == "Conv":
                 w = self._conv_weight(n.input[1])

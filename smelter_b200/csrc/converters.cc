@@ -504,6 +504,9 @@ int convert_flatten(ONNXGraph& g, int ni) {  // :879-915 — axis attribute requ
 // at inference Dropout is the identity, which is what this engine does.  Identity is an extension.
 int convert_identity(ONNXGraph& g, int ni) {
     const NodeProto& node = g.node(ni);
+    // torch's exporter de-duplicates equal initializers (all-zero biases, ...) through Identity nodes: an alias of a weight tensor
+    if (node.op_type == "Identity" && !node.input.empty() && !node.output.empty() && g.output(node.input[0]) < 0)
+        if (const onnx::TensorProto* t = g.tensor(node.input[0])) { g.initTensor(node.output[0], t); return SMELTER_OK; }
     const int input = node.input.empty() ? -1 : g.output(node.input[0]);
     const ImageShape* s = node.input.empty() ? nullptr : g.shape(node.input[0]);
     if (input < 0 || !s) return err(SMELTER_ERR_NO_SUCH_OUTPUT, node, "input is not an image node");

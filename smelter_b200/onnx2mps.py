@@ -94,6 +94,23 @@ def tensor_infos_to_type(infos: List[op.ValueInfo], data_type) -> List[op.ValueI
             for v in infos]
 
 
+def resolve_initializer_aliases(model: op.Model) -> int:
+    """torch's exporter de-duplicates equal initializers (typically all-zero biases) through `Identity` nodes whose input is an
+    initializer.  Point every reader at the original tensor and drop those nodes, so that the weight swizzle below and the engine's
+    converters see plain initializers (onnx.optimizer's eliminate_identity does the same for the reference's script)."""
+    inits = model.initializers()
+    alias: Dict[str, str] = {}
+    kept = []
+    for n in model.graph.node:
+        if n.op_type == "Identity" and n.input and (n.input[0] in inits or n.input[0] in alias):
+            alias[n.output[0]] = alias.get(n.input[0], n.input[0])
+            continue
+        n.input = [alias.get(i, i) for i in n.input]
+        kept.append(n)
+    model.graph.node = kept
+    return len(alias)
+
+
 def model_to_mps(model: op.Model, data_type) -> op.Model:
     is_transpose: Dict[str, bool] = {}
     swizzle_plan: Dict[str, List[int]] = {}
@@ -147,6 +164,7 @@ def check_model(model: op.Model) -> None:
 
 def optimize_model(model: op.Model, data_type=np.float32) -> op.Model:
     check_model(model)          # ONNX2MPS.py:105
+    resolve_initializer_aliases(model)
     # strip_doc_string (:106): this codec never keeps doc strings, nothing to do
     fuse_bn_into_conv(model)    # :107
     return model_to_mps(model, data_type)  # :108

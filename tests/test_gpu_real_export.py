@@ -3,60 +3,32 @@ exported by torch's own (legacy, opset 9) ONNX exporter, taken through the ONNX2
 reader, built and run by the engine, and compared with the EAGER torch module in fp32.  This pins the parser (field order, packed /
 unpacked repeated fields, value_info clutter, doc strings of a real exporter), the BN fold, every converter on the path and the
 kernels against a writer and a model definition outside this repository.  Tolerance: 1e-2 max-abs relative to the logit range."""
-import io
-
 import numpy as np
 import pytest
 import torch
 
+from real_export import export as _export, torchvision_model
+
 pytestmark = pytest.mark.gpu
 
 
-def _export(module, x, **kw):
-    """torch's legacy exporter emits the bytes before its onnx-package hook; neutralise the hook."""
-    try:
-        from torch.onnx._internal.torchscript_exporter import onnx_proto_utils
-    except Exception:  # pragma: no cover
-        pytest.skip("torch exporter internals moved")
-    saved = onnx_proto_utils._add_onnxscript_fn
-    onnx_proto_utils._add_onnxscript_fn = lambda model_bytes, custom_opsets: model_bytes
-    try:
-        f = io.BytesIO()
-        torch.onnx.export(module, x, f, opset_version=9, dynamo=False, **kw)
-        return f.getvalue()
-    except Exception as e:  # pragma: no cover
-        pytest.skip(f"torch legacy exporter unavailable: {e}")
-    finally:
-        onnx_proto_utils._add_onnxscript_fn = saved
-
-
-def _randomise_norms(net):
-    """non-trivial BatchNorm statistics so that the fold is tested and activations stay O(1)."""
-    g = torch.Generator().manual_seed(123)
-    with torch.no_grad():
-        for m in net.modules():
-            if isinstance(m, torch.nn.BatchNorm2d):
-                m.running_mean.normal_(0, 0.1, generator=g)
-                m.running_var.uniform_(0.5, 1.5, generator=g)
-                m.weight.uniform_(0.5, 1.5, generator=g)
-                m.bias.normal_(0, 0.1, generator=g)
-
-
-@pytest.mark.parametrize("arch,fold_in_exporter", [("resnet50", False), ("resnet50", True), ("mobilenet_v2", False), ("resnet18", False)])
+# densenet121: BatchNorm in front of its convolution (un-fused scale/shift kernel), Concat, AveragePool, Pad; squeezenet1_1: Concat and
+# weights aliased through Identity nodes (the exporter de-duplicates equal initializers); googlenet: four-branch Concat, pools with
+# ceil_mode emulated by the exporter
+@pytest.mark.parametrize("arch,fold_in_exporter", [("resnet50", False), ("resnet50", True), ("mobilenet_v2", False), ("resnet18", False),
+                                                   ("resnet34", False), ("densenet121", False), ("squeezenet1_1", False), ("googlenet", False)])
 def test_torchvision_model_exported_by_torch_matches_eager(ctx, arch, fold_in_exporter):
-    torchvision = pytest.importorskip("torchvision")
     from smelter_b200 import onnx2mps
     from smelter_b200 import onnx_proto as op
     from smelter_b200.api import Format, Image, ONNXGraph
 
-    torch.manual_seed(0)
-    net = getattr(torchvision.models, arch)(weights=None).eval()
-    _randomise_norms(net)
+    net = torchvision_model(arch)
     x = torch.rand(2, 3, 224, 224, generator=torch.Generator().manual_seed(1)).half().float()
     # do_constant_folding=False keeps the BatchNormalization nodes for the ONNX2MPS fold; True lets the exporter fold them itself
     data = _export(net, x, do_constant_folding=fold_in_exporter)
     ops = {n.op_type for n in op.Model.parse(data).graph.node}
-    assert ("BatchNormalization" in ops) == (not fold_in_exporter)
+    if arch != "squeezenet1_1":  # no BatchNorm in SqueezeNet
+        assert ("BatchNormalization" in ops) == (not fold_in_exporter)
     mps = onnx2mps.convert_bytes(data, half=True)
     g = ONNXGraph(mps, context=ctx)
     assert g.modelFormat == Format.mpsFlavor

@@ -174,3 +174,25 @@ def test_conv_transpose_group_norm_pow_against_torch_modules():
     assert torch.allclose(got, want, atol=1e-5)
     got_mps = Interpreter(onnx2mps.convert_bytes(m.serialize(), half=False)).run(x)  # [1,2,3,0] swizzle + flip, fp32 kept
     assert torch.allclose(got_mps, want, atol=1e-5)
+
+
+@pytest.mark.parametrize("arch", ["squeezenet1_1", "densenet121", "googlenet"])
+def test_oracle_on_models_exported_by_torch(arch):
+    """The oracle against EAGER torchvision modules on files written by torch's own exporter (a writer and model definitions this
+    repository did not author): fp32 on the plain export, and within the fp16 tolerance after the ONNX2MPS restatement with --half.
+    squeezenet1_1 carries weights aliased through Identity nodes (the exporter de-duplicates equal initializers), densenet121
+    BatchNorms that no convolution precedes, Concat, AveragePool and Pad."""
+    from real_export import export, torchvision_model
+    from smelter_b200 import onnx2mps
+
+    net = torchvision_model(arch)
+    x = torch.rand(1, 3, 224, 224, generator=torch.Generator().manual_seed(1)).half().float()
+    data = export(net, x, do_constant_folding=False)
+    with torch.no_grad():
+        want = net(x)
+    scale = max(1.0, float(want.abs().max()))
+    got = Interpreter(data).run(x).reshape(want.shape)
+    assert float((got - want).abs().max()) <= 2e-3 * scale
+    mps = onnx2mps.convert_bytes(data, half=True)
+    got16 = Interpreter(mps).run(x).reshape(want.shape)
+    assert float((got16 - want).abs().max()) <= 1e-2 * scale

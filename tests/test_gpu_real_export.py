@@ -7,7 +7,7 @@ import numpy as np
 import pytest
 import torch
 
-from real_export import export as _export, torchvision_model
+from real_export import export as _export, torchvision_model, transformer_net
 
 pytestmark = pytest.mark.gpu
 
@@ -47,3 +47,24 @@ def test_torchvision_model_exported_by_torch_matches_eager(ctx, arch, fold_in_ex
     out2 = g2.metalGraph().encode(sourceImages=[Image.fromArray(ctx, x.numpy().astype(np.float16))]).toFloatArray().reshape(2, -1)
     g2.close()
     assert np.abs(out2 - want).max() <= 1e-2 * scale
+
+
+@pytest.mark.parametrize("hw,width", [(128, 16), (256, 32)])
+def test_transformer_net_exported_by_torch_matches_eager(ctx, hw, width):
+    """BASELINE.json configs[3] (reflection Pad + Conv + InstanceNorm + nearest Upsample + Add) from an eager module restated from
+    pytorch/examples and torch's own exporter, through ONNX2MPS --half and as the plain export, against the eager module."""
+    from smelter_b200 import onnx2mps
+    from smelter_b200.api import Image, ONNXGraph
+
+    net = transformer_net(width)
+    x = torch.rand(1, 3, hw, hw, generator=torch.Generator().manual_seed(2)).half().float()
+    data = _export(net, x, do_constant_folding=True)
+    with torch.no_grad():
+        want = net(x).numpy()
+    scale = max(1.0, float(np.abs(want).max()))
+    for model in (onnx2mps.convert_bytes(data, half=True), data):
+        g = ONNXGraph(model, context=ctx)
+        out = g.metalGraph().encode(sourceImages=[Image.fromArray(ctx, x.numpy().astype(np.float16))]).toFloatArray()
+        g.close()
+        assert out.shape == want.shape and np.isfinite(out).all()
+        assert np.abs(out - want).max() <= 1e-2 * scale, float(np.abs(out - want).max())

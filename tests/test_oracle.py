@@ -196,3 +196,22 @@ def test_oracle_on_models_exported_by_torch(arch):
     mps = onnx2mps.convert_bytes(data, half=True)
     got16 = Interpreter(mps).run(x).reshape(want.shape)
     assert float((got16 - want).abs().max()) <= 1e-2 * scale
+
+
+def test_oracle_on_transformer_net_exported_by_torch():
+    """BASELINE.json configs[3] from an eager module restated from pytorch/examples (tests/real_export.py) and torch's own exporter
+    (constant folding on: the Upsample scales arrive as a Constant, the only form the reference's UpsampleConverter reads)."""
+    from real_export import export, transformer_net
+    from smelter_b200 import onnx2mps
+
+    net = transformer_net(16)
+    x = torch.rand(1, 3, 64, 64, generator=torch.Generator().manual_seed(1)).half().float()
+    data = export(net, x, do_constant_folding=True)
+    assert modelzoo.count_ops(op.Model.parse(data)) == {"Pad": 16, "Conv": 16, "InstanceNormalization": 15, "Relu": 10, "Add": 5, "Constant": 2,
+                                                        "Upsample": 2}
+    with torch.no_grad():
+        want = net(x)
+    got = Interpreter(data).run(x).reshape(want.shape)
+    assert float((got - want).abs().max()) <= 1e-4
+    got16 = Interpreter(onnx2mps.convert_bytes(data, half=True)).run(x).reshape(want.shape)
+    assert float((got16 - want).abs().max()) <= 1e-2

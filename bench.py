@@ -192,13 +192,19 @@ def run_reference(args) -> int:
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
+    world = max(1, int(os.environ.get("WORLD_SIZE", args.gpus or 1)))
     base = cpu_reference(args.steps, args.warmup)
     line = {"impl": "reference", "metric": "ResNet-50 fp16 224x224 images/sec", "value": base["value"], "unit": "images/s", "n_gpus": args.gpus,
-            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "ResNet-50 224x224 batch=32 per GPU (BASELINE.json configs[2]); CPU arm runs a bounded sample per step",
-                       "onnx_graph": "seeded random ResNet-50 -> ONNX2MPS --half", "note": "reference = Swift + Apple MPS, not runnable here; "
-                       "this arm is the oracle port on host cores"},
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak" if world == 1 else "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            # the native arm's workload, graph and batch keys word for word (the keys that describe its GPU execution do not apply)
+            "config": {"workload": ("ResNet-50 fp16 224x224 batch=32 on one GPU (BASELINE.json configs[2])" if world == 1 else
+                                    f"ResNet-50 fp16 224x224 global batch={GLOBAL_BATCH} batch-sharded {GLOBAL_BATCH // world} per GPU over {world} GPU(s) "
+                                    "(BASELINE.json configs[4])"),
+                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half",
+                       "global_batch": PER_GPU_BATCH if world == 1 else GLOBAL_BATCH, "per_gpu_batch": PER_GPU_BATCH if world == 1 else GLOBAL_BATCH // world,
+                       "note": "reference = Swift + Apple MPS, not runnable here; this arm is the fp32 oracle port of the same graph on the host "
+                               "cores of rank 0, each step a bounded sample of the batch (cpu_baseline.sample)"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -514,7 +520,7 @@ def run_native(args) -> int:
             "data": "synthetic",
             "config": {"workload": ("ResNet-50 fp16 224x224 batch=32 on one GPU (BASELINE.json configs[2])" if world == 1 and G == PER_GPU_BATCH else
                                     f"ResNet-50 fp16 224x224 global batch={G} batch-sharded {B} per GPU over {world} GPU(s) (BASELINE.json configs[4])"),
-                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half -> libsmelter_b200", "global_batch": G,
+                       "onnx_graph": "seeded random ResNet-50 (53 Conv+BN) -> ONNX2MPS --half", "engine": "libsmelter_b200 (C ABI, ctypes)", "global_batch": G,
                        "per_gpu_batch": B, "parallelism": f"batch-sharded dp{world}, one NCCL weight broadcast, no steady-state collective",
                        "in_flight": S, "sm_share": share,
                        "in_flight_note": f"{S} encodes in flight per GPU, each on its own stream with its own activation arena "

@@ -88,6 +88,30 @@ void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch
         for (int ch = 0; ch < c_pitch; ++ch) dst[size_t(t) * c_pitch + ch] = ch < c ? onnx::float_to_half(w[size_t(ch) * taps + t]) : uint16_t(0);
 }
 
+// Phase-folded convolution (Filter::phase_fold): w is OHWI [co][R][S][c].  The folded problem has 4 * c_out output channels
+// (ey * 2 + ex) * c_out + co, ceil(R / 2) x ceil(S / 2) taps and 4 * cp input channels (dy * 2 + dx) * cp + c:
+//   W'[(ey, ex, co)][r2][s2][(dy, dx, c)] = w[co][2 * r2 + dy - ey][2 * s2 + dx - ex][c]   (zero outside the filter)
+void pack_weights_phase(const float* w, int c_out, int c_in, int k_h, int k_w, int cp, uint16_t* dst) {
+    const int r2n = (k_h + 1) / 2, s2n = (k_w + 1) / 2;
+    const size_t row = size_t(r2n) * s2n * 4 * cp;
+    for (size_t i = 0; i < size_t(4 * c_out) * row; ++i) dst[i] = 0;
+    for (int ey = 0; ey < 2; ++ey)
+        for (int ex = 0; ex < 2; ++ex)
+            for (int co = 0; co < c_out; ++co) {
+                uint16_t* d0 = dst + size_t((ey * 2 + ex) * c_out + co) * row;
+                for (int r2 = 0; r2 < r2n; ++r2)
+                    for (int s2 = 0; s2 < s2n; ++s2)
+                        for (int dy = 0; dy < 2; ++dy)
+                            for (int dx = 0; dx < 2; ++dx) {
+                                const int r = 2 * r2 + dy - ey, sx = 2 * s2 + dx - ex;
+                                if (r < 0 || r >= k_h || sx < 0 || sx >= k_w) continue;
+                                uint16_t* d = d0 + (size_t(r2) * s2n + s2) * 4 * cp + (dy * 2 + dx) * cp;
+                                const float* src = w + ((size_t(co) * k_h + r) * k_w + sx) * c_in;
+                                for (int c = 0; c < c_in; ++c) d[c] = onnx::float_to_half(src[c]);
+                            }
+            }
+}
+
 int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride_h, int stride_w, int dil_w, const int pads[4]) {
     if (groups != 1) {
         if (groups == c_in && groups == c_out) return 4;  // depthwise, multiplier 1 (Converters.swift:57)
@@ -360,6 +384,32 @@ int ONNXGraph::build() {
             f.s2d_h = hp; f.s2d_w = wp;
         }
     }
+    // Phase-folded output convolutions: a stride-1, unpadded k x k convolution (k odd >= 5) with at most 8 output channels and at
+    // most 32 input channels that produces the graph output and reads a Pad nobody else reads -- TransformerNet's 9x9 32 -> 3 layer,
+    // 81 half-empty k-blocks per tile as im2col, 45 as packed rows, all bound by the TMA's pixel-row rate with 3 useful GEMM columns.
+    // On the 2 x 2 space-to-depth fold of the padded image the four output phases of a folded pixel are 4 * c_out columns of one GEMM
+    // over ceil(k / 2)^2 taps of 4 * Cin dense channels: 50 k-blocks for a quarter of the rows (12.5 instead of 45 per output pixel).
+    if (!getenv("SMELTER_NO_PHASE_FOLD")) {
+        auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
+        for (auto& f : filters_) {
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.groups != 1 || f.residual >= 0) continue;
+            if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
+            if (f.k_h != f.k_w || f.k_h < 5 || !(f.k_h & 1) || f.c_out > 8 || round_up(f.c_in_g, 8) > 32 || round_up(f.c_in_g, 8) < 16) continue;
+            if (root_of(f.out) != root_of(output_value_)) continue;
+            Filter* pad = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.out == f.in[0] && g.kind == FilterKind::Pad) pad = &g;
+            if (!pad || consumers_of(pad->out) != 1) continue;
+            const ImageShape& ps = values_[size_t(pad->out)].shape;
+            const ImageShape& os = values_[size_t(f.out)].shape;
+            if ((ps.h | ps.w) & 1 || (os.h | os.w) & 1 || (os.h == 1 && os.w == 1)) continue;
+            f.phase_fold = true;
+            f.conv_mode = k::CONV_MODE_IM2COL;
+            pad->s2d_out = true;
+            std::vector<float> b4(size_t(4) * f.c_out);
+            for (int ph = 0; ph < 4; ++ph) for (int co = 0; co < f.c_out; ++co) b4[size_t(ph) * f.c_out + co] = f.bias[size_t(co)];
+            f.bias.swap(b4);
+        }
+    }
     rc = upload_weights();  // MPSNNGraph(device:resultImage:) pulls weights from the data sources (:185-190)
     if (rc) return fail(SMELTER_ERR_GRAPH_INTERNAL, "weight upload failed: " + last_error_string());
     built_ = true;
@@ -379,6 +429,7 @@ int ONNXGraph::upload_weights() {
             size_t wbytes;
             if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
             else if (f.s2d) wbytes = size_t(f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 16 * 2;
+            else if (f.phase_fold) wbytes = size_t(4 * f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 4 * round_up(c_in, 8) * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
             f.bias_off = total; total = align(total + size_t(round_up(f.c_out, 256)) * 4);
@@ -397,6 +448,7 @@ int ONNXGraph::upload_weights() {
             uint16_t* w = reinterpret_cast<uint16_t*>(host.data() + f.w_off);
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
             else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
+            else if (f.phase_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
         } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {
@@ -501,6 +553,11 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             q.h = (is.h - 1) * f.tr_stride_h + 1 + f.pads[0] + f.pads[2];
             q.w = (is.w - 1) * f.tr_stride_w + 1 + f.pads[1] + f.pads[3];
             q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.phase_fold) {  // the folded problem: [N, H/2, W/2, 4 Cin] -> [N, P/2, Q/2, 4 Cout], ceil(k/2)^2 taps
+            q.h = is.h / 2; q.w = is.w / 2;
+            q.c_in = 4 * round_up(is.c, 8); q.c_in_pitch = 4 * round_up(is.c, 8);
+            q.c_out = 4 * f.c_out; q.c_out_pitch = round_up(4 * f.c_out, 8);
+            q.k_h = (f.k_h + 1) / 2; q.k_w = (f.k_w + 1) / 2;
         } else if (f.s2d) {  // stride-1 convolution over the folded image the boundary conversion writes
             q.h = f.s2d_h / 2; q.w = f.s2d_w / 2;
             q.c_in_pitch = 16;
@@ -536,7 +593,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         if (f.out >= 0 && values_[size_t(f.out)].alias_of < 0) producer[size_t(f.out)] = int(fi);
     }
     auto plain_tc_conv = [&](const Filter& f) {
-        return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
+        return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && !f.phase_fold && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
     };
     if (!getenv("SMELTER_NO_SIDE")) {
         for (size_t fi = 0; fi < filters_.size(); ++fi) {
@@ -781,7 +838,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 L->balanced_grid = cfg_.sm_share >= 2 ? 1 : 0;
-                const char* mode_name = f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
+                const char* mode_name = f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops + side_flops,
@@ -881,8 +938,8 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             }
             case FilterKind::Pad: {
                 const Filter* fp = &f;
-                add_step("pad " + name, [=](cudaStream_t st) {
-                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st);
+                add_step(std::string(f.s2d_out ? "pad+s2d " : "pad ") + name, [=](cudaStream_t st) {
+                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st, fp->s2d_out ? 1 : 0);
                 }, 0, io_bytes);
                 break;
             }
@@ -901,6 +958,14 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         const __half* src = ptr_of(output_value_);
         const int cp = round_up(os.c, 8);
         const ImageShape o2 = os;
+        bool folded = false;  // produced by a phase-folded convolution: [N, H/2, W/2, 4 C] with the four phases as channel blocks
+        for (const Filter& pf : filters_) folded = folded || (!pf.removed && pf.phase_fold && root_of(pf.out) == out_root);
+        if (folded) {
+            const int cp4 = round_up(4 * os.c, 8);
+            add_step("phase_to_nchw " + values_[size_t(output_value_)].name,
+                     [=](cudaStream_t st) { return k::phase_to_nchw(src, dst, N, o2.c, o2.h / 2, o2.w / 2, cp4, long(o2.c) * o2.h * o2.w, st); }, 0,
+                     double(N) * o2.h * o2.w * o2.c * 2 + double(N) * (o2.h / 2) * (o2.w / 2) * cp4 * 2);
+        } else
         add_step("nhwc_to_nchw " + values_[size_t(output_value_)].name,
                  [=](cudaStream_t st) { return k::nhwc_to_nchw(src, dst, N, o2.c, o2.h, o2.w, cp, long(o2.c) * o2.h * o2.w, st); }, 0,
                  double(N) * o2.h * o2.w * (o2.c + cp) * 2);

@@ -106,6 +106,11 @@ struct Filter {
     bool transposed = false;
     int tr_stride_h = 1, tr_stride_w = 1, out_pad_h = 0, out_pad_w = 0;
     bool s2d = false;
+    // Narrow-output stride-1 convolution behind a Pad (TransformerNet's 9x9 32 -> 3 output layer): computed on the 2 x 2
+    // space-to-depth fold of its padded input, all four output phases of a folded pixel as 4 * c_out GEMM columns -- ceil(k / 2)^2
+    // taps of 4 * Cin dense channels instead of k^2 taps of Cin (engine.cc "phase-folded").  The Pad writes the fold (s2d_out).
+    bool phase_fold = false;
+    bool s2d_out = false;          // Pad: output in space-to-depth layout
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };
 

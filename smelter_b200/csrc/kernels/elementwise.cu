@@ -471,7 +471,7 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 
 // blockIdx.y = (image, output row): the source row is resolved once per block; threads walk (ox, channel group) of the row.
 __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
-                                                        int pt, int pl, int ho, int wo, int mode, float value) {
+                                                        int pt, int pl, int ho, int wo, int mode, float value, int s2d) {
     pdl_prologue();
     const int oy = blockIdx.y % ho;
     const int img = blockIdx.y / ho;
@@ -498,9 +498,44 @@ __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restric
         else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
         v[u] = inside ? ld8(xr + (size_t(sx) * cp8 + g) * 8) : fill;
     }
+    if (!s2d) {
 #pragma unroll
-    for (int u = 0; u < kUnroll; ++u)
-        if (base + u * kThreads < row_items) st8(yr + size_t(base + u * kThreads) * 8, v[u]);
+        for (int u = 0; u < kUnroll; ++u)
+            if (base + u * kThreads < row_items) st8(yr + size_t(base + u * kThreads) * 8, v[u]);
+        return;
+    }
+    // 2 x 2 space-to-depth output [n, ho / 2, wo / 2, 4 * cp]: padded pixel (oy, ox) is channel block (oy & 1) * 2 + (ox & 1) of folded
+    // pixel (oy / 2, ox / 2) -- the input layout of a phase-folded convolution (engine.cc, Filter::phase_fold)
+    __half* y2 = y + (size_t(img) * (ho >> 1) + (oy >> 1)) * size_t(wo >> 1) * (4 * cp8 * 8) + size_t(oy & 1) * 2 * cp8 * 8;
+#pragma unroll
+    for (int u = 0; u < kUnroll; ++u) {
+        const unsigned it = base + u * kThreads;
+        if (it >= row_items) break;
+        const unsigned ox = it / unsigned(cp8), g = it - ox * unsigned(cp8);
+        st8(y2 + (size_t(ox >> 1) * 4 * cp8 + size_t(ox & 1) * cp8 + g) * 8, v[u]);
+    }
+}
+
+// Result of a phase-folded convolution -> NCHW: src [n, p2, q2, cp] holds, per folded pixel, channel (ey * 2 + ex) * c + co = output
+// channel co of full-resolution pixel (2 * p2 + ey, 2 * q2 + ex).  One thread per folded pixel, q2 fastest: the two ex of a row are one
+// 32-bit store and neighbouring threads write neighbouring words.
+__global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c, int p2,
+                                                                int q2, int cp, long dst_image_pitch) {
+    pdl_prologue();
+    const size_t total = size_t(n) * p2 * q2;
+    const int q = 2 * q2;
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int x2 = int(i % q2);
+        const int y2 = int((i / q2) % p2);
+        const int img = int(i / (size_t(q2) * p2));
+        const __half* sp = src + i * cp;
+        __half* dp = dst + size_t(img) * dst_image_pitch;
+        for (int co = 0; co < c; ++co)
+            for (int ey = 0; ey < 2; ++ey) {
+                const __half2 v = __halves2half2(sp[(ey * 2 + 0) * c + co], sp[(ey * 2 + 1) * c + co]);
+                *reinterpret_cast<__half2*>(dp + (size_t(co) * (2 * p2) + 2 * y2 + ey) * q + 2 * x2) = v;
+            }
+    }
 }
 
 __global__ void __launch_bounds__(kThreads) concat_vec_kernel(const __half* __restrict__ src, __half* __restrict__ dst, size_t pixels,
@@ -645,6 +680,10 @@ cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, in
     (void)launch_pdl(nhwc_to_nchw_kernel, dim3(grid_for(size_t(n) * (cp / 8) * h * w)), dim3(kThreads), s, src, dst, n, c, h * w, cp, dst_image_pitch);
     return cudaGetLastError();
 }
+cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s) {
+    (void)launch_pdl(phase_to_nchw_kernel, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    return cudaGetLastError();
+}
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
                        cudaStream_t s) {
     const size_t total = size_t(n) * h * scale_h * w * scale_w * (cp / 8);
@@ -657,12 +696,13 @@ cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, 
     return cudaGetLastError();
 }
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
-                  cudaStream_t s) {
+                  cudaStream_t s, int s2d_out) {
     const int ho = h + pt + pb, wo = w + pl + pr;
+    if (s2d_out && ((ho | wo) & 1)) return cudaErrorInvalidValue;
     if (size_t(n) * ho > 65535) return cudaErrorInvalidValue;  // grid.y = (image, output row)
     const unsigned row_items = unsigned(wo) * unsigned(cp / 8);
     (void)launch_pdl(pad2d_kernel, dim3(dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho))), dim3(kThreads), s, x, y, n, h, w, cp / 8, pt, pl, ho, wo,
-                                                                                                                 mode, value);
+                                                                                                                 mode, value, s2d_out);
     return cudaGetLastError();
 }
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,

@@ -112,6 +112,28 @@ void pack_weights_phase(const float* w, int c_out, int c_in, int k_h, int k_w, i
             }
 }
 
+// Width-folded convolution (Filter::wfold = F): F horizontally neighbouring pixels are one pixel of F * cp channels (dx * cp + c), the F
+// outputs computed from a folded pixel are F * c_out GEMM columns (ex * c_out + co), the filter has ceil((k_w + F - 1) / F) horizontal taps:
+//   W'[(ex, co)][r][s2][(dx, c)] = w[co][r][F * s2 + dx - ex][c]   (zero outside the filter)
+void pack_weights_wfold(const float* w, int c_out, int c_in, int k_h, int k_w, int cp, int fold, uint16_t* dst) {
+    const int s2n = (k_w + 2 * fold - 2) / fold;
+    const size_t row = size_t(k_h) * s2n * fold * cp;
+    for (size_t i = 0; i < size_t(fold) * c_out * row; ++i) dst[i] = 0;
+    for (int ex = 0; ex < fold; ++ex)
+        for (int co = 0; co < c_out; ++co) {
+            uint16_t* d0 = dst + size_t(ex * c_out + co) * row;
+            for (int r = 0; r < k_h; ++r)
+                for (int s2 = 0; s2 < s2n; ++s2)
+                    for (int dx = 0; dx < fold; ++dx) {
+                        const int sx = fold * s2 + dx - ex;
+                        if (sx < 0 || sx >= k_w) continue;
+                        uint16_t* d = d0 + ((size_t(r) * s2n + s2) * fold + dx) * cp;
+                        const float* src = w + ((size_t(co) * k_h + r) * k_w + sx) * c_in;
+                        for (int c = 0; c < c_in; ++c) d[c] = onnx::float_to_half(src[c]);
+                    }
+        }
+}
+
 int pick_conv_mode(int c_in, int c_out, int groups, int k_h, int k_w, int stride_h, int stride_w, int dil_w, const int pads[4]) {
     if (groups != 1) {
         if (groups == c_in && groups == c_out) return 4;  // depthwise, multiplier 1 (Converters.swift:57)
@@ -410,6 +432,32 @@ int ONNXGraph::build() {
             f.bias.swap(b4);
         }
     }
+    // Width-folded input convolutions: a stride-1, unpadded convolution on at most 32 input channels whose packed filter rows leave
+    // most of every 128-byte TMA pixel row empty (9x9 on 3 channels: 18 k-blocks per 128 output pixels, 72 of 128 bytes used in one
+    // half of them and 16 in the other) reads and writes the SAME NHWC buffers re-interpreted with F = 64 / pitch neighbouring pixels
+    // as one: [H, W / F, 64] -> [P, Q / F, F * Cout], ceil((k_w + F - 1) / F) horizontal taps of 64 dense channels.  Pixel rows per output
+    // pixel: k_h * ceil(k_w * pitch / 64) -> k_h * taps / F (18 -> 2.25 for TransformerNet's input layer); the zero weights it multiplies
+    // cost tensor time the layer has to spare.  No kernel and no layout change: weights, bias and the problem's dimensions only.
+    if (!getenv("SMELTER_NO_WIDTH_FOLD")) {
+        for (auto& f : filters_) {
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.groups != 1 || f.residual >= 0) continue;
+            if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
+            const int cp = round_up(f.c_in_g, 8);
+            if (cp > 32 || f.k_w < 3 || f.c_out % 8) continue;
+            const int fold = 64 / cp;  // 8, 4 (pitch 16) or 2 (pitch 24 / 32: 48 / 64 channels per folded pixel)
+            const ImageShape& is = values_[size_t(f.in[0])].shape;
+            const ImageShape& os = values_[size_t(f.out)].shape;
+            if (round_up(is.c, 8) != cp || is.w % fold || os.w % fold || fold * f.c_out > 512) continue;
+            const int taps = (f.k_w + 2 * fold - 2) / fold;
+            const int rows_before = f.k_h * ((f.k_w * cp + 63) / 64) * fold, rows_after = f.k_h * taps * ((fold * cp + 63) / 64);
+            if (rows_after * 2 > rows_before) continue;  // worth it only with at least half of the pixel rows gone
+            f.wfold = fold;
+            f.conv_mode = k::CONV_MODE_IM2COL;
+            std::vector<float> bf(size_t(fold) * f.c_out);
+            for (int ex = 0; ex < fold; ++ex) for (int co = 0; co < f.c_out; ++co) bf[size_t(ex) * f.c_out + co] = f.bias[size_t(co)];
+            f.bias.swap(bf);
+        }
+    }
     rc = upload_weights();  // MPSNNGraph(device:resultImage:) pulls weights from the data sources (:185-190)
     if (rc) return fail(SMELTER_ERR_GRAPH_INTERNAL, "weight upload failed: " + last_error_string());
     built_ = true;
@@ -430,9 +478,10 @@ int ONNXGraph::upload_weights() {
             if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
             else if (f.s2d) wbytes = size_t(f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 16 * 2;
             else if (f.phase_fold) wbytes = size_t(4 * f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 4 * round_up(c_in, 8) * 2;
+            else if (f.wfold) wbytes = size_t(f.wfold) * f.c_out * f.k_h * ((f.k_w + 2 * f.wfold - 2) / f.wfold) * f.wfold * round_up(c_in, 8) * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
-            f.bias_off = total; total = align(total + size_t(round_up(f.c_out, 256)) * 4);
+            f.bias_off = total; total = align(total + size_t(round_up(std::max<int>(f.c_out, int(f.bias.size())), 256)) * 4);
         } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {
             const size_t n = size_t(round_up(int(f.p0.size()), 8)) * 4;
             f.p0_off = total; total = align(total + n);
@@ -449,6 +498,7 @@ int ONNXGraph::upload_weights() {
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
             else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
             else if (f.phase_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
+            else if (f.wfold) pack_weights_wfold(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), f.wfold, w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
         } else if (f.kind == FilterKind::BatchNorm || f.kind == FilterKind::InstanceNorm) {
@@ -553,6 +603,11 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             q.h = (is.h - 1) * f.tr_stride_h + 1 + f.pads[0] + f.pads[2];
             q.w = (is.w - 1) * f.tr_stride_w + 1 + f.pads[1] + f.pads[3];
             q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.wfold) {  // the same buffers with wfold neighbouring pixels as one: [N, H, W/F, F Cin] -> [N, P, Q/F, F Cout]
+            q.w = is.w / f.wfold;
+            q.c_in = f.wfold * round_up(is.c, 8); q.c_in_pitch = f.wfold * round_up(is.c, 8);
+            q.c_out = f.wfold * f.c_out; q.c_out_pitch = f.wfold * f.c_out;
+            q.k_w = (f.k_w + 2 * f.wfold - 2) / f.wfold;
         } else if (f.phase_fold) {  // the folded problem: [N, H/2, W/2, 4 Cin] -> [N, P/2, Q/2, 4 Cout], ceil(k/2)^2 taps
             q.h = is.h / 2; q.w = is.w / 2;
             q.c_in = 4 * round_up(is.c, 8); q.c_in_pitch = 4 * round_up(is.c, 8);
@@ -593,7 +648,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         if (f.out >= 0 && values_[size_t(f.out)].alias_of < 0) producer[size_t(f.out)] = int(fi);
     }
     auto plain_tc_conv = [&](const Filter& f) {
-        return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && !f.phase_fold && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
+        return f.kind == FilterKind::Conv && !f.is_gemm && !f.transposed && !f.s2d && !f.phase_fold && !f.wfold && (f.conv_mode == k::CONV_MODE_TILED || f.conv_mode == k::CONV_MODE_IM2COL);
     };
     if (!getenv("SMELTER_NO_SIDE")) {
         for (size_t fi = 0; fi < filters_.size(); ++fi) {
@@ -838,7 +893,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 L->balanced_grid = cfg_.sm_share >= 2 ? 1 : 0;
-                const char* mode_name = f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
+                const char* mode_name = f.wfold ? "im2col/width-fold" : f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops + side_flops,

@@ -110,6 +110,10 @@ struct Filter {
     // space-to-depth fold of its padded input, all four output phases of a folded pixel as 4 * c_out GEMM columns -- ceil(k / 2)^2
     // taps of 4 * Cin dense channels instead of k^2 taps of Cin (engine.cc "phase-folded").  The Pad writes the fold (s2d_out).
     bool phase_fold = false;
+    // Narrow-input stride-1 convolution without padding of its own (TransformerNet's 9x9 3 -> 32 input layer): `wfold` horizontally
+    // neighbouring pixels are one pixel of wfold x Cin channels -- a pure re-interpretation of the NHWC input and output buffers
+    // (engine.cc "width-folded"); 0 = not folded
+    int wfold = 0;
     bool s2d_out = false;          // Pad: output in space-to-depth layout
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };

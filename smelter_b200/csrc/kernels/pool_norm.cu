@@ -778,10 +778,13 @@ int inorm_group(int n, int hw, int cp) {
 }  // namespace
 // One-launch cluster form (inorm_cluster_kernel): group statistics must pool inside a 16-channel slab, and a CTA's share of the
 // pixels (32 bytes each) should stay small enough to come back from L2 on the second pass.  Returns the cluster size, 0 = three-launch form.
+// Largest cluster the device schedules for inorm_cluster_kernel: 16 CTAs (non-portable size, one cluster per GPC) where the driver
+// allows it, else the portable 8.  Asked once.
+int inorm_max_cluster();
 int inorm_cluster_size(int hw, int group_size) {
     const bool off = getenv("SMELTER_NO_CLUSTER_NORM") != nullptr;  // read on every call: tests switch it inside one process
     if (off || group_size < 1 || group_size > 16 || (group_size & (group_size - 1))) return 0;
-    int csz = 8;
+    int csz = inorm_max_cluster();
     while (csz > 1 && hw / csz < 512) csz >>= 1;
     // measured (TransformerNet, one image): 64 KiB per CTA (128 x 128 pixels) 16 -> 10 us against the three-launch form, but 256 KiB /
     // 1 MiB per CTA (256^2, 512^2 pixels) 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches
@@ -795,6 +798,27 @@ int instance_norm_launches(int n, int hw, int cp, int group_size) {
 }
 size_t instance_norm_scratch_floats(int n, int hw, int cp) {  // split partials + per-(image, channel) scale / shift
     return size_t(n) * instance_norm_splits(hw, cp) * cp * 2 + size_t(n) * cp * 2;
+}
+
+int inorm_max_cluster() {
+    static const int best = [] {
+        if (getenv("SMELTER_CLUSTER_NORM_8")) return 8;
+        if (cudaFuncSetAttribute(inorm_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) { cudaGetLastError(); return 8; }
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(16);
+        cfg.blockDim = dim3(kThreads);
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 16;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        int clusters = 0;
+        if (cudaOccupancyMaxActiveClusters(&clusters, inorm_cluster_kernel, &cfg) != cudaSuccess || clusters < 1) { cudaGetLastError(); return 8; }
+        return 16;
+    }();
+    return best;
 }
 
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,

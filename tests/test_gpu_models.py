@@ -407,3 +407,74 @@ def test_force_input_scale_resizes_sources(ctx, scale):
     assert np.abs(out - want).max() <= TOL
     with pytest.raises(Exception):  # without the constraint a mis-sized source is still unsupportedInput
         _run(ctx, model, x)
+
+
+@pytest.mark.parametrize("c_in,c_out,k,hw,pad_mode", [(3, 32, 9, (40, 56), "reflect"), (16, 24, 5, (21, 28), "edge"), (32, 64, 5, (18, 20), "reflect"),
+                                                      (20, 16, 3, (11, 34), "reflect"), (8, 40, 9, (26, 48), "reflect")])
+def test_width_folded_input_convolution(ctx, monkeypatch, c_in, c_out, k, hw, pad_mode):
+    """A narrow-input stride-1 convolution behind an explicit Pad runs on the width-folded view of its NHWC buffers (64 / pitch
+    neighbouring pixels as one; engine.cc "width-folded"; needs k_w - 1 and the width divisible by the fold factor): same result as the
+    plain packed-row form and the oracle, fold factors 8 / 4 / 2, a second convolution behind it so that the re-interpreted output is read as plain NHWC again."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c_in + k, name="wfold")
+    x = b.input("input", [2, c_in, h, w])
+    y = b.relu(b.conv(b.pad(x, k // 2, pad_mode), c_out, k, 1, 0))
+    y = b.conv(y, 8, 1)
+    b.output(y, [2, 8, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(k).standard_normal((2, c_in, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+        dump = nn.planDump(2)
+        g.close()
+        return out, dump
+
+    out, dump = run()
+    assert "width-fold" in dump
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_WIDTH_FOLD", "1")
+    plain, dump0 = run()
+    assert "width-fold" not in dump0
+    assert np.abs(out - plain).max() <= 4e-3 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("c_in,c_out,k,hw", [(32, 3, 9, (24, 40)), (16, 8, 5, (30, 18)), (24, 1, 7, (16, 16))])
+def test_phase_folded_output_convolution(ctx, monkeypatch, c_in, c_out, k, hw):
+    """A narrow-output stride-1 convolution that produces the graph output behind a Pad runs on the 2 x 2 space-to-depth fold of its
+    padded input with the four output phases as GEMM columns (engine.cc "phase-folded"): the Pad writes the fold, the final
+    conversion un-folds; same result as the unfolded plan and the oracle."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c_in + k, name="pfold")
+    x = b.input("input", [2, c_in, h, w])
+    y = b.conv(b.pad(b.relu(b.conv(x, c_in, 1)), k // 2, "reflect"), c_out, k, 1, 0)
+    b.output(y, [2, c_out, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(k).standard_normal((2, c_in, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+        dump = nn.planDump(2)
+        g.close()
+        return out, dump
+
+    out, dump = run()
+    assert "phase-fold" in dump and "pad+s2d" in dump and "phase_to_nchw" in dump
+    assert out.shape == want.shape
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_PHASE_FOLD", "1")
+    plain, dump0 = run()
+    assert "phase-fold" not in dump0
+    assert np.abs(out - plain).max() <= 4e-3 * max(1.0, np.abs(want).max())

@@ -442,32 +442,45 @@ __global__ void __launch_bounds__(kThreads) inorm_stats_kernel(const __half* __r
     }
 }
 // pass 1b: per (image, channel) scale = rstd * gamma and shift = beta - mean * scale from the split partials, once (one block per
-// image; fixed summation order, fp64).  It used to be recomputed by every block of pass 2 -- a serial 256-step fp64 chain per block,
-// which was most of that kernel's time (ncu: 182 us for the 16 x 32 x 512 x 512 case against 48 us for pass 1).
+// image; fixed summation order, fp64).  `parts` lanes of a warp share a channel: each sums every parts-th split, a shuffle tree adds
+// them up -- with one thread per channel walking all 256 splits of a 512 x 512 image serially this kernel took 26 us (ncu), four times
+// the statistics and apply passes next to it.  (It used to be recomputed by every block of pass 2 before that.)
 __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* __restrict__ partials, const float* __restrict__ gamma,
                                                                  const float* __restrict__ beta, float* __restrict__ params, int hw, int cp, int splits,
-                                                                 float eps, int group_size, int channels) {
+                                                                 float eps, int group_size, int channels, int parts) {
     pdl_prologue();
     const int img = blockIdx.x;
-    for (int ch = threadIdx.x; ch < cp; ch += blockDim.x) {
+    const int part = threadIdx.x % parts;
+    const int per_pass = blockDim.x / parts;
+    for (int ch0 = 0; ch0 < cp; ch0 += per_pass) {  // every thread of the block takes part in every pass (warp shuffles below)
+        const int ch = ch0 + threadIdx.x / parts;
         double a = 0.0, b = 0.0;
         // statistics are shared by the `group_size` channels of ch's group (custom_group_norm, Converters.swift:1273-1300);
         // group_size == 1 is InstanceNormalization
-        const int c_lo = ch < channels ? (ch / group_size) * group_size : ch;
-        const int c_hi = ch < channels ? min(c_lo + group_size, channels) : ch + 1;
-        for (int cc = c_lo; cc < c_hi; ++cc)
-            for (int sp = 0; sp < splits; ++sp) {
-                const float* o = partials + ((size_t(img) * splits + sp) * cp + cc) * 2;
-                a += o[0]; b += o[1];
-            }
-        const double cnt = double(hw) * (c_hi - c_lo);
-        const double mean = a / cnt;
-        double var = b / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        const float rstd = float(1.0 / sqrt(var + double(eps)));
-        const float sc = rstd * gamma[ch];
-        params[(size_t(img) * cp + ch) * 2] = sc;
-        params[(size_t(img) * cp + ch) * 2 + 1] = beta[ch] - float(mean) * sc;
+        int c_lo = 0, c_hi = 0;
+        if (ch < cp) {
+            c_lo = ch < channels ? (ch / group_size) * group_size : ch;
+            c_hi = ch < channels ? min(c_lo + group_size, channels) : ch + 1;
+            for (int cc = c_lo; cc < c_hi; ++cc)
+                for (int sp = part; sp < splits; sp += parts) {
+                    const float* o = partials + ((size_t(img) * splits + sp) * cp + cc) * 2;
+                    a += o[0]; b += o[1];
+                }
+        }
+        for (int o = 1; o < parts; o <<= 1) {
+            a += __shfl_xor_sync(0xffffffffu, a, o);
+            b += __shfl_xor_sync(0xffffffffu, b, o);
+        }
+        if (ch < cp && part == 0) {
+            const double cnt = double(hw) * (c_hi - c_lo);
+            const double mean = a / cnt;
+            double var = b / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            const float rstd = float(1.0 / sqrt(var + double(eps)));
+            const float sc = rstd * gamma[ch];
+            params[(size_t(img) * cp + ch) * 2] = sc;
+            params[(size_t(img) * cp + ch) * 2 + 1] = beta[ch] - float(mean) * sc;
+        }
     }
 }
 // pass 2: y = act(x * scale + shift)
@@ -861,7 +874,9 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         if (e != cudaSuccess) return e;
         const int chunks = int(std::max<size_t>(1, (n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)));  // one block per 2048 vectors
         float* params = pg + size_t(gn) * splits * cp * 2;  // after this group's partials (see instance_norm_scratch_floats)
-        (void)launch_pdl(inorm_finalize_kernel, dim3(gn), dim3(kThreads), s, pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels);
+        int parts = 1;  // lanes per channel: a power of two, at most a warp, no more than the splits there are
+        while (parts < 32 && parts * 2 <= splits && cp * parts * 2 <= kThreads * 4) parts <<= 1;
+        (void)launch_pdl(inorm_finalize_kernel, dim3(gn), dim3(kThreads), s, pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels, parts);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
         (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act);

@@ -462,9 +462,15 @@ __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* _
             c_lo = ch < channels ? (ch / group_size) * group_size : ch;
             c_hi = ch < channels ? min(c_lo + group_size, channels) : ch + 1;
             for (int cc = c_lo; cc < c_hi; ++cc)
-                for (int sp = part; sp < splits; sp += parts) {
-                    const float* o = partials + ((size_t(img) * splits + sp) * cp + cc) * 2;
-                    a += o[0]; b += o[1];
+                for (int sp0 = part; sp0 < splits; sp0 += 8 * parts) {  // eight independent loads in flight, then the adds (fixed order)
+                    float2 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int sp = sp0 + u * parts;
+                        v[u] = sp < splits ? __ldg(reinterpret_cast<const float2*>(partials + ((size_t(img) * splits + sp) * cp + cc) * 2)) : make_float2(0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) { a += v[u].x; b += v[u].y; }
                 }
         }
         for (int o = 1; o < parts; o <<= 1) {
@@ -596,8 +602,14 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
     cluster.sync();  // every CTA's partial sums are in its shared memory
     if (threadIdx.x < 32) {
         const int tv = threadIdx.x >> 4, tj = (threadIdx.x >> 1) & 7, tk = threadIdx.x & 1;
+        // all peers' values are requested before any is added: a dependent chain of distributed-shared-memory round trips (one per
+        // peer) was most of this kernel's time
+        double pv[16];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) pv[r] = r < csz ? cluster.map_shared_rank(&cta_part[0][0][0], r)[(tv * 8 + tj) * 2 + tk] : 0.0;
         double a = 0.0;
-        for (int r = 0; r < csz; ++r) a += cluster.map_shared_rank(&cta_part[0][0][0], r)[(tv * 8 + tj) * 2 + tk];
+#pragma unroll
+        for (int r = 0; r < 16; ++r) a += pv[r];
         // custom_group_norm: statistics pooled over the group_size channels of a group (Converters.swift:1273-1300).  group_size is a
         // power of two <= 16 here (host check), groups are aligned in the slab, consecutive channels sit two lanes apart.
         double pooled = a;

@@ -674,6 +674,29 @@ __global__ void __launch_bounds__(kThreads) depthwise_kernel(const __half* __res
         float acc[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc[j] = __ldg(bias + g * 8 + j);
+        if (kh == 3 && kw == 3) {
+            // the 3 x 3 case (every MobileNetV2 layer): all nine input vectors and nine weight vectors are requested before the first
+            // multiply -- with the loads inside the tap loop they were nine dependent L2 round trips, ~5 us for a kernel that moves a
+            // few hundred KB (batch 1: as long as the tensor-core convolutions around it)
+            Half8 xv[9], wv9[9];
+            bool ok[9];
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+                const int iy = op * sh - pt + (t / 3) * dh, ix = oq * sw - pl + (t % 3) * dw;
+                ok[t] = iy >= 0 && iy < h && ix >= 0 && ix < w;
+                if (ok[t]) xv[t] = ld8(x + (((size_t(img) * h + iy) * w + ix) * cp8 + g) * 8);
+                wv9[t] = ld8(wt + (size_t(t) * cp8 + g) * 8);
+            }
+#pragma unroll
+            for (int t = 0; t < 9; ++t)
+                if (ok[t]) {
+                    float f[8], wf[8];
+                    unpack(xv[t], f);
+                    unpack(wv9[t], wf);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) acc[j] = fmaf(f[j], wf[j], acc[j]);
+                }
+        } else
         for (int r = 0; r < kh; ++r) {
             const int iy = op * sh - pt + r * dh;
             if (iy < 0 || iy >= h) continue;

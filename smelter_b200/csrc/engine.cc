@@ -88,27 +88,51 @@ void pack_weights_depthwise(const float* w, int c, int k_h, int k_w, int c_pitch
         for (int ch = 0; ch < c_pitch; ++ch) dst[size_t(t) * c_pitch + ch] = ch < c ? onnx::float_to_half(w[size_t(ch) * taps + t]) : uint16_t(0);
 }
 
-// Phase-folded convolution (Filter::phase_fold): w is OHWI [co][R][S][c].  The folded problem has 4 * c_out output channels
-// (ey * 2 + ex) * c_out + co, ceil(R / 2) x ceil(S / 2) taps and 4 * cp input channels (dy * 2 + dx) * cp + c:
-//   W'[(ey, ex, co)][r2][s2][(dy, dx, c)] = w[co][2 * r2 + dy - ey][2 * s2 + dx - ex][c]   (zero outside the filter)
-void pack_weights_phase(const float* w, int c_out, int c_in, int k_h, int k_w, int cp, uint16_t* dst) {
-    const int r2n = (k_h + 1) / 2, s2n = (k_w + 1) / 2;
-    const size_t row = size_t(r2n) * s2n * 4 * cp;
-    for (size_t i = 0; i < size_t(4 * c_out) * row; ++i) dst[i] = 0;
-    for (int ey = 0; ey < 2; ++ey)
-        for (int ex = 0; ex < 2; ++ex)
+// Phase-folded convolution (Filter::phase_fold = F, 2 or 4): w is OHWI [co][R][S][c].  The folded problem has F^2 * c_out output
+// channels (ey * F + ex) * c_out + co, taps(R) x taps(S) taps with taps(k) = (k + 2F - 2) / F, and F^2 * cp input channels
+// (dy * F + dx) * cp + c:
+//   W'[(ey, ex, co)][r2][s2][(dy, dx, c)] = w[co][F * r2 + dy - ey][F * s2 + dx - ex][c]   (zero outside the filter)
+void pack_weights_phase(const float* w, int c_out, int c_in, int k_h, int k_w, int cp, int fold, uint16_t* dst) {
+    const int r2n = (k_h + 2 * fold - 2) / fold, s2n = (k_w + 2 * fold - 2) / fold, ff = fold * fold;
+    const size_t row = size_t(r2n) * s2n * ff * cp;
+    for (size_t i = 0; i < size_t(ff * c_out) * row; ++i) dst[i] = 0;
+    for (int ey = 0; ey < fold; ++ey)
+        for (int ex = 0; ex < fold; ++ex)
             for (int co = 0; co < c_out; ++co) {
-                uint16_t* d0 = dst + size_t((ey * 2 + ex) * c_out + co) * row;
+                uint16_t* d0 = dst + size_t((ey * fold + ex) * c_out + co) * row;
                 for (int r2 = 0; r2 < r2n; ++r2)
                     for (int s2 = 0; s2 < s2n; ++s2)
-                        for (int dy = 0; dy < 2; ++dy)
-                            for (int dx = 0; dx < 2; ++dx) {
-                                const int r = 2 * r2 + dy - ey, sx = 2 * s2 + dx - ex;
+                        for (int dy = 0; dy < fold; ++dy)
+                            for (int dx = 0; dx < fold; ++dx) {
+                                const int r = fold * r2 + dy - ey, sx = fold * s2 + dx - ex;
                                 if (r < 0 || r >= k_h || sx < 0 || sx >= k_w) continue;
-                                uint16_t* d = d0 + (size_t(r2) * s2n + s2) * 4 * cp + (dy * 2 + dx) * cp;
+                                uint16_t* d = d0 + (size_t(r2) * s2n + s2) * ff * cp + (dy * fold + dx) * cp;
                                 const float* src = w + ((size_t(co) * k_h + r) * k_w + sx) * c_in;
                                 for (int c = 0; c < c_in; ++c) d[c] = onnx::float_to_half(src[c]);
                             }
+            }
+}
+
+// Upsample-folded convolution (Filter::upfold): w is OHWI [co][3][3][c] of a 3x3 convolution that reads the reflect-padded (1) nearest
+// x2 upsampling of an image.  Output pixel (2y + ey, 2x + ex) reads upsampled rows 2y + ey + r - 1, i.e. low-resolution rows
+// y + floor((ey + r - 1) / 2): tap r of phase ey lands on tap (ey + r + 1) / 2 of a 3x3 filter over the edge-padded (1) low-resolution
+// image (reflection of the upsampled border row -1 is row 1 = low-resolution row 0 = edge padding).  Taps that meet are summed in fp32:
+//   W'[(ey, ex, co)][r'][s'][c] = sum over r, s with (ey + r + 1) / 2 == r', (ex + s + 1) / 2 == s' of w[co][r][s][c]
+void pack_weights_upfold(const float* w, int c_out, int c_in, int cp, uint16_t* dst) {
+    const size_t row = size_t(9) * cp;
+    std::vector<float> acc(row);
+    for (int ey = 0; ey < 2; ++ey)
+        for (int ex = 0; ex < 2; ++ex)
+            for (int co = 0; co < c_out; ++co) {
+                std::fill(acc.begin(), acc.end(), 0.f);
+                for (int r = 0; r < 3; ++r)
+                    for (int sx = 0; sx < 3; ++sx) {
+                        float* d = acc.data() + (size_t((ey + r + 1) / 2) * 3 + (ex + sx + 1) / 2) * cp;
+                        const float* src = w + ((size_t(co) * 3 + r) * 3 + sx) * c_in;
+                        for (int c = 0; c < c_in; ++c) d[c] += src[c];
+                    }
+                uint16_t* d0 = dst + size_t((ey * 2 + ex) * c_out + co) * row;
+                for (size_t i = 0; i < row; ++i) d0[i] = onnx::float_to_half(acc[i]);
             }
 }
 
@@ -406,6 +430,43 @@ int ONNXGraph::build() {
             f.s2d_h = hp; f.s2d_w = wp;
         }
     }
+    // Upsample-folded convolutions (Filter::upfold, engine.h): nearest Upsample x2 -> reflect Pad 1 -> Conv 3x3 -> InstanceNorm with
+    // single readers all along.  The Upsample goes, the Pad becomes an edge pad of the low-resolution image, the convolution gets
+    // 4 * Cout phase columns, the normalisation un-permutes its pixels on the way out.
+    if (!getenv("SMELTER_NO_UPSAMPLE_FOLD")) {
+        auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
+        auto producer_of = [&](int v) -> Filter* {
+            for (auto& g : filters_) if (!g.removed && g.out >= 0 && root_of(g.out) == root_of(v)) return &g;
+            return nullptr;
+        };
+        for (auto& f : filters_) {
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.groups != 1 || f.residual >= 0) continue;
+            if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
+            if (f.k_h != 3 || f.k_w != 3 || f.c_out % 8 || 4 * f.c_out > 1024 || f.c_in_g < 16) continue;
+            if (root_of(f.out) == root_of(output_value_) || consumers_of(f.out) != 1) continue;
+            Filter* pad = producer_of(f.in[0]);
+            if (!pad || pad->kind != FilterKind::Pad || pad->sub != k::PAD_REFLECT || consumers_of(pad->out) != 1) continue;
+            if (pad->pads[0] != 1 || pad->pads[1] != 1 || pad->pads[2] != 1 || pad->pads[3] != 1) continue;
+            Filter* up = producer_of(pad->in[0]);
+            if (!up || up->kind != FilterKind::Upsample || up->sub != k::UP_NEAREST || up->scale_h != 2 || up->scale_w != 2 || consumers_of(up->out) != 1) continue;
+            if (root_of(up->out) == root_of(output_value_) || root_of(pad->out) == root_of(output_value_)) continue;
+            Filter* norm = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.kind == FilterKind::InstanceNorm && !g.in.empty() && root_of(g.in[0]) == root_of(f.out)) norm = &g;
+            if (!norm) continue;
+            const ImageShape low = values_[size_t(up->in[0])].shape;
+            if (low.h < 2 || low.w < 2) continue;
+            up->removed = true;
+            pad->in[0] = up->in[0];
+            pad->sub = k::PAD_EDGE;
+            values_[size_t(pad->out)].shape.h = low.h + 2;
+            values_[size_t(pad->out)].shape.w = low.w + 2;
+            f.upfold = true;
+            norm->unfold_w = low.w;
+            std::vector<float> b4(size_t(4) * f.c_out);
+            for (int ph = 0; ph < 4; ++ph) for (int co = 0; co < f.c_out; ++co) b4[size_t(ph) * f.c_out + co] = f.bias[size_t(co)];
+            f.bias.swap(b4);
+        }
+    }
     // Phase-folded output convolutions: a stride-1, unpadded k x k convolution (k odd >= 5) with at most 8 output channels and at
     // most 32 input channels that produces the graph output and reads a Pad nobody else reads -- TransformerNet's 9x9 32 -> 3 layer,
     // 81 half-empty k-blocks per tile as im2col, 45 as packed rows, all bound by the TMA's pixel-row rate with 3 useful GEMM columns.
@@ -414,7 +475,7 @@ int ONNXGraph::build() {
     if (!getenv("SMELTER_NO_PHASE_FOLD")) {
         auto root_of = [&](int v) { while (values_[size_t(v)].alias_of >= 0) v = values_[size_t(v)].alias_of; return v; };
         for (auto& f : filters_) {
-            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.groups != 1 || f.residual >= 0) continue;
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.upfold || f.groups != 1 || f.residual >= 0) continue;
             if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
             if (f.k_h != f.k_w || f.k_h < 5 || !(f.k_h & 1) || f.c_out > 8 || round_up(f.c_in_g, 8) > 32 || round_up(f.c_in_g, 8) < 16) continue;
             if (root_of(f.out) != root_of(output_value_)) continue;
@@ -424,11 +485,15 @@ int ONNXGraph::build() {
             const ImageShape& ps = values_[size_t(pad->out)].shape;
             const ImageShape& os = values_[size_t(f.out)].shape;
             if ((ps.h | ps.w) & 1 || (os.h | os.w) & 1 || (os.h == 1 && os.w == 1)) continue;
-            f.phase_fold = true;
+            // fold by 4 where the sizes divide: operand bytes per output pixel go with taps^2 * Cin, (k + 2F - 2) / F taps per axis --
+            // 25 -> 9 for k = 9 -- and the 16 * c_out GEMM columns still fit one narrow tile
+            const bool by4 = !getenv("SMELTER_PHASE_FOLD_2") && (ps.h | ps.w | os.h | os.w) % 4 == 0 && 16 * f.c_out <= 64 && f.k_h >= 7;
+            const int fold = by4 ? 4 : 2, ff = fold * fold;
+            f.phase_fold = fold;
             f.conv_mode = k::CONV_MODE_IM2COL;
-            pad->s2d_out = true;
-            std::vector<float> b4(size_t(4) * f.c_out);
-            for (int ph = 0; ph < 4; ++ph) for (int co = 0; co < f.c_out; ++co) b4[size_t(ph) * f.c_out + co] = f.bias[size_t(co)];
+            pad->s2d_out = fold;
+            std::vector<float> b4(size_t(ff) * f.c_out);
+            for (int ph = 0; ph < ff; ++ph) for (int co = 0; co < f.c_out; ++co) b4[size_t(ph) * f.c_out + co] = f.bias[size_t(co)];
             f.bias.swap(b4);
         }
     }
@@ -440,7 +505,7 @@ int ONNXGraph::build() {
     // cost tensor time the layer has to spare.  No kernel and no layout change: weights, bias and the problem's dimensions only.
     if (!getenv("SMELTER_NO_WIDTH_FOLD")) {
         for (auto& f : filters_) {
-            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.groups != 1 || f.residual >= 0) continue;
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.upfold || f.groups != 1 || f.residual >= 0) continue;
             if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
             const int cp = round_up(f.c_in_g, 8);
             if (cp > 32 || f.k_w < 3 || f.c_out % 8) continue;
@@ -477,7 +542,11 @@ int ONNXGraph::upload_weights() {
             size_t wbytes;
             if (f.conv_mode == 4) wbytes = size_t(f.k_h) * f.k_w * round_up(f.c_out, 8) * 2;
             else if (f.s2d) wbytes = size_t(f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 16 * 2;
-            else if (f.phase_fold) wbytes = size_t(4 * f.c_out) * ((f.k_h + 1) / 2) * ((f.k_w + 1) / 2) * 4 * round_up(c_in, 8) * 2;
+            else if (f.phase_fold) {
+                const int F = f.phase_fold;
+                wbytes = size_t(F * F * f.c_out) * ((f.k_h + 2 * F - 2) / F) * ((f.k_w + 2 * F - 2) / F) * F * F * round_up(c_in, 8) * 2;
+            }
+            else if (f.upfold) wbytes = size_t(4 * f.c_out) * 9 * round_up(c_in, 8) * 2;
             else if (f.wfold) wbytes = size_t(f.wfold) * f.c_out * f.k_h * ((f.k_w + 2 * f.wfold - 2) / f.wfold) * f.wfold * round_up(c_in, 8) * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
@@ -497,7 +566,8 @@ int ONNXGraph::upload_weights() {
             uint16_t* w = reinterpret_cast<uint16_t*>(host.data() + f.w_off);
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
             else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
-            else if (f.phase_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
+            else if (f.phase_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), f.phase_fold, w);
+            else if (f.upfold) pack_weights_upfold(f.w.data(), f.c_out, c_in, round_up(c_in, 8), w);
             else if (f.wfold) pack_weights_wfold(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), f.wfold, w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
             memcpy(host.data() + f.bias_off, f.bias.data(), f.bias.size() * 4);
@@ -603,16 +673,19 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             q.h = (is.h - 1) * f.tr_stride_h + 1 + f.pads[0] + f.pads[2];
             q.w = (is.w - 1) * f.tr_stride_w + 1 + f.pads[1] + f.pads[3];
             q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.upfold) {  // [N, H + 2, W + 2, Cin] -> [N, H, W, 4 Cout]: the 2H x 2W output with its pixels in (y, x, phase) order
+            q.c_out = 4 * f.c_out; q.c_out_pitch = 4 * f.c_out;
         } else if (f.wfold) {  // the same buffers with wfold neighbouring pixels as one: [N, H, W/F, F Cin] -> [N, P, Q/F, F Cout]
             q.w = is.w / f.wfold;
             q.c_in = f.wfold * round_up(is.c, 8); q.c_in_pitch = f.wfold * round_up(is.c, 8);
             q.c_out = f.wfold * f.c_out; q.c_out_pitch = f.wfold * f.c_out;
             q.k_w = (f.k_w + 2 * f.wfold - 2) / f.wfold;
-        } else if (f.phase_fold) {  // the folded problem: [N, H/2, W/2, 4 Cin] -> [N, P/2, Q/2, 4 Cout], ceil(k/2)^2 taps
-            q.h = is.h / 2; q.w = is.w / 2;
-            q.c_in = 4 * round_up(is.c, 8); q.c_in_pitch = 4 * round_up(is.c, 8);
-            q.c_out = 4 * f.c_out; q.c_out_pitch = round_up(4 * f.c_out, 8);
-            q.k_h = (f.k_h + 1) / 2; q.k_w = (f.k_w + 1) / 2;
+        } else if (f.phase_fold) {  // the folded problem: [N, H/F, W/F, F^2 Cin] -> [N, P/F, Q/F, F^2 Cout], ((k + 2F - 2) / F)^2 taps
+            const int F = f.phase_fold;
+            q.h = is.h / F; q.w = is.w / F;
+            q.c_in = F * F * round_up(is.c, 8); q.c_in_pitch = F * F * round_up(is.c, 8);
+            q.c_out = F * F * f.c_out; q.c_out_pitch = round_up(F * F * f.c_out, 8);
+            q.k_h = (f.k_h + 2 * F - 2) / F; q.k_w = (f.k_w + 2 * F - 2) / F;
         } else if (f.s2d) {  // stride-1 convolution over the folded image the boundary conversion writes
             q.h = f.s2d_h / 2; q.w = f.s2d_w / 2;
             q.c_in_pitch = 16;
@@ -893,7 +966,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 L->balanced_grid = cfg_.sm_share >= 2 ? 1 : 0;
-                const char* mode_name = f.wfold ? "im2col/width-fold" : f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
+                const char* mode_name = f.upfold ? (f.conv_mode == k::CONV_MODE_PACKED_ROW ? "rows/upsample-fold" : "im2col/upsample-fold") : f.wfold ? "im2col/width-fold" : f.phase_fold == 4 ? "im2col/phase-fold4" : f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops + side_flops,
@@ -914,9 +987,9 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 float* partials = reinterpret_cast<float*>(abase + scratch[fi].off);
                 const int act = f.act;
                 const float eps = f.eps;
-                const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c;
-                add_step(std::string(group_size > 1 ? "group_norm " : "instance_norm ") + name,
-                         [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels); }, 0,
+                const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c, unfold_w = f.unfold_w;
+                add_step(std::string(group_size > 1 ? "group_norm " : unfold_w ? "instance_norm+unfold " : "instance_norm ") + name,
+                         [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels, unfold_w); }, 0,
                          io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)
                 plan->steps.back().launches = k::instance_norm_launches(N, is.h * is.w, icp, group_size);
                 break;
@@ -994,7 +1067,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             case FilterKind::Pad: {
                 const Filter* fp = &f;
                 add_step(std::string(f.s2d_out ? "pad+s2d " : "pad ") + name, [=](cudaStream_t st) {
-                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st, fp->s2d_out ? 1 : 0);
+                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st, fp->s2d_out);
                 }, 0, io_bytes);
                 break;
             }
@@ -1013,13 +1086,13 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         const __half* src = ptr_of(output_value_);
         const int cp = round_up(os.c, 8);
         const ImageShape o2 = os;
-        bool folded = false;  // produced by a phase-folded convolution: [N, H/2, W/2, 4 C] with the four phases as channel blocks
-        for (const Filter& pf : filters_) folded = folded || (!pf.removed && pf.phase_fold && root_of(pf.out) == out_root);
+        int folded = 0;  // produced by a phase-folded convolution: [N, H/F, W/F, F^2 C] with the F^2 phases as channel blocks
+        for (const Filter& pf : filters_) if (!pf.removed && pf.phase_fold && root_of(pf.out) == out_root) folded = pf.phase_fold;
         if (folded) {
-            const int cp4 = round_up(4 * os.c, 8);
+            const int F = folded, cpf = round_up(F * F * os.c, 8);
             add_step("phase_to_nchw " + values_[size_t(output_value_)].name,
-                     [=](cudaStream_t st) { return k::phase_to_nchw(src, dst, N, o2.c, o2.h / 2, o2.w / 2, cp4, long(o2.c) * o2.h * o2.w, st); }, 0,
-                     double(N) * o2.h * o2.w * o2.c * 2 + double(N) * (o2.h / 2) * (o2.w / 2) * cp4 * 2);
+                     [=](cudaStream_t st) { return k::phase_to_nchw(src, dst, N, o2.c, o2.h / F, o2.w / F, cpf, long(o2.c) * o2.h * o2.w, st, F); }, 0,
+                     double(N) * o2.h * o2.w * o2.c * 2 + double(N) * (o2.h / F) * (o2.w / F) * cpf * 2);
         } else
         add_step("nhwc_to_nchw " + values_[size_t(output_value_)].name,
                  [=](cudaStream_t st) { return k::nhwc_to_nchw(src, dst, N, o2.c, o2.h, o2.w, cp, long(o2.c) * o2.h * o2.w, st); }, 0,

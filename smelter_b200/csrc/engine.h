@@ -109,12 +109,19 @@ struct Filter {
     // Narrow-output stride-1 convolution behind a Pad (TransformerNet's 9x9 32 -> 3 output layer): computed on the 2 x 2
     // space-to-depth fold of its padded input, all four output phases of a folded pixel as 4 * c_out GEMM columns -- ceil(k / 2)^2
     // taps of 4 * Cin dense channels instead of k^2 taps of Cin (engine.cc "phase-folded").  The Pad writes the fold (s2d_out).
-    bool phase_fold = false;
+    int phase_fold = 0;            // fold factor F (2 or 4), 0 = not folded
     // Narrow-input stride-1 convolution without padding of its own (TransformerNet's 9x9 3 -> 32 input layer): `wfold` horizontally
     // neighbouring pixels are one pixel of wfold x Cin channels -- a pure re-interpretation of the NHWC input and output buffers
     // (engine.cc "width-folded"); 0 = not folded
     int wfold = 0;
-    bool s2d_out = false;          // Pad: output in space-to-depth layout
+    int s2d_out = 0;               // Pad: output in F x F space-to-depth layout (F = 2 or 4)
+    // nearest Upsample x2 -> reflect Pad 1 -> Conv 3x3 -> InstanceNorm (TransformerNet's decoder stages): the convolution runs on the
+    // edge-padded LOW-resolution image with the four output phases of a low-resolution pixel as 4 * Cout GEMM columns (every phase
+    // sees a 2 x 2 neighbourhood, tap weights that meet the same source pixel pre-summed): a quarter of the operand bytes and of the
+    // multiply-adds, no upsampled tensor.  Its output [H, W, 4, Cout] is the 2H x 2W image in a permuted pixel order -- which the
+    // normalisation's statistics do not see; its store un-permutes (unfold_w = W).  engine.cc "upsample-folded".
+    bool upfold = false;           // Conv
+    int unfold_w = 0;              // InstanceNorm behind an upsample-folded convolution: low-resolution width
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };
 

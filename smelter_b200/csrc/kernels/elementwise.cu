@@ -504,26 +504,29 @@ __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restric
             if (base + u * kThreads < row_items) st8(yr + size_t(base + u * kThreads) * 8, v[u]);
         return;
     }
-    // 2 x 2 space-to-depth output [n, ho / 2, wo / 2, 4 * cp]: padded pixel (oy, ox) is channel block (oy & 1) * 2 + (ox & 1) of folded
-    // pixel (oy / 2, ox / 2) -- the input layout of a phase-folded convolution (engine.cc, Filter::phase_fold)
-    __half* y2 = y + (size_t(img) * (ho >> 1) + (oy >> 1)) * size_t(wo >> 1) * (4 * cp8 * 8) + size_t(oy & 1) * 2 * cp8 * 8;
+    // s2d x s2d space-to-depth output [n, ho / s2d, wo / s2d, s2d^2 * cp] (s2d = 2 or 4): padded pixel (oy, ox) is channel block
+    // (oy % s2d) * s2d + (ox % s2d) of folded pixel (oy / s2d, ox / s2d) -- the input layout of a phase-folded convolution (engine.cc,
+    // Filter::phase_fold).  The s2d pixels of a folded pixel's row are contiguous: runs of s2d * cp channels.
+    const unsigned sh = s2d == 4 ? 2u : 1u, sm = unsigned(s2d) - 1u, blk = unsigned(s2d * s2d) * unsigned(cp8);
+    __half* y2 = y + (size_t(img) * (ho >> sh) + (unsigned(oy) >> sh)) * size_t(wo >> sh) * (blk * 8) + size_t(unsigned(oy) & sm) * s2d * cp8 * 8;
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         const unsigned it = base + u * kThreads;
         if (it >= row_items) break;
         const unsigned ox = it / unsigned(cp8), g = it - ox * unsigned(cp8);
-        st8(y2 + (size_t(ox >> 1) * 4 * cp8 + size_t(ox & 1) * cp8 + g) * 8, v[u]);
+        st8(y2 + (size_t(ox >> sh) * blk + size_t(ox & sm) * cp8 + g) * 8, v[u]);
     }
 }
 
-// Result of a phase-folded convolution -> NCHW: src [n, p2, q2, cp] holds, per folded pixel, channel (ey * 2 + ex) * c + co = output
-// channel co of full-resolution pixel (2 * p2 + ey, 2 * q2 + ex).  One thread per folded pixel, q2 fastest: the two ex of a row are one
-// 32-bit store and neighbouring threads write neighbouring words.
+// Result of a phase-folded convolution -> NCHW: src [n, p2, q2, cp] holds, per folded pixel, channel (ey * F + ex) * c + co = output
+// channel co of full-resolution pixel (F * p2 + ey, F * q2 + ex).  One thread per folded pixel, q2 fastest: the F ex of a row are one
+// 32-bit (F = 2) or 64-bit (F = 4) store and neighbouring threads write neighbouring words.
+template <int F>
 __global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c, int p2,
                                                                 int q2, int cp, long dst_image_pitch) {
     pdl_prologue();
     const size_t total = size_t(n) * p2 * q2;
-    const int q = 2 * q2;
+    const int q = F * q2;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int x2 = int(i % q2);
         const int y2 = int((i / q2) % p2);
@@ -531,9 +534,18 @@ __global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* _
         const __half* sp = src + i * cp;
         __half* dp = dst + size_t(img) * dst_image_pitch;
         for (int co = 0; co < c; ++co)
-            for (int ey = 0; ey < 2; ++ey) {
-                const __half2 v = __halves2half2(sp[(ey * 2 + 0) * c + co], sp[(ey * 2 + 1) * c + co]);
-                *reinterpret_cast<__half2*>(dp + (size_t(co) * (2 * p2) + 2 * y2 + ey) * q + 2 * x2) = v;
+            for (int ey = 0; ey < F; ++ey) {
+                __half* d = dp + (size_t(co) * (F * p2) + F * y2 + ey) * q + F * x2;
+                const __half2 v0 = __halves2half2(sp[(ey * F + 0) * c + co], sp[(ey * F + 1) * c + co]);
+                if constexpr (F == 2) {
+                    *reinterpret_cast<__half2*>(d) = v0;
+                } else {
+                    const __half2 v1 = __halves2half2(sp[(ey * F + 2) * c + co], sp[(ey * F + 3) * c + co]);
+                    uint2 w;
+                    w.x = *reinterpret_cast<const unsigned*>(&v0);
+                    w.y = *reinterpret_cast<const unsigned*>(&v1);
+                    *reinterpret_cast<uint2*>(d) = w;
+                }
             }
     }
 }
@@ -680,8 +692,10 @@ cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, in
     (void)launch_pdl(nhwc_to_nchw_kernel, dim3(grid_for(size_t(n) * (cp / 8) * h * w)), dim3(kThreads), s, src, dst, n, c, h * w, cp, dst_image_pitch);
     return cudaGetLastError();
 }
-cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s) {
-    (void)launch_pdl(phase_to_nchw_kernel, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s, int fold) {
+    if (fold != 2 && fold != 4) return cudaErrorInvalidValue;
+    if (fold == 2) (void)launch_pdl(phase_to_nchw_kernel<2>, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    else (void)launch_pdl(phase_to_nchw_kernel<4>, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
     return cudaGetLastError();
 }
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
@@ -698,7 +712,7 @@ cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, 
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
                   cudaStream_t s, int s2d_out) {
     const int ho = h + pt + pb, wo = w + pl + pr;
-    if (s2d_out && ((ho | wo) & 1)) return cudaErrorInvalidValue;
+    if (s2d_out && ((s2d_out != 2 && s2d_out != 4) || (ho | wo) % s2d_out)) return cudaErrorInvalidValue;
     if (size_t(n) * ho > 65535) return cudaErrorInvalidValue;  // grid.y = (image, output row)
     const unsigned row_items = unsigned(wo) * unsigned(cp / 8);
     (void)launch_pdl(pad2d_kernel, dim3(dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho))), dim3(kThreads), s, x, y, n, h, w, cp / 8, pt, pl, ho, wo,

@@ -26,8 +26,8 @@ cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, in
                          int pad_r, cudaStream_t s);
 // dst[n * dst_image_pitch + (c*H + h)*W + w] = src[n,h,w,c]
 cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, int w, int cp, long dst_image_pitch, cudaStream_t s);
-// result of a phase-folded convolution [n, p2, q2, cp] (channel (ey * 2 + ex) * c + co) -> NCHW [n, c, 2 * p2, 2 * q2]
-cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s);
+// result of a phase-folded convolution [n, p2, q2, cp] (channel (ey * F + ex) * c + co, F = fold = 2 or 4) -> NCHW [n, c, F * p2, F * q2]
+cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s, int fold = 2);
 
 // ConvTranspose input: y[n][lo_h + s_h*i][lo_w + s_w*j][c] = x[n][i][j][c], zero elsewhere; y is [n][hz][wz][cp]
 cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp, int hz, int wz, int stride_h, int stride_w, int lo_h, int lo_w,
@@ -47,8 +47,8 @@ cudaError_t global_avgpool(const __half* x, __half* y, int n, int hw, int cp, cu
 cudaError_t softmax_rows(const __half* x, __half* y, size_t rows, int c, int cp, int log_softmax, cudaStream_t s);
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,
                        cudaStream_t s);
-// s2d_out = 1: the padded image is written as its 2 x 2 space-to-depth fold [n, ho / 2, wo / 2, 4 * cp] (ho, wo even): the input
-// layout of a phase-folded convolution
+// s2d_out = F (2 or 4): the padded image is written as its F x F space-to-depth fold [n, ho / F, wo / F, F * F * cp] (F divides ho
+// and wo): the input layout of a phase-folded convolution
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
                   cudaStream_t s, int s2d_out = 0);
 // Instance normalisation: deterministic three-kernel scheme (split statistics, per-image scale / shift, apply).
@@ -58,7 +58,9 @@ int instance_norm_splits(int hw, int cp);
 int instance_norm_launches(int n, int hw, int cp, int group_size = 1);  // kernels instance_norm() enqueues: 1 (cluster form) or 3
 // group_size = channels that share one mean / variance: 1 = InstanceNormalization, C / groups = group normalisation
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
-                          int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0);
+                          int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0, int unfold_w = 0);
+// unfold_w = W > 0: x holds a 2H x 2W image as [H, W, 2 x 2 phases] pixels (hw = 4 H W, the output of an upsample-folded convolution,
+// engine.h Filter::upfold); statistics do not depend on pixel order, the store goes to plain row-major pixels.  x != y.
 // copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s);

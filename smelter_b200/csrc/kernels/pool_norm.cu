@@ -489,9 +489,14 @@ __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* _
         }
     }
 }
+// pixel p = (y * w + x) * 4 + ey * 2 + ex of an upsample-folded convolution's output -> row-major pixel (2y + ey, 2x + ex) of the 2h x 2w image
+__device__ __forceinline__ unsigned unfold_pixel(unsigned p, unsigned w) {
+    const unsigned ph = p & 3u, t = p >> 2, yy = t / w, xx = t - yy * w;
+    return (2u * yy + (ph >> 1)) * (2u * w) + 2u * xx + (ph & 1u);
+}
 // pass 2: y = act(x * scale + shift)
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
-                                                              int hw, int cp8, int act) {
+                                                              int hw, int cp8, int act, int unfold_w) {
     pdl_prologue();
     const int img = blockIdx.y;
     const float* sm = params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
@@ -529,7 +534,12 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
             const float r = fmaf(f[j], sc[j], sh[j]);
             f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
         }
-        st8(yb + i * 8, pack(f));
+        size_t o = i;
+        if (unfold_w) {
+            const unsigned pix = unsigned(i / size_t(cp8));
+            o = size_t(unfold_pixel(pix, unsigned(unfold_w))) * cp8 + (i - size_t(pix) * cp8);
+        }
+        st8(yb + o * 8, pack(f));
     }
 }
 
@@ -541,7 +551,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
 //      Thread t: vector (t & 1) of the slab (8 channels), pixel lane t >> 1; 32 contiguous bytes per pixel.
 __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int hw, int cp8, float eps, int act, int group_size,
-                                                                int channels) {
+                                                                int channels, int unfold_w) {
     pdl_prologue();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -651,7 +661,8 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
                         const float r = fmaf(f[j], sc[j], sh[j]);
                         f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
                     }
-                    st8(yb + size_t(pix + u * kLanes) * cp8 * 8, pack(f));
+                    const unsigned dp = unfold_w ? unfold_pixel(unsigned(pix + u * kLanes), unsigned(unfold_w)) : unsigned(pix + u * kLanes);
+                    st8(yb + size_t(dp) * cp8 * 8, pack(f));
                 }
         }
     }
@@ -870,8 +881,9 @@ int inorm_max_cluster() {
 }
 
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                          float* partials, cudaStream_t s, int group_size, int channels) {
+                          float* partials, cudaStream_t s, int group_size, int channels, int unfold_w) {
     if (group_size < 1) group_size = 1;
+    if (unfold_w && (x == y || unfold_w < 0 || hw % (4 * unfold_w))) return cudaErrorInvalidValue;
     if (channels <= 0) channels = cp;
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
@@ -889,7 +901,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels);
+        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, unfold_w);
     }
     const int splits = instance_norm_splits(hw, cp);
     const int lanes = kThreads / cp8;
@@ -914,7 +926,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         (void)launch_pdl(inorm_finalize_kernel, dim3(gn), dim3(kThreads), s, pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels, parts);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act);
+        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, unfold_w);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

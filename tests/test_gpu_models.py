@@ -445,11 +445,12 @@ def test_width_folded_input_convolution(ctx, monkeypatch, c_in, c_out, k, hw, pa
     assert np.abs(out - plain).max() <= 4e-3 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("c_in,c_out,k,hw", [(32, 3, 9, (24, 40)), (16, 8, 5, (30, 18)), (24, 1, 7, (16, 16))])
-def test_phase_folded_output_convolution(ctx, monkeypatch, c_in, c_out, k, hw):
-    """A narrow-output stride-1 convolution that produces the graph output behind a Pad runs on the 2 x 2 space-to-depth fold of its
-    padded input with the four output phases as GEMM columns (engine.cc "phase-folded"): the Pad writes the fold, the final
-    conversion un-folds; same result as the unfolded plan and the oracle."""
+@pytest.mark.parametrize("c_in,c_out,k,hw,fold", [(32, 3, 9, (24, 40), 4), (16, 8, 5, (30, 18), 2), (24, 1, 7, (16, 16), 2),
+                                                  (32, 2, 13, (20, 28), 4), (16, 4, 9, (32, 32), 4), (32, 3, 9, (26, 40), 2)])
+def test_phase_folded_output_convolution(ctx, monkeypatch, c_in, c_out, k, hw, fold):
+    """A narrow-output stride-1 convolution that produces the graph output behind a Pad runs on the F x F space-to-depth fold of its
+    padded input (F = 4 where the sizes divide, else 2) with the F^2 output phases as GEMM columns (engine.cc "phase-folded"): the
+    Pad writes the fold, the final conversion un-folds; same result as the unfolded plan, the 2 x 2 fold and the oracle."""
     from smelter_b200 import modelzoo
     from smelter_b200.api import Image, ONNXGraph
 
@@ -472,9 +473,55 @@ def test_phase_folded_output_convolution(ctx, monkeypatch, c_in, c_out, k, hw):
 
     out, dump = run()
     assert "phase-fold" in dump and "pad+s2d" in dump and "phase_to_nchw" in dump
+    assert ("phase-fold4" in dump) == (fold == 4)
     assert out.shape == want.shape
     assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+    if fold == 4:
+        monkeypatch.setenv("SMELTER_PHASE_FOLD_2", "1")
+        by2, dump2 = run()
+        assert "phase-fold" in dump2 and "phase-fold4" not in dump2
+        assert np.abs(out - by2).max() <= 4e-3 * max(1.0, np.abs(want).max())
     monkeypatch.setenv("SMELTER_NO_PHASE_FOLD", "1")
     plain, dump0 = run()
     assert "phase-fold" not in dump0
     assert np.abs(out - plain).max() <= 4e-3 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("c_in,c_out,hw,batch,cluster", [(64, 32, (12, 20), 2, True), (16, 8, (9, 7), 1, True), (128, 64, (16, 16), 1, False),
+                                                        (32, 16, (33, 18), 3, True)])
+def test_upsample_folded_convolution(ctx, monkeypatch, c_in, c_out, hw, batch, cluster):
+    """nearest Upsample x2 -> reflect Pad 1 -> Conv 3x3 -> InstanceNorm (TransformerNet's decoder stages) runs as one 3x3 convolution
+    on the edge-padded low-resolution image with the four output phases as GEMM columns and pre-summed taps; the normalisation
+    un-permutes the pixels (engine.cc "upsample-folded").  Same result as the literal plan and the oracle, in both forms of the
+    normalisation (cluster / three launches)."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c_in + h, name="upfold")
+    x = b.input("input", [batch, c_in, h, w])
+    y = b.relu(b.instancenorm(b.conv(b.pad(b.upsample(b.relu(b.conv(x, c_in, 1)), 2), 1, "reflect"), c_out, 3, 1, 0)))
+    y = b.conv(y, 8, 1)
+    b.output(y, [batch, 8, 2 * h, 2 * w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(h).standard_normal((batch, c_in, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+    if not cluster:
+        monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return out, dump, n
+
+    out, dump, n = run()
+    assert "upsample-fold" in dump and "instance_norm+unfold" in dump and "upsample " not in dump
+    assert out.shape == want.shape
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_UPSAMPLE_FOLD", "1")
+    plain, dump0, n0 = run()
+    assert "upsample-fold" not in dump0 and "upsample " in dump0 and n0 == n + 1
+    assert np.abs(out - plain).max() <= 6e-3 * max(1.0, np.abs(want).max())

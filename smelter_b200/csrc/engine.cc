@@ -523,6 +523,24 @@ int ONNXGraph::build() {
             f.bias.swap(bf);
         }
     }
+    // Reflection pads behind an instance norm are written by the norm (Filter::norm_pad): one launch and one round trip of the
+    // tensor less per Pad.  The apply pass stores the interior at its padded position; the border pixels (a few hundred to a few
+    // thousand) are extra tasks that re-read their mirror source -- not a per-pixel test on the latency-bound apply loop.
+    if (!getenv("SMELTER_NO_NORM_PAD")) {
+        for (auto& pd : filters_) {
+            if (pd.removed || pd.kind != FilterKind::Pad || pd.sub != k::PAD_REFLECT) continue;
+            Filter* nm = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.out == pd.in[0] && g.kind == FilterKind::InstanceNorm) nm = &g;
+            if (!nm || nm->norm_padded || consumers_of(nm->out) != 1 || nm->out == output_value_) continue;
+            const ImageShape& s = values_[size_t(nm->out)].shape;
+            if (pd.pads[0] >= s.h || pd.pads[2] >= s.h || pd.pads[1] >= s.w || pd.pads[3] >= s.w) continue;
+            for (int i = 0; i < 4; ++i) nm->norm_pad[i] = pd.pads[i];
+            nm->norm_s2d = pd.s2d_out;
+            nm->norm_padded = true;
+            nm->out = pd.out;
+            pd.removed = true;
+        }
+    }
     rc = upload_weights();  // MPSNNGraph(device:resultImage:) pulls weights from the data sources (:185-190)
     if (rc) return fail(SMELTER_ERR_GRAPH_INTERNAL, "weight upload failed: " + last_error_string());
     built_ = true;
@@ -987,9 +1005,16 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 float* partials = reinterpret_cast<float*>(abase + scratch[fi].off);
                 const int act = f.act;
                 const float eps = f.eps;
-                const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c, unfold_w = f.unfold_w;
-                add_step(std::string(group_size > 1 ? "group_norm " : unfold_w ? "instance_norm+unfold " : "instance_norm ") + name,
-                         [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels, unfold_w); }, 0,
+                const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c;
+                k::NormStore store;
+                store.unfold_w = f.unfold_w;
+                store.h = is.h; store.w = is.w;
+                if (f.norm_padded) { store.pad_t = f.norm_pad[0]; store.pad_l = f.norm_pad[1]; store.pad_b = f.norm_pad[2]; store.pad_r = f.norm_pad[3]; store.s2d = f.norm_s2d; }
+                std::string what = group_size > 1 ? "group_norm" : "instance_norm";
+                if (f.unfold_w) what += "+unfold";
+                if (f.norm_padded) what += f.norm_s2d ? "+pad+s2d" : "+pad";
+                add_step(what + " " + name,
+                         [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels, &store); }, 0,
                          io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)
                 plan->steps.back().launches = k::instance_norm_launches(N, is.h * is.w, icp, group_size);
                 break;

@@ -122,6 +122,11 @@ struct Filter {
     // normalisation's statistics do not see; its store un-permutes (unfold_w = W).  engine.cc "upsample-folded".
     bool upfold = false;           // Conv
     int unfold_w = 0;              // InstanceNorm behind an upsample-folded convolution: low-resolution width
+    // InstanceNorm whose only reader was a reflection Pad: the norm writes the padded image itself (interior at an offset, the border
+    // pixels from their mirror sources, kernels.h NormStore) -- `out` is the Pad's output, the Pad is gone.  norm_s2d = its s2d_out.
+    int norm_pad[4] = {0, 0, 0, 0};
+    int norm_s2d = 0;
+    bool norm_padded = false;
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };
 

@@ -57,10 +57,18 @@ size_t instance_norm_scratch_floats(int n, int hw, int cp);
 int instance_norm_splits(int hw, int cp);
 int instance_norm_launches(int n, int hw, int cp, int group_size = 1);  // kernels instance_norm() enqueues: 1 (cluster form) or 3
 // group_size = channels that share one mean / variance: 1 = InstanceNormalization, C / groups = group normalisation
+// Where instance_norm() stores a normalised pixel (default: where it came from).  Statistics do not depend on pixel order, so the
+// kernel can undo a permutation and write into a larger image on its way out.  x != y whenever anything is set.
+struct NormStore {
+    int unfold_w = 0;  // W > 0: x holds a 2H x 2W image as [H, W, 2 x 2 phases] pixels (hw = 4 H W, the output of an upsample-folded
+                       // convolution, engine.h Filter::upfold); the store goes to plain row-major pixels
+    int h = 0, w = 0;  // image size as stored (after un-folding, h * w == hw); needed with padding
+    int pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0;  // the reflection Pad behind the norm, written by the norm: y is the padded image
+    int s2d = 0;       // ... in pad2d's F x F space-to-depth layout (F = 2 or 4)
+    bool padded() const { return pad_t || pad_l || pad_b || pad_r || s2d; }
+};
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
-                          int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0, int unfold_w = 0);
-// unfold_w = W > 0: x holds a 2H x 2W image as [H, W, 2 x 2 phases] pixels (hw = 4 H W, the output of an upsample-folded convolution,
-// engine.h Filter::upfold); statistics do not depend on pixel order, the store goes to plain row-major pixels.  x != y.
+                          int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0, const NormStore* store = nullptr);
 // copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s);

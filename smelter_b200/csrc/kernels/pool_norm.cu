@@ -489,14 +489,53 @@ __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* _
         }
     }
 }
+// ---- where a normalised pixel goes (kernels.h NormStore) ----
+struct NormDst {
+    int unfold_w, h, w, pt, pl, ho, wo, s2d;  // ho == 0: no padding
+};
+__device__ __forceinline__ int reflect_at(int i, int n) {  // ONNX 'reflect' (no edge repeat), pads < n
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
 // pixel p = (y * w + x) * 4 + ey * 2 + ex of an upsample-folded convolution's output -> row-major pixel (2y + ey, 2x + ex) of the 2h x 2w image
 __device__ __forceinline__ unsigned unfold_pixel(unsigned p, unsigned w) {
     const unsigned ph = p & 3u, t = p >> 2, yy = t / w, xx = t - yy * w;
     return (2u * yy + (ph >> 1)) * (2u * w) + 2u * xx + (ph & 1u);
 }
-// pass 2: y = act(x * scale + shift)
+// 16-byte vector index (vector 0 of the pixel) of padded pixel (oy, ox)
+__device__ __forceinline__ size_t padded_vec(const NormDst& d, unsigned oy, unsigned ox, unsigned cp8) {
+    if (!d.s2d) return (size_t(oy) * unsigned(d.wo) + ox) * cp8;
+    const unsigned sh = d.s2d == 4 ? 2u : 1u, sm = unsigned(d.s2d) - 1u;
+    return ((size_t(oy >> sh) * (unsigned(d.wo) >> sh) + (ox >> sh)) * unsigned(d.s2d * d.s2d) + ((oy & sm) * unsigned(d.s2d) + (ox & sm))) * cp8;
+}
+// ... of source pixel p (storage order of x)
+__device__ __forceinline__ size_t norm_dst_vec(const NormDst& d, unsigned p, unsigned cp8) {
+    const unsigned q = d.unfold_w ? unfold_pixel(p, unsigned(d.unfold_w)) : p;
+    if (!d.ho) return size_t(q) * cp8;
+    const unsigned yy = q / unsigned(d.w), xx = q - yy * unsigned(d.w);
+    return padded_vec(d, yy + unsigned(d.pt), xx + unsigned(d.pl), cp8);
+}
+// border pixel j (0 <= j < ho * wo - h * w: top rows, bottom rows, then the left / right columns of the rows between) -> its
+// position and the storage index of the pixel it mirrors
+__device__ __forceinline__ void ring_pixel(const NormDst& d, unsigned j, unsigned& oy, unsigned& ox, unsigned& src) {
+    const unsigned wo = unsigned(d.wo), top = unsigned(d.pt) * wo, bottom = unsigned(d.ho - d.h - d.pt) * wo;
+    if (j < top) {
+        oy = j / wo; ox = j - oy * wo;
+    } else if (j < top + bottom) {
+        const unsigned t = j - top, r = t / wo;
+        oy = unsigned(d.pt + d.h) + r; ox = t - r * wo;
+    } else {
+        const unsigned t = j - top - bottom, side = unsigned(d.wo - d.w), r = t / side, kk = t - r * side;
+        oy = unsigned(d.pt) + r; ox = kk < unsigned(d.pl) ? kk : unsigned(d.w) + kk;
+    }
+    const unsigned sy = unsigned(reflect_at(int(oy) - d.pt, d.h)), sx = unsigned(reflect_at(int(ox) - d.pl, d.w));
+    src = d.unfold_w ? ((sy >> 1) * unsigned(d.unfold_w) + (sx >> 1)) * 4u + (sy & 1u) * 2u + (sx & 1u) : sy * unsigned(d.w) + sx;
+}
+// pass 2: y = act(x * scale + shift).  Blocks past `chunks` write the reflection border (NormStore::pad_*): one task per (border
+// pixel, 8 channels), source pixel re-read.
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
-                                                              int hw, int cp8, int act, int unfold_w) {
+                                                              int hw, int cp8, int act, NormDst dst, int chunks) {
     pdl_prologue();
     const int img = blockIdx.y;
     const float* sm = params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
@@ -504,13 +543,34 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
     // channels in every vector it handles and keeps their scale / shift in registers
     constexpr int U = 8;
     const size_t n8 = size_t(hw) * cp8;
+    const bool plain = !dst.unfold_w && !dst.ho;
+    const bool ring = int(blockIdx.x) >= chunks;
+    const size_t tasks = ring ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : n8;
     const __half* xb = x + size_t(img) * n8 * 8;
-    __half* yb = y + size_t(img) * n8 * 8;
-    const size_t base = size_t(blockIdx.x) * (kThreads * U) + threadIdx.x;
+    __half* yb = y + size_t(img) * (dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) * 8;
+    const size_t base = size_t(ring ? int(blockIdx.x) - chunks : int(blockIdx.x)) * (kThreads * U) + threadIdx.x;
     Half8 v[U];
+    size_t o[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u)
-        if (base + u * kThreads < n8) v[u] = ld8(xb + (base + u * kThreads) * 8);
+    for (int u = 0; u < U; ++u) {
+        const size_t i = base + u * kThreads;
+        if (i >= tasks) break;
+        if (!ring) {
+            v[u] = ld8(xb + i * 8);
+            if (plain) {
+                o[u] = i;
+            } else {
+                const unsigned pix = unsigned(i / size_t(cp8));
+                o[u] = norm_dst_vec(dst, pix, unsigned(cp8)) + (i - size_t(pix) * cp8);
+            }
+        } else {
+            const unsigned j = unsigned(i / size_t(cp8)), g = unsigned(i - size_t(j) * cp8);
+            unsigned oy, ox, src;
+            ring_pixel(dst, j, oy, ox, src);
+            v[u] = ld8(xb + (size_t(src) * cp8 + g) * 8);
+            o[u] = padded_vec(dst, oy, ox, unsigned(cp8)) + g;
+        }
+    }
     const bool fixed = (kThreads % cp8) == 0;
     float sc[8], sh[8];
     if (fixed) {
@@ -521,7 +581,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const size_t i = base + u * kThreads;
-        if (i >= n8) break;
+        if (i >= tasks) break;
         if (!fixed) {
             const int c0 = int(i % size_t(cp8)) * 8;
 #pragma unroll
@@ -534,12 +594,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
             const float r = fmaf(f[j], sc[j], sh[j]);
             f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
         }
-        size_t o = i;
-        if (unfold_w) {
-            const unsigned pix = unsigned(i / size_t(cp8));
-            o = size_t(unfold_pixel(pix, unsigned(unfold_w))) * cp8 + (i - size_t(pix) * cp8);
-        }
-        st8(yb + o * 8, pack(f));
+        st8(yb + o[u] * 8, pack(f));
     }
 }
 
@@ -551,7 +606,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
 //      Thread t: vector (t & 1) of the slab (8 channels), pixel lane t >> 1; 32 contiguous bytes per pixel.
 __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int hw, int cp8, float eps, int act, int group_size,
-                                                                int channels, int unfold_w) {
+                                                                int channels, NormDst dst) {
     pdl_prologue();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -570,7 +625,8 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
     __shared__ float scsh[2][8][2];
     const bool live = v < ng;
     const __half* xb = x + (size_t(img) * hw * cp8 + g0 + v) * 8;
-    __half* yb = y + (size_t(img) * hw * cp8 + g0 + v) * 8;
+    __half* yb = y + (size_t(img) * (dst.ho ? size_t(dst.ho) * dst.wo : size_t(hw)) * cp8 + g0 + v) * 8;
+    const bool plain = !dst.unfold_w && !dst.ho;
     float s1[8] = {0, 0, 0, 0, 0, 0, 0, 0}, s2[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (live) {
         for (int pix = p0 + pl; pix < p1; pix += kU * kLanes) {  // kU independent loads in flight per thread
@@ -646,6 +702,17 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
         float sc[8], sh[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = scsh[v][j][0]; sh[j] = scsh[v][j][1]; }
+        // the reflection border (NormStore::pad_*): its pixels dealt round-robin over the cluster's threads, at most a few each
+        const unsigned nring = dst.ho ? unsigned(dst.ho * dst.wo - dst.h * dst.w) : 0u;
+        const unsigned ring_j = unsigned(rank * kLanes + pl);
+        Half8 ring_v;
+        size_t ring_o = 0;
+        if (ring_j < nring) {
+            unsigned oy, ox, src;
+            ring_pixel(dst, ring_j, oy, ox, src);
+            ring_v = ld8(xb + size_t(src) * cp8 * 8);
+            ring_o = padded_vec(dst, oy, ox, unsigned(cp8));
+        }
         for (int pix = p0 + pl; pix < p1; pix += kU * kLanes) {
             Half8 t[kU];
 #pragma unroll
@@ -661,9 +728,25 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
                         const float r = fmaf(f[j], sc[j], sh[j]);
                         f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
                     }
-                    const unsigned dp = unfold_w ? unfold_pixel(unsigned(pix + u * kLanes), unsigned(unfold_w)) : unsigned(pix + u * kLanes);
-                    st8(yb + size_t(dp) * cp8 * 8, pack(f));
+                    const size_t o = plain ? size_t(pix + u * kLanes) * cp8 : norm_dst_vec(dst, unsigned(pix + u * kLanes), unsigned(cp8));
+                    st8(yb + o * 8, pack(f));
                 }
+        }
+        for (unsigned j = ring_j; j < nring; j += unsigned(csz * kLanes)) {  // the first one was requested before the apply loop
+            if (j != ring_j) {
+                unsigned oy, ox, src;
+                ring_pixel(dst, j, oy, ox, src);
+                ring_v = ld8(xb + size_t(src) * cp8 * 8);
+                ring_o = padded_vec(dst, oy, ox, unsigned(cp8));
+            }
+            float f[8];
+            unpack(ring_v, f);
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                const float r = fmaf(f[jj], sc[jj], sh[jj]);
+                f[jj] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
+            }
+            st8(yb + ring_o * 8, pack(f));
         }
     }
 }
@@ -881,10 +964,24 @@ int inorm_max_cluster() {
 }
 
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                          float* partials, cudaStream_t s, int group_size, int channels, int unfold_w) {
+                          float* partials, cudaStream_t s, int group_size, int channels, const NormStore* store) {
     if (group_size < 1) group_size = 1;
-    if (unfold_w && (x == y || unfold_w < 0 || hw % (4 * unfold_w))) return cudaErrorInvalidValue;
     if (channels <= 0) channels = cp;
+    NormDst dst{};
+    if (store) {
+        if (x == y && (store->unfold_w || store->padded())) return cudaErrorInvalidValue;
+        if (store->unfold_w < 0 || (store->unfold_w && hw % (4 * store->unfold_w))) return cudaErrorInvalidValue;
+        dst.unfold_w = store->unfold_w;
+        if (store->padded()) {
+            if (store->h <= 0 || store->w <= 0 || size_t(store->h) * store->w != size_t(hw)) return cudaErrorInvalidValue;
+            if (store->unfold_w && 2 * store->unfold_w != store->w) return cudaErrorInvalidValue;
+            if (store->pad_t >= store->h || store->pad_b >= store->h || store->pad_l >= store->w || store->pad_r >= store->w) return cudaErrorInvalidValue;
+            dst.h = store->h; dst.w = store->w; dst.pt = store->pad_t; dst.pl = store->pad_l;
+            dst.ho = store->h + store->pad_t + store->pad_b; dst.wo = store->w + store->pad_l + store->pad_r;
+            dst.s2d = store->s2d;
+            if (dst.s2d && ((dst.s2d != 2 && dst.s2d != 4) || dst.ho % dst.s2d || dst.wo % dst.s2d)) return cudaErrorInvalidValue;
+        }
+    }
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
     if (const int csz = inorm_cluster_size(hw, group_size); csz > 0 && n <= 65535) {
@@ -901,7 +998,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, unfold_w);
+        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, dst);
     }
     const int splits = instance_norm_splits(hw, cp);
     const int lanes = kThreads / cp8;
@@ -914,7 +1011,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
     for (int i0 = 0; i0 < n; i0 += group) {
         const int gn = std::min(group, n - i0);
         const __half* xg = x + size_t(i0) * n8 * 8;
-        __half* yg = y + size_t(i0) * n8 * 8;
+        __half* yg = y + size_t(i0) * (dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) * 8;
         float* pg = partials + size_t(i0) * splits * cp * 2;
         (void)launch_pdl_smem(inorm_stats_kernel, dim3(dim3(splits, gn)), dim3(kThreads), smem1, s, xg, pg, hw, cp8, splits);
         cudaError_t e = cudaGetLastError();
@@ -926,7 +1023,9 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         (void)launch_pdl(inorm_finalize_kernel, dim3(gn), dim3(kThreads), s, pg, gamma, beta, params, hw, cp, splits, eps, group_size, channels, parts);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
-        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, unfold_w);
+        const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
+        const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
+        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

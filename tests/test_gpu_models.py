@@ -525,3 +525,43 @@ def test_upsample_folded_convolution(ctx, monkeypatch, c_in, c_out, hw, batch, c
     plain, dump0, n0 = run()
     assert "upsample-fold" not in dump0 and "upsample " in dump0 and n0 == n + 1
     assert np.abs(out - plain).max() <= 6e-3 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("c,hw,pad,k,batch,cluster", [(32, (16, 24), 1, 3, 2, True), (16, (20, 12), 4, 9, 1, True), (64, (9, 11), 2, 5, 3, True),
+                                                     (32, (16, 24), 1, 3, 2, False), (32, (24, 40), 4, 9, 2, False), (24, (7, 5), 3, 7, 1, True)])
+def test_reflection_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pad, k, batch, cluster):
+    """InstanceNorm (+ReLU) -> reflect Pad: the norm stores the padded image itself (interior at an offset, border pixels re-read
+    from their mirror sources; space-to-depth layout when the Pad feeds a phase-folded convolution) in both of its forms.  Same
+    result as the plan with the Pad kernel, bit for bit up to the convolution (same values, same positions), and the oracle."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c + pad, name="normpad")
+    x = b.input("input", [batch, c, h, w])
+    y = b.relu(b.instancenorm(b.conv(x, c, 3, 1, 1)))
+    c_out = 3 if k == 9 else 16
+    y = b.conv(b.pad(y, pad, "reflect"), c_out, k, 1, 0)
+    b.output(y, [batch, c_out, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(pad).standard_normal((batch, c, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+    if not cluster:
+        monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toHalfArray().copy()
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return out, dump, n
+
+    out, dump, n = run()
+    assert "instance_norm+pad" in dump and "pad Pad" not in dump
+    assert ("+pad+s2d" in dump) == (k == 9)
+    assert np.abs(out.astype(np.float32) - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_NORM_PAD", "1")
+    plain, dump0, n0 = run()
+    assert "instance_norm+pad" not in dump0 and n0 == n + 1
+    assert np.array_equal(out.view(np.uint16), plain.view(np.uint16))

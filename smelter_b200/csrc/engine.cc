@@ -523,12 +523,44 @@ int ONNXGraph::build() {
             f.bias.swap(bf);
         }
     }
+    // A residual Add in front of a Pad runs inside the Pad kernel (Filter::pad_add): one launch and one read of the sum less.  The
+    // plain sum is stored too while it has other readers, all of which must come after the Pad in execution order.
+    if (!getenv("SMELTER_NO_PAD_ADD")) {
+        for (size_t pi = 0; pi < filters_.size(); ++pi) {
+            Filter& pd = filters_[pi];
+            if (pd.removed || pd.kind != FilterKind::Pad || pd.s2d_out || pd.pad_add || pd.in.size() != 1) continue;
+            Filter* ad = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.out == pd.in[0] && g.kind == FilterKind::Binary && g.sub == k::BIN_ADD) ad = &g;
+            if (!ad || ad->in.size() != 2 || ad->out == output_value_ || (ad->act != k::ACT_NONE && ad->act != k::ACT_RELU)) continue;
+            const ImageShape& sa = values_[size_t(ad->in[0])].shape;
+            const ImageShape& sb = values_[size_t(ad->in[1])].shape;
+            const ImageShape& so = values_[size_t(ad->out)].shape;
+            auto same = [](const ImageShape& p, const ImageShape& q) { return p.c == q.c && p.h == q.h && p.w == q.w; };
+            if (!same(sa, so) || !same(sb, so)) continue;  // no broadcasting
+            bool ok = true;
+            int others = 0;
+            for (size_t gi = 0; gi < filters_.size(); ++gi) {
+                const Filter& g = filters_[gi];
+                if (g.removed || gi == pi) continue;
+                bool reads = g.residual == ad->out;
+                for (int i : g.in) reads = reads || i == ad->out;
+                if (reads) { ++others; ok = ok && gi > pi; }
+            }
+            for (const auto& v : values_) ok = ok && v.alias_of != ad->out;
+            if (!ok) continue;
+            pd.in = {ad->in[0], ad->in[1]};
+            pd.act = ad->act;
+            pd.out2 = others ? ad->out : -1;
+            pd.pad_add = true;
+            ad->removed = true;
+        }
+    }
     // Reflection pads behind an instance norm are written by the norm (Filter::norm_pad): one launch and one round trip of the
     // tensor less per Pad.  The apply pass stores the interior at its padded position; the border pixels (a few hundred to a few
     // thousand) are extra tasks that re-read their mirror source -- not a per-pixel test on the latency-bound apply loop.
     if (!getenv("SMELTER_NO_NORM_PAD")) {
         for (auto& pd : filters_) {
-            if (pd.removed || pd.kind != FilterKind::Pad || pd.sub != k::PAD_REFLECT) continue;
+            if (pd.removed || pd.kind != FilterKind::Pad || pd.sub != k::PAD_REFLECT || pd.pad_add) continue;
             Filter* nm = nullptr;
             for (auto& g : filters_) if (!g.removed && g.out == pd.in[0] && g.kind == FilterKind::InstanceNorm) nm = &g;
             if (!nm || nm->norm_padded || consumers_of(nm->out) != 1 || nm->out == output_value_) continue;
@@ -845,6 +877,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             }
         }
         off[size_t(f.out)] = arena.alloc(bytes_of(f.out));
+        if (f.out2 >= 0) off[size_t(f.out2)] = arena.alloc(bytes_of(f.out2));
         if (scratch[fi].off != size_t(-1)) arena.release(scratch[fi].off, scratch[fi].bytes);
         if (scratch2[fi].off != size_t(-1)) arena.release(scratch2[fi].off, scratch2[fi].bytes);
         // release inputs whose last use is this filter
@@ -1091,9 +1124,12 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             }
             case FilterKind::Pad: {
                 const Filter* fp = &f;
-                add_step(std::string(f.s2d_out ? "pad+s2d " : "pad ") + name, [=](cudaStream_t st) {
-                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st, fp->s2d_out);
-                }, 0, io_bytes);
+                const __half* x2 = f.pad_add ? ptr_of(f.in[1]) : nullptr;
+                __half* y2 = f.pad_add && f.out2 >= 0 ? ptr_of(f.out2) : nullptr;
+                const int act = f.pad_add ? f.act : int(k::ACT_NONE);
+                add_step(std::string(f.pad_add ? (y2 ? "add+pad+sum " : "add+pad ") : f.s2d_out ? "pad+s2d " : "pad ") + name, [=](cudaStream_t st) {
+                    return k::pad2d(x, y, N, is.h, is.w, icp, fp->pads[0], fp->pads[1], fp->pads[2], fp->pads[3], fp->sub, fp->alpha, st, fp->s2d_out, x2, y2, act);
+                }, 0, io_bytes + (x2 ? double(N) * is.h * is.w * icp * 2 * (y2 ? 2 : 1) : 0));
                 break;
             }
             case FilterKind::Alias:

@@ -124,6 +124,10 @@ struct Filter {
     int unfold_w = 0;              // InstanceNorm behind an upsample-folded convolution: low-resolution width
     // InstanceNorm whose only reader was a reflection Pad: the norm writes the padded image itself (interior at an offset, the border
     // pixels from their mirror sources, kernels.h NormStore) -- `out` is the Pad's output, the Pad is gone.  norm_s2d = its s2d_out.
+    // Pad whose input was a residual Add: the Pad kernel adds (in[0] + in[1], activation `act`) on its way, and also stores the plain
+    // sum as value out2 when the Add had other readers (the next block's skip connection); out2 < 0: nobody else reads it
+    bool pad_add = false;
+    int out2 = -1;
     int norm_pad[4] = {0, 0, 0, 0};
     int norm_s2d = 0;
     bool norm_padded = false;

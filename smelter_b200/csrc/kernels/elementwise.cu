@@ -470,23 +470,65 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
 }
 
 // blockIdx.y = (image, output row): the source row is resolved once per block; threads walk (ox, channel group) of the row.
+// x2 != nullptr: the padded tensor is act(x + x2) (a residual Add in front of the Pad, engine.h Filter::pad_add); y_plain != nullptr:
+// the un-padded sum is stored as well (it has other readers).
 __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
-                                                        int pt, int pl, int ho, int wo, int mode, float value, int s2d) {
+                                                        int pt, int pl, int ho, int wo, int mode, float value, int s2d,
+                                                        const __half* __restrict__ x2, __half* __restrict__ y_plain, int act) {
     pdl_prologue();
     const int oy = blockIdx.y % ho;
     const int img = blockIdx.y / ho;
     int sy = oy - pt;
     bool row_inside = sy >= 0 && sy < h;
+    const bool row_interior = row_inside;
     if (mode == PAD_REFLECT) { sy = reflect_idx(sy, h); row_inside = true; }
     else if (mode == PAD_EDGE) { sy = min(max(sy, 0), h - 1); row_inside = true; }
     Half8 fill;
 #pragma unroll
     for (int j = 0; j < 4; ++j) fill.v[j] = __floats2half2_rn(value, value);
     const unsigned row_items = unsigned(wo) * unsigned(cp8);
-    const __half* xr = x + (size_t(img) * h + (row_inside ? sy : 0)) * w * cp8 * 8;
+    const size_t src_row = (size_t(img) * h + (row_inside ? sy : 0)) * w * cp8 * 8;
+    const __half* xr = x + src_row;
     __half* yr = y + (size_t(img) * ho + oy) * row_items * 8;
     const unsigned base = blockIdx.x * (kThreads * kUnroll) + threadIdx.x;
     Half8 v[kUnroll];
+    if (x2) {
+        Half8 v2[kUnroll];
+        unsigned so[kUnroll];  // source vector of the row, bit 31: the pixel is an interior one; all ones: nothing to add
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) so[u] = 0xffffffffu;
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            const unsigned it = base + u * kThreads;
+            if (it >= row_items) break;
+            const unsigned ox = it / unsigned(cp8), g = it - ox * unsigned(cp8);
+            int sx = int(ox) - pl;
+            bool inside = row_inside && sx >= 0 && sx < w;
+            const bool interior = row_interior && sx >= 0 && sx < w;
+            if (mode == PAD_REFLECT) { sx = reflect_idx(sx, w); inside = true; }
+            else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
+            v[u] = fill;
+            if (inside) {
+                v[u] = ld8(xr + (size_t(sx) * cp8 + g) * 8);
+                v2[u] = ld8(x2 + src_row + (size_t(sx) * cp8 + g) * 8);
+                so[u] = (unsigned(sx) * unsigned(cp8) + g) | (interior ? 0x80000000u : 0u);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < kUnroll; ++u) {
+            if (so[u] == 0xffffffffu) continue;
+            float a[8], b[8];
+            unpack(v[u], a);
+            unpack(v2[u], b);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float r = a[j] + b[j];
+                a[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
+            }
+            v[u] = pack(a);
+            if (y_plain && (so[u] & 0x80000000u)) st8(y_plain + src_row + size_t(so[u] & 0x7fffffffu) * 8, v[u]);
+        }
+    } else {
 #pragma unroll
     for (int u = 0; u < kUnroll; ++u) {
         const unsigned it = base + u * kThreads;
@@ -497,6 +539,7 @@ __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restric
         if (mode == PAD_REFLECT) { sx = reflect_idx(sx, w); inside = true; }
         else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
         v[u] = inside ? ld8(xr + (size_t(sx) * cp8 + g) * 8) : fill;
+    }
     }
     if (!s2d) {
 #pragma unroll
@@ -710,13 +753,15 @@ cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, 
     return cudaGetLastError();
 }
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
-                  cudaStream_t s, int s2d_out) {
+                  cudaStream_t s, int s2d_out, const __half* x2, __half* y_plain, int act) {
     const int ho = h + pt + pb, wo = w + pl + pr;
     if (s2d_out && ((s2d_out != 2 && s2d_out != 4) || (ho | wo) % s2d_out)) return cudaErrorInvalidValue;
     if (size_t(n) * ho > 65535) return cudaErrorInvalidValue;  // grid.y = (image, output row)
+    if (!x2 && (y_plain || act != ACT_NONE)) return cudaErrorInvalidValue;
+    if (x2 && size_t(w) * (cp / 8) >= 0x7fffffffu) return cudaErrorInvalidValue;
     const unsigned row_items = unsigned(wo) * unsigned(cp / 8);
     (void)launch_pdl(pad2d_kernel, dim3(dim3((row_items + kThreads * kUnroll - 1) / (kThreads * kUnroll), unsigned(n * ho))), dim3(kThreads), s, x, y, n, h, w, cp / 8, pt, pl, ho, wo,
-                                                                                                                 mode, value, s2d_out);
+                                                                                                                 mode, value, s2d_out, x2, y_plain, act);
     return cudaGetLastError();
 }
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,

@@ -49,8 +49,9 @@ cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, 
                        cudaStream_t s);
 // s2d_out = F (2 or 4): the padded image is written as its F x F space-to-depth fold [n, ho / F, wo / F, F * F * cp] (F divides ho
 // and wo): the input layout of a phase-folded convolution
+// x2 != nullptr: the padded tensor is act(x + x2) (the residual Add in front of the Pad); y_plain != nullptr also stores the un-padded sum
 cudaError_t pad2d(const __half* x, __half* y, int n, int h, int w, int cp, int pt, int pl, int pb, int pr, int mode, float value,
-                  cudaStream_t s, int s2d_out = 0);
+                  cudaStream_t s, int s2d_out = 0, const __half* x2 = nullptr, __half* y_plain = nullptr, int act = 0);
 // Instance normalisation: deterministic three-kernel scheme (split statistics, per-image scale / shift, apply).
 // `partials` holds instance_norm_scratch_floats(n, hw, cp) floats.
 size_t instance_norm_scratch_floats(int n, int hw, int cp);

@@ -565,3 +565,45 @@ def test_reflection_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pa
     plain, dump0, n0 = run()
     assert "instance_norm+pad" not in dump0 and n0 == n + 1
     assert np.array_equal(out.view(np.uint16), plain.view(np.uint16))
+
+
+@pytest.mark.parametrize("mode,relu,second_reader,hw,batch", [("reflect", False, True, (16, 24), 2), ("reflect", True, False, (9, 7), 1),
+                                                             ("constant", False, True, (12, 12), 3), ("edge", True, True, (20, 10), 1)])
+def test_residual_add_inside_the_pad_kernel(ctx, monkeypatch, mode, relu, second_reader, hw, batch):
+    """Add (-> ReLU) -> Pad: the Pad kernel adds on its way and also stores the plain sum while another filter reads it (the next
+    block's skip connection).  Bit-identical to the two-kernel plan; oracle within tolerance."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    c = 32
+    b = modelzoo.GraphBuilder(seed=h, name="padadd")
+    x = b.input("input", [batch, c, h, w])
+    a = b.relu(b.conv(x, c, 3, 1, 1))
+    z = b.instancenorm(b.conv(a, c, 1))  # a norm in between: the Add is not a convolution epilogue
+    y = b.add(z, a)
+    if relu:
+        y = b.relu(y)
+    t = b.conv(b.pad(y, 2, mode), c, 5, 1, 0)
+    if second_reader:
+        t = b.add(t, y)
+    b.output(t, [batch, c, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(h).standard_normal((batch, c, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toHalfArray().copy()
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return out, dump, n
+
+    out, dump, n = run()
+    assert ("add+pad+sum" in dump) == second_reader and "add+pad" in dump
+    assert np.abs(out.astype(np.float32) - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_PAD_ADD", "1")
+    plain, dump0, n0 = run()
+    assert "add+pad" not in dump0 and n0 == n + 1
+    assert np.array_equal(out.view(np.uint16), plain.view(np.uint16))

@@ -497,6 +497,39 @@ int ONNXGraph::build() {
             f.bias.swap(b4);
         }
     }
+    // Input-folded convolutions (Filter::in_fold, engine.h): graph input -> Pad -> Conv k x k (k = 1 mod 4, stride 1) -> InstanceNorm
+    // with single readers.  The Pad goes into the boundary conversion, which writes the 4 x 4 space-to-depth fold.
+    if (!getenv("SMELTER_NO_INPUT_FOLD")) {
+        for (auto& f : filters_) {
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.upfold || f.groups != 1 || f.residual >= 0) continue;
+            if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
+            if (f.k_h != f.k_w || f.k_h < 5 || f.k_h % 4 != 1 || f.c_in_g > 4 || f.c_out % 8 || 16 * f.c_out > 1024) continue;
+            if (f.out == output_value_ || consumers_of(f.out) != 1) continue;
+            Filter* pad = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.out == f.in[0] && g.kind == FilterKind::Pad) pad = &g;
+            if (!pad || pad->s2d_out || pad->pad_add || consumers_of(pad->out) != 1) continue;
+            const int v = pad->in[0];
+            if (!values_[size_t(v)].is_input || consumers_of(v) != 1 || v == output_value_) continue;
+            Filter* norm = nullptr;
+            for (auto& g : filters_) if (!g.removed && g.kind == FilterKind::InstanceNorm && !g.in.empty() && g.in[0] == f.out) norm = &g;
+            if (!norm || norm->unfold_w) continue;
+            const ImageShape& ps = values_[size_t(pad->out)].shape;
+            const ImageShape& os = values_[size_t(f.out)].shape;
+            if ((ps.h | ps.w | os.h | os.w) % 4) continue;
+            f.in_fold = true;
+            for (int i = 0; i < 4; ++i) f.in_fold_pad[i] = pad->pads[i];
+            f.in_fold_mode = pad->sub;
+            f.in_fold_value = pad->alpha;
+            f.in[0] = v;
+            f.conv_mode = k::CONV_MODE_IM2COL;
+            pad->removed = true;
+            norm->unfold_w = os.w / 4;
+            norm->unfold_f = 4;
+            std::vector<float> bf(size_t(16) * f.c_out);
+            for (int ph = 0; ph < 16; ++ph) for (int co = 0; co < f.c_out; ++co) bf[size_t(ph) * f.c_out + co] = f.bias[size_t(co)];
+            f.bias.swap(bf);
+        }
+    }
     // Width-folded input convolutions: a stride-1, unpadded convolution on at most 32 input channels whose packed filter rows leave
     // most of every 128-byte TMA pixel row empty (9x9 on 3 channels: 18 k-blocks per 128 output pixels, 72 of 128 bytes used in one
     // half of them and 16 in the other) reads and writes the SAME NHWC buffers re-interpreted with F = 64 / pitch neighbouring pixels
@@ -505,7 +538,7 @@ int ONNXGraph::build() {
     // cost tensor time the layer has to spare.  No kernel and no layout change: weights, bias and the problem's dimensions only.
     if (!getenv("SMELTER_NO_WIDTH_FOLD")) {
         for (auto& f : filters_) {
-            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.upfold || f.groups != 1 || f.residual >= 0) continue;
+            if (f.removed || f.kind != FilterKind::Conv || f.is_gemm || f.transposed || f.s2d || f.phase_fold || f.upfold || f.in_fold || f.groups != 1 || f.residual >= 0) continue;
             if (f.stride_h != 1 || f.stride_w != 1 || f.dil_h != 1 || f.dil_w != 1 || f.pads[0] || f.pads[1] || f.pads[2] || f.pads[3]) continue;
             const int cp = round_up(f.c_in_g, 8);
             if (cp > 32 || f.k_w < 3 || f.c_out % 8) continue;
@@ -559,16 +592,31 @@ int ONNXGraph::build() {
     // tensor less per Pad.  The apply pass stores the interior at its padded position; the border pixels (a few hundred to a few
     // thousand) are extra tasks that re-read their mirror source -- not a per-pixel test on the latency-bound apply loop.
     if (!getenv("SMELTER_NO_NORM_PAD")) {
-        for (auto& pd : filters_) {
-            if (pd.removed || pd.kind != FilterKind::Pad || pd.sub != k::PAD_REFLECT || pd.pad_add) continue;
+        for (size_t pi = 0; pi < filters_.size(); ++pi) {
+            Filter& pd = filters_[pi];
+            if (pd.removed || pd.kind != FilterKind::Pad || (pd.sub != k::PAD_REFLECT && pd.sub != k::PAD_EDGE) || pd.pad_add) continue;
             Filter* nm = nullptr;
             for (auto& g : filters_) if (!g.removed && g.out == pd.in[0] && g.kind == FilterKind::InstanceNorm) nm = &g;
-            if (!nm || nm->norm_padded || consumers_of(nm->out) != 1 || nm->out == output_value_) continue;
+            if (!nm || nm->norm_padded || nm->out == output_value_) continue;
+            // other readers of the norm's result (a skip connection) get the plain image as a second store; they must run after the Pad
+            bool ok = true;
+            int others = 0;
+            for (size_t gi = 0; gi < filters_.size(); ++gi) {
+                const Filter& g = filters_[gi];
+                if (g.removed || gi == pi) continue;
+                bool reads = g.residual == nm->out;
+                for (int i : g.in) reads = reads || i == nm->out;
+                if (reads) { ++others; ok = ok && gi > pi; }
+            }
+            for (const auto& v : values_) ok = ok && v.alias_of != nm->out;
+            if (!ok || others > 1) continue;
             const ImageShape& s = values_[size_t(nm->out)].shape;
-            if (pd.pads[0] >= s.h || pd.pads[2] >= s.h || pd.pads[1] >= s.w || pd.pads[3] >= s.w) continue;
+            if (pd.sub == k::PAD_REFLECT && (pd.pads[0] >= s.h || pd.pads[2] >= s.h || pd.pads[1] >= s.w || pd.pads[3] >= s.w)) continue;
             for (int i = 0; i < 4; ++i) nm->norm_pad[i] = pd.pads[i];
             nm->norm_s2d = pd.s2d_out;
+            nm->norm_pad_mode = pd.sub;
             nm->norm_padded = true;
+            nm->out2 = others ? nm->out : -1;
             nm->out = pd.out;
             pd.removed = true;
         }
@@ -597,6 +645,7 @@ int ONNXGraph::upload_weights() {
                 wbytes = size_t(F * F * f.c_out) * ((f.k_h + 2 * F - 2) / F) * ((f.k_w + 2 * F - 2) / F) * F * F * round_up(c_in, 8) * 2;
             }
             else if (f.upfold) wbytes = size_t(4 * f.c_out) * 9 * round_up(c_in, 8) * 2;
+            else if (f.in_fold) wbytes = size_t(16 * f.c_out) * ((f.k_h + 6) / 4) * ((f.k_w + 6) / 4) * 64 * 2;
             else if (f.wfold) wbytes = size_t(f.wfold) * f.c_out * f.k_h * ((f.k_w + 2 * f.wfold - 2) / f.wfold) * f.wfold * round_up(c_in, 8) * 2;
             else wbytes = size_t(f.c_out) * f.k_h * f.k_w * round_up(c_in, 8) * 2;
             f.w_off = total; total = align(total + wbytes);
@@ -617,6 +666,7 @@ int ONNXGraph::upload_weights() {
             if (f.conv_mode == 4) pack_weights_depthwise(f.w.data(), f.c_out, f.k_h, f.k_w, round_up(f.c_out, 8), w);
             else if (f.s2d) pack_weights_s2d(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, w);
             else if (f.phase_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), f.phase_fold, w);
+            else if (f.in_fold) pack_weights_phase(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, 4, 4, w);
             else if (f.upfold) pack_weights_upfold(f.w.data(), f.c_out, c_in, round_up(c_in, 8), w);
             else if (f.wfold) pack_weights_wfold(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), f.wfold, w);
             else pack_weights_ohwi(f.w.data(), f.c_out, c_in, f.k_h, f.k_w, round_up(c_in, 8), w);
@@ -723,6 +773,11 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             q.h = (is.h - 1) * f.tr_stride_h + 1 + f.pads[0] + f.pads[2];
             q.w = (is.w - 1) * f.tr_stride_w + 1 + f.pads[1] + f.pads[3];
             q.pad_t = q.pad_l = q.pad_b = q.pad_r = 0;
+        } else if (f.in_fold) {  // [N, Hp/4, Wp/4, 16 x 4] -> [N, P/4, Q/4, 16 Cout], ((k + 6) / 4)^2 taps
+            q.h = (is.h + f.in_fold_pad[0] + f.in_fold_pad[2]) / 4; q.w = (is.w + f.in_fold_pad[1] + f.in_fold_pad[3]) / 4;
+            q.c_in = 64; q.c_in_pitch = 64;
+            q.c_out = 16 * f.c_out; q.c_out_pitch = 16 * f.c_out;
+            q.k_h = (f.k_h + 6) / 4; q.k_w = (f.k_w + 6) / 4;
         } else if (f.upfold) {  // [N, H + 2, W + 2, Cin] -> [N, H, W, 4 Cout]: the 2H x 2W output with its pixels in (y, x, phase) order
             q.c_out = 4 * f.c_out; q.c_out_pitch = 4 * f.c_out;
         } else if (f.wfold) {  // the same buffers with wfold neighbouring pixels as one: [N, H, W/F, F Cin] -> [N, P, Q/F, F Cout]
@@ -828,12 +883,14 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         if (readers == 1 && v != out_root && only->kind == FilterKind::Conv && only->conv_mode == k::CONV_MODE_PACKED_ROW && root_of(only->in[0]) == v &&
             (only->s2d || only->pads[0] || only->pads[1] || only->pads[2] || only->pads[3]))
             stem_of[size_t(v)] = only;
+        if (readers == 1 && only->kind == FilterKind::Conv && only->in_fold && only->in[0] == v) stem_of[size_t(v)] = only;
     }
     auto input_bytes = [&](int v) {
         const Filter* f = stem_of[size_t(v)];
         if (!f) return bytes_of(v);
         const ImageShape& s = values_[size_t(v)].shape;
         if (f->s2d) return size_t(N) * (f->s2d_h / 2) * (f->s2d_w / 2) * 16 * 2;
+        if (f->in_fold) return size_t(N) * ((s.h + f->in_fold_pad[0] + f->in_fold_pad[2]) / 4) * ((s.w + f->in_fold_pad[1] + f->in_fold_pad[3]) / 4) * 64 * 2;
         return size_t(N) * (s.h + f->pads[0] + f->pads[2]) * (s.w + f->pads[1] + f->pads[3]) * round_up(s.c, 8) * 2;
     };
     // graph inputs: NHWC copies produced by the boundary conversion
@@ -932,6 +989,16 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         const int cp = pitch_of(v);
         int pt = 0, pl = 0, pb = 0, pr = 0;
         if (const Filter* sf = stem_of[size_t(v)]) { pt = sf->pads[0]; pl = sf->pads[1]; pb = sf->pads[2]; pr = sf->pads[3]; }
+        if (const Filter* sf = stem_of[size_t(v)]; sf && sf->in_fold) {
+            const int h4 = (s.h + sf->in_fold_pad[0] + sf->in_fold_pad[2]) / 4, w4 = (s.w + sf->in_fold_pad[1] + sf->in_fold_pad[3]) / 4;
+            const int fpt = sf->in_fold_pad[0], fpl = sf->in_fold_pad[1], mode = sf->in_fold_mode;
+            const float value = sf->in_fold_value;
+            add_step("nchw_to_s2d4+pad " + values_[size_t(v)].name,
+                     [=](cudaStream_t st) { return k::nchw_to_s2d4(*slot, dst, N, s.c, s.h, s.w, fpt, fpl, h4, w4, mode, value, st); }, 0,
+                     double(N) * (double(s.h) * s.w * s.c + double(h4) * w4 * 64) * 2);
+            plan->steps.back().boundary = true;
+            continue;
+        }
         if (const Filter* sf = stem_of[size_t(v)]; sf && sf->s2d) {
             const int h2 = sf->s2d_h / 2, w2 = sf->s2d_w / 2;
             add_step("nchw_to_s2d+pad0 " + values_[size_t(v)].name,
@@ -1017,7 +1084,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 std::string cerr;
                 if (!k::conv_tc_prepare(L.get(), q, num_sms, &cerr)) return fail(SMELTER_ERR_GRAPH_INTERNAL, name + ": " + cerr);
                 L->balanced_grid = cfg_.sm_share >= 2 ? 1 : 0;
-                const char* mode_name = f.upfold ? (f.conv_mode == k::CONV_MODE_PACKED_ROW ? "rows/upsample-fold" : "im2col/upsample-fold") : f.wfold ? "im2col/width-fold" : f.phase_fold == 4 ? "im2col/phase-fold4" : f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
+                const char* mode_name = f.in_fold ? "im2col/input-fold4" : f.upfold ? (f.conv_mode == k::CONV_MODE_PACKED_ROW ? "rows/upsample-fold" : "im2col/upsample-fold") : f.wfold ? "im2col/width-fold" : f.phase_fold == 4 ? "im2col/phase-fold4" : f.phase_fold ? "im2col/phase-fold" : f.conv_mode == k::CONV_MODE_TILED ? "tiled" : f.conv_mode == k::CONV_MODE_IM2COL ? "im2col" : f.s2d ? "rows/s2d" : "rows";
                 add_step(std::string(L->pair ? "conv_pair[" : "conv_igemm[") + mode_name + ",bn" + std::to_string(L->block_n) + (L->splits > 1 ? ",k/" + std::to_string(L->splits) : "") +
                              "]" + suffix + " " + name,
                          [L](cudaStream_t st) { return k::conv_tc_launch(*L, st); }, flops + side_flops,
@@ -1041,11 +1108,16 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 const int group_size = f.sub > 0 ? f.sub : 1, channels = is.c;
                 k::NormStore store;
                 store.unfold_w = f.unfold_w;
+                store.unfold_f = f.unfold_f;
                 store.h = is.h; store.w = is.w;
-                if (f.norm_padded) { store.pad_t = f.norm_pad[0]; store.pad_l = f.norm_pad[1]; store.pad_b = f.norm_pad[2]; store.pad_r = f.norm_pad[3]; store.s2d = f.norm_s2d; }
+                if (f.norm_padded) {
+                    store.pad_t = f.norm_pad[0]; store.pad_l = f.norm_pad[1]; store.pad_b = f.norm_pad[2]; store.pad_r = f.norm_pad[3];
+                    store.s2d = f.norm_s2d; store.pad_mode = f.norm_pad_mode;
+                    store.plain = f.out2 >= 0 ? ptr_of(f.out2) : nullptr;
+                }
                 std::string what = group_size > 1 ? "group_norm" : "instance_norm";
                 if (f.unfold_w) what += "+unfold";
-                if (f.norm_padded) what += f.norm_s2d ? "+pad+s2d" : "+pad";
+                if (f.norm_padded) what += f.norm_s2d ? "+pad+s2d" : f.out2 >= 0 ? "+pad+plain" : "+pad";
                 add_step(what + " " + name,
                          [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels, &store); }, 0,
                          io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)

@@ -121,6 +121,14 @@ struct Filter {
     // multiply-adds, no upsampled tensor.  Its output [H, W, 4, Cout] is the 2H x 2W image in a permuted pixel order -- which the
     // normalisation's statistics do not see; its store un-permutes (unfold_w = W).  engine.cc "upsample-folded".
     bool upfold = false;           // Conv
+    // Network-input convolution behind a Pad (TransformerNet's 9x9 3 -> 32 layer, k = 1 mod 4, at most 4 input channels): the boundary
+    // conversion writes the padded image as its 4 x 4 space-to-depth fold with 4 channels per pixel (64 dense channels), the
+    // convolution runs on it with ((k + 6) / 4)^2 taps and the 16 output phases as 16 * Cout GEMM columns, the instance norm behind it
+    // un-permutes (unfold_f = 4).  in_fold_pad / in_fold_mode / in_fold_value: the absorbed Pad.
+    bool in_fold = false;
+    int in_fold_pad[4] = {0, 0, 0, 0}, in_fold_mode = 0;
+    float in_fold_value = 0.f;
+    int unfold_f = 2;              // InstanceNorm: fold factor of the permuted pixels (2 or 4)
     int unfold_w = 0;              // InstanceNorm behind an upsample-folded convolution: low-resolution width
     // InstanceNorm whose only reader was a reflection Pad: the norm writes the padded image itself (interior at an offset, the border
     // pixels from their mirror sources, kernels.h NormStore) -- `out` is the Pad's output, the Pad is gone.  norm_s2d = its s2d_out.
@@ -129,7 +137,7 @@ struct Filter {
     bool pad_add = false;
     int out2 = -1;
     int norm_pad[4] = {0, 0, 0, 0};
-    int norm_s2d = 0;
+    int norm_s2d = 0, norm_pad_mode = 1;  // k::PAD_REFLECT or k::PAD_EDGE; out2 >= 0: the un-padded result has another reader and is stored too
     bool norm_padded = false;
     int s2d_h = 0, s2d_w = 0;      // padded input size (even) that is folded: the s2d image is s2d_h/2 x s2d_w/2
 };

@@ -310,6 +310,48 @@ __global__ void __launch_bounds__(kThreads) nchw_to_s2d_kernel(const __half* __r
     }
 }
 
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+    // ONNX 'reflect' (no edge repeat); pads < n assumed
+    if (i < 0) i = -i;
+    if (i >= n) i = 2 * (n - 1) - i;
+    return i;
+}
+
+// Network input of an input-folded convolution (engine.h Filter::in_fold): padded image folded 4 x 4 with 4 channels per pixel.  One
+// thread per (folded pixel, dy): 4 * c scalar reads of one source row (neighbouring threads read neighbouring pixels), 32 bytes out.
+__global__ void __launch_bounds__(kThreads) nchw_to_s2d4_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c, int h,
+                                                               int w, int pt, int pl, int h4, int w4, int mode, float value) {
+    const size_t total = size_t(n) * h4 * w4 * 4;
+    const size_t plane = size_t(h) * w;
+    const __half fill = __float2half(value);
+    for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
+        const int dy = int(i & 3);
+        const size_t fp = i >> 2;
+        const int x4 = int(fp % w4);
+        const int y4 = int((fp / w4) % h4);
+        const int img = int(fp / (size_t(w4) * h4));
+        const __half* sp = src + size_t(img) * c * plane;
+        int sy = 4 * y4 + dy - pt;
+        bool row_inside = sy >= 0 && sy < h;
+        if (mode == PAD_REFLECT) { sy = reflect_idx(sy, h); row_inside = true; }
+        else if (mode == PAD_EDGE) { sy = min(max(sy, 0), h - 1); row_inside = true; }
+        Half8 v[2];
+        __half* hv = reinterpret_cast<__half*>(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hv[j] = __float2half(0.f);
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            int sx = 4 * x4 + dx - pl;
+            bool inside = row_inside && sx >= 0 && sx < w;
+            if (mode == PAD_REFLECT) { sx = reflect_idx(sx, w); inside = true; }
+            else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
+            for (int ch = 0; ch < c; ++ch) hv[dx * 4 + ch] = inside ? sp[size_t(ch) * plane + size_t(sy) * w + sx] : fill;
+        }
+        st8(dst + i * 16, v[0]);
+        st8(dst + i * 16 + 8, v[1]);
+    }
+}
+
 // ConvTranspose = stride-1 convolution over the zero-stuffed, bordered input (MPSCNNConvolutionTransposeNode's job, Converters.swift
 // :266-287).  One thread per destination (pixel, 8 channels): copies the source vector when the pixel sits on the stride lattice.
 __global__ void __launch_bounds__(kThreads) zero_stuff2d_kernel(const __half* __restrict__ x, __half* __restrict__ y, int n, int h, int w, int cp8,
@@ -462,13 +504,6 @@ __global__ void __launch_bounds__(kThreads) upsample_bilinear_kernel(const __hal
     }
 }
 
-__device__ __forceinline__ int reflect_idx(int i, int n) {
-    // ONNX 'reflect' (no edge repeat); pads < n assumed
-    if (i < 0) i = -i;
-    if (i >= n) i = 2 * (n - 1) - i;
-    return i;
-}
-
 // blockIdx.y = (image, output row): the source row is resolved once per block; threads walk (ox, channel group) of the row.
 // x2 != nullptr: the padded tensor is act(x + x2) (a residual Add in front of the Pad, engine.h Filter::pad_add); y_plain != nullptr:
 // the un-padded sum is stored as well (it has other readers).
@@ -564,19 +599,31 @@ __global__ void __launch_bounds__(kThreads) pad2d_kernel(const __half* __restric
 // Result of a phase-folded convolution -> NCHW: src [n, p2, q2, cp] holds, per folded pixel, channel (ey * F + ex) * c + co = output
 // channel co of full-resolution pixel (F * p2 + ey, F * q2 + ex).  One thread per folded pixel, q2 fastest: the F ex of a row are one
 // 32-bit (F = 2) or 64-bit (F = 4) store and neighbouring threads write neighbouring words.
-template <int F>
-__global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c, int p2,
+// C > 0: the channel count is a compile-time constant and the folded pixel (cp <= 64 halves) is read with 128-bit loads.
+template <int F, int C>
+__global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int n, int c_rt, int p2,
                                                                 int q2, int cp, long dst_image_pitch) {
     pdl_prologue();
     const size_t total = size_t(n) * p2 * q2;
     const int q = F * q2;
+    const int c = C > 0 ? C : c_rt;
     for (size_t i = blockIdx.x * size_t(blockDim.x) + threadIdx.x; i < total; i += size_t(gridDim.x) * blockDim.x) {
         const int x2 = int(i % q2);
         const int y2 = int((i / q2) % p2);
         const int img = int(i / (size_t(q2) * p2));
         const __half* sp = src + i * cp;
         __half* dp = dst + size_t(img) * dst_image_pitch;
-        for (int co = 0; co < c; ++co)
+        constexpr int kVecs = C > 0 ? (F * F * C + 7) / 8 : 1;
+        Half8 pix[kVecs];
+        if constexpr (C > 0) {
+#pragma unroll
+            for (int v = 0; v < kVecs; ++v) pix[v] = ld8(sp + v * 8);
+            sp = reinterpret_cast<const __half*>(pix);
+        }
+#pragma unroll
+        for (int co = 0; co < (C > 0 ? C : 1024); ++co) {
+            if (co >= c) break;
+#pragma unroll
             for (int ey = 0; ey < F; ++ey) {
                 __half* d = dp + (size_t(co) * (F * p2) + F * y2 + ey) * q + F * x2;
                 const __half2 v0 = __halves2half2(sp[(ey * F + 0) * c + co], sp[(ey * F + 1) * c + co]);
@@ -590,6 +637,7 @@ __global__ void __launch_bounds__(kThreads) phase_to_nchw_kernel(const __half* _
                     *reinterpret_cast<uint2*>(d) = w;
                 }
             }
+        }
     }
 }
 
@@ -712,6 +760,65 @@ __global__ void __launch_bounds__(128) nchw_to_s2d_rows_kernel(const __half* __r
     }
 }
 
+// Row-staged variant: one block per (image, folded row): its 4 * c source rows (reflected / clamped as the pad mode says) go to
+// shared memory with coalesced 128-bit loads, then one thread per (folded pixel, dy) assembles 32 bytes.
+__global__ void __launch_bounds__(kThreads) nchw_to_s2d4_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int c, int h, int w,
+                                                                    int pt, int pl, int h4, int w4, int mode, float value) {
+    extern __shared__ __align__(16) __half rows4[];  // [4][c][w]
+    const int y4 = blockIdx.x, img = blockIdx.y;
+    const size_t plane = size_t(h) * w;
+    const int vec_per_row = w / 8;
+    const __half fill = __float2half(value);
+    uint4 fill4;
+    {
+        const __half2 f2 = __halves2half2(fill, fill);
+        const unsigned u = *reinterpret_cast<const unsigned*>(&f2);
+        fill4 = make_uint4(u, u, u, u);
+    }
+    for (int i = threadIdx.x; i < 4 * c * vec_per_row; i += blockDim.x) {
+        const int r = i / vec_per_row, vx = i - r * vec_per_row;
+        const int dy = r / c, ch = r - dy * c;
+        int sy = 4 * y4 + dy - pt;
+        bool inside = sy >= 0 && sy < h;
+        if (mode == PAD_REFLECT) { sy = reflect_idx(sy, h); inside = true; }
+        else if (mode == PAD_EDGE) { sy = min(max(sy, 0), h - 1); inside = true; }
+        uint4 v = fill4;
+        if (inside) v = __ldg(reinterpret_cast<const uint4*>(src + (size_t(img) * c + ch) * plane + size_t(sy) * w) + vx);
+        reinterpret_cast<uint4*>(rows4 + size_t(r) * w)[vx] = v;
+    }
+    __syncthreads();
+    __half* drow = dst + (size_t(img) * h4 + y4) * w4 * 64;
+    for (int t = threadIdx.x; t < 4 * w4; t += blockDim.x) {
+        const int dy = t & 3, x4 = t >> 2;
+        Half8 v[2];
+        __half* hv = reinterpret_cast<__half*>(v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) hv[j] = __float2half(0.f);
+#pragma unroll
+        for (int dx = 0; dx < 4; ++dx) {
+            int sx = 4 * x4 + dx - pl;
+            bool inside = sx >= 0 && sx < w;
+            if (mode == PAD_REFLECT) { sx = reflect_idx(sx, w); inside = true; }
+            else if (mode == PAD_EDGE) { sx = min(max(sx, 0), w - 1); inside = true; }
+            for (int ch = 0; ch < c; ++ch) hv[dx * 4 + ch] = inside ? rows4[size_t(dy * c + ch) * w + sx] : fill;
+        }
+        st8(drow + size_t(t) * 16, v[0]);
+        st8(drow + size_t(t) * 16 + 8, v[1]);
+    }
+}
+
+cudaError_t nchw_to_s2d4(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h4, int w4, int mode, float value,
+                         cudaStream_t s) {
+    if (c < 1 || c > 4 || 4 * h4 < h + pad_t || 4 * w4 < w + pad_l) return cudaErrorInvalidValue;
+    if (mode == PAD_REFLECT && (pad_t >= h || pad_l >= w || 4 * h4 - h - pad_t >= h || 4 * w4 - w - pad_l >= w)) return cudaErrorInvalidValue;
+    const size_t smem = size_t(4) * c * w * sizeof(__half);
+    if (w % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && smem <= 48 * 1024 && n <= 65535) {
+        nchw_to_s2d4_rows_kernel<<<dim3(unsigned(h4), unsigned(n)), kThreads, smem, s>>>(src, dst, c, h, w, pad_t, pad_l, h4, w4, mode, value);
+        return cudaGetLastError();
+    }
+    nchw_to_s2d4_kernel<<<grid_for(size_t(n) * h4 * w4 * 4), kThreads, 0, s>>>(src, dst, n, c, h, w, pad_t, pad_l, h4, w4, mode, value);
+    return cudaGetLastError();
+}
 cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s) {
     if (c < 1 || c > 4) return cudaErrorInvalidValue;
     const size_t smem = size_t(2) * c * w * sizeof(__half);
@@ -737,8 +844,11 @@ cudaError_t nhwc_to_nchw(const __half* src, __half* dst, int n, int c, int h, in
 }
 cudaError_t phase_to_nchw(const __half* src, __half* dst, int n, int c, int p2, int q2, int cp, long dst_image_pitch, cudaStream_t s, int fold) {
     if (fold != 2 && fold != 4) return cudaErrorInvalidValue;
-    if (fold == 2) (void)launch_pdl(phase_to_nchw_kernel<2>, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
-    else (void)launch_pdl(phase_to_nchw_kernel<4>, dim3(grid_for(size_t(n) * p2 * q2)), dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    const dim3 grid(grid_for(size_t(n) * p2 * q2));
+    if (fold == 2 && c == 3) (void)launch_pdl(phase_to_nchw_kernel<2, 3>, grid, dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    else if (fold == 4 && c == 3) (void)launch_pdl(phase_to_nchw_kernel<4, 3>, grid, dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    else if (fold == 2) (void)launch_pdl(phase_to_nchw_kernel<2, 0>, grid, dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
+    else (void)launch_pdl(phase_to_nchw_kernel<4, 0>, grid, dim3(kThreads), s, src, dst, n, c, p2, q2, cp, dst_image_pitch);
     return cudaGetLastError();
 }
 cudaError_t upsample2d(const __half* x, __half* y, int n, int h, int w, int cp, int scale_h, int scale_w, int mode, int align_corners,

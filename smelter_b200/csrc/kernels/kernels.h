@@ -22,6 +22,11 @@ enum UpsampleMode : int { UP_NEAREST = 0, UP_BILINEAR = 1 };
 // Boundary layout conversion.  dst is [N, H+pt+pb, W+pl+pr, cp] with zero borders and zero padded channels.
 // NCHW (c <= 4) -> zero-padded, 2x2 space-to-depth NHWC with 16-channel pixels: out[n][y][x][(dy*2+dx)*c + ch] = in[n][ch][2y+dy-pad_t][2x+dx-pad_l]
 cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s);
+// NCHW source (c <= 4) -> the 4 x 4 space-to-depth fold [n, h4, w4, 16 x 4] of its padded image (PadMode `mode`, pads top / left; the
+// bottom / right pads follow from h4, w4): channel (dy * 4 + dx) * 4 + ch of folded pixel (y4, x4) = padded pixel (4 y4 + dy, 4 x4 + dx).
+// The input layout of an input-folded convolution (engine.h Filter::in_fold).
+cudaError_t nchw_to_s2d4(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h4, int w4, int mode, float value,
+                         cudaStream_t s);
 cudaError_t nchw_to_nhwc(const __half* src, __half* dst, int n, int c, int h, int w, int cp, int pad_t, int pad_l, int pad_b,
                          int pad_r, cudaStream_t s);
 // dst[n * dst_image_pitch + (c*H + h)*W + w] = src[n,h,w,c]
@@ -63,8 +68,11 @@ int instance_norm_launches(int n, int hw, int cp, int group_size = 1);  // kerne
 struct NormStore {
     int unfold_w = 0;  // W > 0: x holds a 2H x 2W image as [H, W, 2 x 2 phases] pixels (hw = 4 H W, the output of an upsample-folded
                        // convolution, engine.h Filter::upfold); the store goes to plain row-major pixels
+    int unfold_f = 2;  // fold factor F of those pixels: [H, W, F x F phases] of an F H x F W image (2, or 4 behind an input-folded convolution)
     int h = 0, w = 0;  // image size as stored (after un-folding, h * w == hw); needed with padding
-    int pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0;  // the reflection Pad behind the norm, written by the norm: y is the padded image
+    int pad_t = 0, pad_l = 0, pad_b = 0, pad_r = 0;  // the Pad behind the norm, written by the norm: y is the padded image
+    int pad_mode = PAD_REFLECT;                      // PAD_REFLECT or PAD_EDGE
+    __half* plain = nullptr;  // with padding: the un-padded result is stored here as well (it has other readers)
     int s2d = 0;       // ... in pad2d's F x F space-to-depth layout (F = 2 or 4)
     bool padded() const { return pad_t || pad_l || pad_b || pad_r || s2d; }
 };

@@ -491,17 +491,18 @@ __global__ void __launch_bounds__(kThreads) inorm_finalize_kernel(const float* _
 }
 // ---- where a normalised pixel goes (kernels.h NormStore) ----
 struct NormDst {
-    int unfold_w, h, w, pt, pl, ho, wo, s2d;  // ho == 0: no padding
+    int unfold_w, unfold_f, h, w, pt, pl, ho, wo, s2d, edge;  // ho == 0: no padding; unfold_f: 2 or 4; edge: clamp instead of reflect
 };
 __device__ __forceinline__ int reflect_at(int i, int n) {  // ONNX 'reflect' (no edge repeat), pads < n
     if (i < 0) i = -i;
     if (i >= n) i = 2 * (n - 1) - i;
     return i;
 }
-// pixel p = (y * w + x) * 4 + ey * 2 + ex of an upsample-folded convolution's output -> row-major pixel (2y + ey, 2x + ex) of the 2h x 2w image
-__device__ __forceinline__ unsigned unfold_pixel(unsigned p, unsigned w) {
-    const unsigned ph = p & 3u, t = p >> 2, yy = t / w, xx = t - yy * w;
-    return (2u * yy + (ph >> 1)) * (2u * w) + 2u * xx + (ph & 1u);
+// pixel p = (y * w + x) * F^2 + ey * F + ex of a phase-column convolution's output (upsample-folded: F = 2, input-folded: F = 4) ->
+// row-major pixel (F y + ey, F x + ex) of the F h x F w image
+__device__ __forceinline__ unsigned unfold_pixel(unsigned p, unsigned w, unsigned f) {
+    const unsigned sh = f == 4u ? 2u : 1u, ph = p & (f * f - 1u), t = p >> (2u * sh), yy = t / w, xx = t - yy * w;
+    return (f * yy + (ph >> sh)) * (f * w) + f * xx + (ph & (f - 1u));
 }
 // 16-byte vector index (vector 0 of the pixel) of padded pixel (oy, ox)
 __device__ __forceinline__ size_t padded_vec(const NormDst& d, unsigned oy, unsigned ox, unsigned cp8) {
@@ -509,9 +510,9 @@ __device__ __forceinline__ size_t padded_vec(const NormDst& d, unsigned oy, unsi
     const unsigned sh = d.s2d == 4 ? 2u : 1u, sm = unsigned(d.s2d) - 1u;
     return ((size_t(oy >> sh) * (unsigned(d.wo) >> sh) + (ox >> sh)) * unsigned(d.s2d * d.s2d) + ((oy & sm) * unsigned(d.s2d) + (ox & sm))) * cp8;
 }
-// ... of source pixel p (storage order of x)
-__device__ __forceinline__ size_t norm_dst_vec(const NormDst& d, unsigned p, unsigned cp8) {
-    const unsigned q = d.unfold_w ? unfold_pixel(p, unsigned(d.unfold_w)) : p;
+// ... of source pixel p (storage order of x); q = its row-major index in the un-padded image
+__device__ __forceinline__ size_t norm_dst_vec(const NormDst& d, unsigned p, unsigned cp8, unsigned& q) {
+    q = d.unfold_w ? unfold_pixel(p, unsigned(d.unfold_w), unsigned(d.unfold_f)) : p;
     if (!d.ho) return size_t(q) * cp8;
     const unsigned yy = q / unsigned(d.w), xx = q - yy * unsigned(d.w);
     return padded_vec(d, yy + unsigned(d.pt), xx + unsigned(d.pl), cp8);
@@ -529,13 +530,19 @@ __device__ __forceinline__ void ring_pixel(const NormDst& d, unsigned j, unsigne
         const unsigned t = j - top - bottom, side = unsigned(d.wo - d.w), r = t / side, kk = t - r * side;
         oy = unsigned(d.pt) + r; ox = kk < unsigned(d.pl) ? kk : unsigned(d.w) + kk;
     }
-    const unsigned sy = unsigned(reflect_at(int(oy) - d.pt, d.h)), sx = unsigned(reflect_at(int(ox) - d.pl, d.w));
-    src = d.unfold_w ? ((sy >> 1) * unsigned(d.unfold_w) + (sx >> 1)) * 4u + (sy & 1u) * 2u + (sx & 1u) : sy * unsigned(d.w) + sx;
+    const unsigned sy = unsigned(d.edge ? min(max(int(oy) - d.pt, 0), d.h - 1) : reflect_at(int(oy) - d.pt, d.h));
+    const unsigned sx = unsigned(d.edge ? min(max(int(ox) - d.pl, 0), d.w - 1) : reflect_at(int(ox) - d.pl, d.w));
+    if (d.unfold_w) {
+        const unsigned f = unsigned(d.unfold_f), sh = f == 4u ? 2u : 1u;
+        src = ((sy >> sh) * unsigned(d.unfold_w) + (sx >> sh)) * (f * f) + (sy & (f - 1u)) * f + (sx & (f - 1u));
+    } else {
+        src = sy * unsigned(d.w) + sx;
+    }
 }
 // pass 2: y = act(x * scale + shift).  Blocks past `chunks` write the reflection border (NormStore::pad_*): one task per (border
 // pixel, 8 channels), source pixel re-read.
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
-                                                              int hw, int cp8, int act, NormDst dst, int chunks) {
+                                                              int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain) {
     pdl_prologue();
     const int img = blockIdx.y;
     const float* sm = params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
@@ -550,7 +557,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
     __half* yb = y + size_t(img) * (dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) * 8;
     const size_t base = size_t(ring ? int(blockIdx.x) - chunks : int(blockIdx.x)) * (kThreads * U) + threadIdx.x;
     Half8 v[U];
-    size_t o[U];
+    size_t o[U], o2[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const size_t i = base + u * kThreads;
@@ -561,7 +568,9 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
                 o[u] = i;
             } else {
                 const unsigned pix = unsigned(i / size_t(cp8));
-                o[u] = norm_dst_vec(dst, pix, unsigned(cp8)) + (i - size_t(pix) * cp8);
+                unsigned q;
+                o[u] = norm_dst_vec(dst, pix, unsigned(cp8), q) + (i - size_t(pix) * cp8);
+                o2[u] = size_t(q) * cp8 + (i - size_t(pix) * cp8);
             }
         } else {
             const unsigned j = unsigned(i / size_t(cp8)), g = unsigned(i - size_t(j) * cp8);
@@ -595,6 +604,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
             f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
         }
         st8(yb + o[u] * 8, pack(f));
+        if (y_plain && !ring) st8(y_plain + (size_t(img) * n8 + o2[u]) * 8, pack(f));
     }
 }
 
@@ -606,7 +616,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
 //      Thread t: vector (t & 1) of the slab (8 channels), pixel lane t >> 1; 32 contiguous bytes per pixel.
 __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ gamma,
                                                                 const float* __restrict__ beta, int hw, int cp8, float eps, int act, int group_size,
-                                                                int channels, NormDst dst) {
+                                                                int channels, NormDst dst, __half* __restrict__ y_plain) {
     pdl_prologue();
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
@@ -728,8 +738,10 @@ __global__ void __launch_bounds__(kThreads) inorm_cluster_kernel(const __half* _
                         const float r = fmaf(f[j], sc[j], sh[j]);
                         f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
                     }
-                    const size_t o = plain ? size_t(pix + u * kLanes) * cp8 : norm_dst_vec(dst, unsigned(pix + u * kLanes), unsigned(cp8));
+                    unsigned q = unsigned(pix + u * kLanes);
+                    const size_t o = plain ? size_t(q) * cp8 : norm_dst_vec(dst, q, unsigned(cp8), q);
                     st8(yb + o * 8, pack(f));
+                    if (y_plain) st8(y_plain + ((size_t(img) * hw + q) * cp8 + g0 + v) * 8, pack(f));
                 }
         }
         for (unsigned j = ring_j; j < nring; j += unsigned(csz * kLanes)) {  // the first one was requested before the apply loop
@@ -929,7 +941,9 @@ int inorm_cluster_size(int hw, int group_size) {
     int csz = inorm_max_cluster();
     while (csz > 1 && hw / csz < 512) csz >>= 1;
     // measured (TransformerNet, one image): 64 KiB per CTA (128 x 128 pixels) 16 -> 10 us against the three-launch form, but 256 KiB /
-    // 1 MiB per CTA (256^2, 512^2 pixels) 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches
+    // 1 MiB per CTA (256^2, 512^2 pixels) 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches.
+    // 1024-thread CTAs do not change that (256^2 x 64: 24 us either way, 512^2 x 32: 52 us against 30 us for three launches): a slab
+    // is 32 bytes of every 128-byte line, so the passes are bound by the lines a CTA touches, not by the bytes it keeps in flight.
     if (size_t(hw) / csz * 32 > (size_t(128) << 10)) return 0;
     return csz;
 }
@@ -968,17 +982,23 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
     if (group_size < 1) group_size = 1;
     if (channels <= 0) channels = cp;
     NormDst dst{};
+    __half* y_plain = store && store->padded() ? store->plain : nullptr;
     if (store) {
         if (x == y && (store->unfold_w || store->padded())) return cudaErrorInvalidValue;
-        if (store->unfold_w < 0 || (store->unfold_w && hw % (4 * store->unfold_w))) return cudaErrorInvalidValue;
+        if (store->unfold_f != 2 && store->unfold_f != 4) return cudaErrorInvalidValue;
+        if (store->unfold_w < 0 || (store->unfold_w && hw % (store->unfold_f * store->unfold_f * store->unfold_w))) return cudaErrorInvalidValue;
         dst.unfold_w = store->unfold_w;
+        dst.unfold_f = store->unfold_f;
         if (store->padded()) {
             if (store->h <= 0 || store->w <= 0 || size_t(store->h) * store->w != size_t(hw)) return cudaErrorInvalidValue;
-            if (store->unfold_w && 2 * store->unfold_w != store->w) return cudaErrorInvalidValue;
-            if (store->pad_t >= store->h || store->pad_b >= store->h || store->pad_l >= store->w || store->pad_r >= store->w) return cudaErrorInvalidValue;
+            if (store->unfold_w && store->unfold_f * store->unfold_w != store->w) return cudaErrorInvalidValue;
+            if (store->pad_mode == PAD_REFLECT && (store->pad_t >= store->h || store->pad_b >= store->h || store->pad_l >= store->w || store->pad_r >= store->w))
+                return cudaErrorInvalidValue;
             dst.h = store->h; dst.w = store->w; dst.pt = store->pad_t; dst.pl = store->pad_l;
             dst.ho = store->h + store->pad_t + store->pad_b; dst.wo = store->w + store->pad_l + store->pad_r;
             dst.s2d = store->s2d;
+            dst.edge = store->pad_mode == PAD_EDGE;
+            if (store->pad_mode != PAD_EDGE && store->pad_mode != PAD_REFLECT) return cudaErrorInvalidValue;
             if (dst.s2d && ((dst.s2d != 2 && dst.s2d != 4) || dst.ho % dst.s2d || dst.wo % dst.s2d)) return cudaErrorInvalidValue;
         }
     }
@@ -998,7 +1018,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         attr[1].val.programmaticStreamSerializationAllowed = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 2;
-        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, dst);
+        return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, dst, y_plain);
     }
     const int splits = instance_norm_splits(hw, cp);
     const int lanes = kThreads / cp8;
@@ -1025,7 +1045,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         if (e != cudaSuccess) return e;
         const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
         const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
-        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks);
+        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

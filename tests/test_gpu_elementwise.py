@@ -167,7 +167,8 @@ def test_instance_norm(ctx, shape, act):
     _close(y.toFloatArray(), ref, 4e-3)
 
 
-@pytest.mark.parametrize("shape,act", [((2, 128, 128, 128), 1), ((1, 24, 61, 47), 0), ((3, 40, 9, 200), 1), ((1, 32, 300, 300), 0)])
+@pytest.mark.parametrize("shape,act", [((2, 128, 128, 128), 1), ((1, 24, 61, 47), 0), ((3, 40, 9, 200), 1), ((1, 32, 300, 300), 0),
+                                       ((2, 64, 256, 256), 1), ((1, 32, 512, 512), 1), ((1, 8, 1024, 640), 0)])
 def test_instance_norm_cluster_form_matches_three_launch_form(ctx, shape, act, monkeypatch):
     """Small images take the one-launch cluster kernel (partial sums meet through distributed shared memory), large ones and
     SMELTER_NO_CLUSTER_NORM=1 the partials -> finalize -> apply form: same statistics in a different fixed summation order, so the

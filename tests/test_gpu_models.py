@@ -527,12 +527,16 @@ def test_upsample_folded_convolution(ctx, monkeypatch, c_in, c_out, hw, batch, c
     assert np.abs(out - plain).max() <= 6e-3 * max(1.0, np.abs(want).max())
 
 
-@pytest.mark.parametrize("c,hw,pad,k,batch,cluster", [(32, (16, 24), 1, 3, 2, True), (16, (20, 12), 4, 9, 1, True), (64, (9, 11), 2, 5, 3, True),
-                                                     (32, (16, 24), 1, 3, 2, False), (32, (24, 40), 4, 9, 2, False), (24, (7, 5), 3, 7, 1, True)])
-def test_reflection_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pad, k, batch, cluster):
-    """InstanceNorm (+ReLU) -> reflect Pad: the norm stores the padded image itself (interior at an offset, border pixels re-read
-    from their mirror sources; space-to-depth layout when the Pad feeds a phase-folded convolution) in both of its forms.  Same
-    result as the plan with the Pad kernel, bit for bit up to the convolution (same values, same positions), and the oracle."""
+@pytest.mark.parametrize("c,hw,pad,k,batch,cluster,mode,second_reader",
+                         [(32, (16, 24), 1, 3, 2, True, "reflect", False), (16, (20, 12), 4, 9, 1, True, "reflect", False),
+                          (64, (9, 11), 2, 5, 3, True, "reflect", True), (32, (16, 24), 1, 3, 2, False, "reflect", True),
+                          (32, (24, 40), 4, 9, 2, False, "reflect", False), (24, (7, 5), 3, 7, 1, True, "reflect", False),
+                          (32, (10, 14), 2, 5, 2, True, "edge", False), (16, (12, 8), 1, 3, 1, False, "edge", True)])
+def test_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pad, k, batch, cluster, mode, second_reader):
+    """InstanceNorm (+ReLU) -> reflect / edge Pad: the norm stores the padded image itself (interior at an offset, border pixels
+    re-read from their mirror sources; space-to-depth layout when the Pad feeds a phase-folded convolution; the plain image too while
+    a skip connection reads it) in both of its forms.  Same result as the plan with the Pad kernel, bit for bit (same values, same
+    positions), and the oracle."""
     from smelter_b200 import modelzoo
     from smelter_b200.api import Image, ONNXGraph
 
@@ -540,9 +544,11 @@ def test_reflection_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pa
     b = modelzoo.GraphBuilder(seed=c + pad, name="normpad")
     x = b.input("input", [batch, c, h, w])
     y = b.relu(b.instancenorm(b.conv(x, c, 3, 1, 1)))
-    c_out = 3 if k == 9 else 16
-    y = b.conv(b.pad(y, pad, "reflect"), c_out, k, 1, 0)
-    b.output(y, [batch, c_out, h, w])
+    c_out = 3 if k == 9 else c if second_reader else 16
+    t = b.conv(b.pad(y, pad, mode), c_out, k, 1, 0)
+    if second_reader:
+        t = b.add(t, y)
+    b.output(t, [batch, c_out, h, w])
     model = b.model().serialize()
     xin = np.random.default_rng(pad).standard_normal((batch, c, h, w)).astype(np.float16)
     want = _oracle(model, xin)
@@ -559,7 +565,7 @@ def test_reflection_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pa
 
     out, dump, n = run()
     assert "instance_norm+pad" in dump and "pad Pad" not in dump
-    assert ("+pad+s2d" in dump) == (k == 9)
+    assert ("+pad+s2d" in dump) == (k == 9) and ("+pad+plain" in dump) == second_reader
     assert np.abs(out.astype(np.float32) - want).max() <= TOL * max(1.0, np.abs(want).max())
     monkeypatch.setenv("SMELTER_NO_NORM_PAD", "1")
     plain, dump0, n0 = run()
@@ -607,3 +613,42 @@ def test_residual_add_inside_the_pad_kernel(ctx, monkeypatch, mode, relu, second
     plain, dump0, n0 = run()
     assert "add+pad" not in dump0 and n0 == n + 1
     assert np.array_equal(out.view(np.uint16), plain.view(np.uint16))
+
+
+@pytest.mark.parametrize("c_in,c_out,k,hw,mode,batch,cluster", [(3, 32, 9, (24, 40), "reflect", 2, True), (1, 8, 5, (16, 12), "constant", 1, True),
+                                                               (4, 16, 13, (32, 28), "edge", 3, True), (3, 32, 9, (32, 32), "reflect", 1, False)])
+def test_input_folded_convolution(ctx, monkeypatch, c_in, c_out, k, hw, mode, batch, cluster):
+    """graph input -> Pad -> Conv k x k (k = 1 mod 4) -> InstanceNorm (TransformerNet's input layer): the boundary conversion writes
+    the padded image folded 4 x 4 with 4 channels per pixel, the convolution computes the 16 output phases of a folded pixel as
+    GEMM columns, the norm un-permutes (engine.cc "input-folded").  Same result as the width-folded / plain plans and the oracle."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=k + c_in, name="infold")
+    x = b.input("input", [batch, c_in, h, w])
+    y = b.relu(b.instancenorm(b.conv(b.pad(x, k // 2, mode), c_out, k, 1, 0)))
+    y = b.conv(b.pad(y, 1, "reflect"), 8, 3, 1, 0)
+    b.output(y, [batch, 8, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(k).standard_normal((batch, c_in, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+    if not cluster:
+        monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+
+    def run():
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return out, dump, n
+
+    out, dump, n = run()
+    assert "input-fold4" in dump and "nchw_to_s2d4+pad" in dump and "instance_norm+unfold+pad" in dump
+    assert out.shape == want.shape
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+    monkeypatch.setenv("SMELTER_NO_INPUT_FOLD", "1")
+    plain, dump0, n0 = run()
+    assert "input-fold4" not in dump0 and n0 == n + 1
+    assert np.abs(out - plain).max() <= 6e-3 * max(1.0, np.abs(want).max())

@@ -893,6 +893,36 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         if (f->in_fold) return size_t(N) * ((s.h + f->in_fold_pad[0] + f->in_fold_pad[2]) / 4) * ((s.w + f->in_fold_pad[1] + f->in_fold_pad[3]) / 4) * 64 * 2;
         return size_t(N) * (s.h + f->pads[0] + f->pads[2]) * (s.w + f->pads[1] + f->pads[3]) * round_up(s.c, 8) * 2;
     };
+    // ---- instance-norm statistics accumulated by the producing convolution's epilogue ----
+    // Conv -> InstanceNormalization (the convolution's only reader): the two-CTA kernel adds the column sums / sums of squares of
+    // every output tile to per-image fp64 accumulators (ConvKernelParams::stats), and the norm is ONE pass over the tensor
+    // (k::instance_norm_from_stats) instead of statistics + apply.  Phase-column convolutions (upsample-, input-, width-folded)
+    // keep one accumulator per (phase, channel) column; the norm adds the phases up.  SMELTER_NO_CONV_STATS=1 turns it off.
+    std::vector<size_t> stats_off(filters_.size(), size_t(-1));  // by convolution, into plan->counters: [N][replicas][c_out_pitch][2] fp64, then the arrival counter
+    std::vector<int> stats_conv(filters_.size(), -1);            // by norm: the convolution that supplies its statistics
+    std::vector<int> stats_phases(filters_.size(), 1);
+    if (!getenv("SMELTER_NO_CONV_STATS")) {
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& f = filters_[fi];
+            if (f.removed || absorbed[fi] || f.kind != FilterKind::InstanceNorm || f.sub > 1 || f.in.empty()) continue;
+            const int src = root_of(f.in[0]);
+            const int ci = producer[size_t(src)];
+            if (ci < 0 || reads[size_t(src)] != 1 || src == out_root) continue;
+            const Filter& c = filters_[size_t(ci)];
+            if (c.removed || absorbed[size_t(ci)] || c.kind != FilterKind::Conv || c.is_gemm || c.transposed || c.conv_mode == 4 || c.phase_fold || c.residual >= 0 ||
+                side_of[size_t(ci)] >= 0 || c.act != k::ACT_NONE)
+                continue;
+            const int phases = c.in_fold ? 16 : c.upfold ? 4 : c.wfold ? c.wfold : 1;
+            if (phases > 1 && c.c_out % 8) continue;
+            const k::ConvTcProblem q = conv_problem(c, stem_of);
+            if (q.c_out_pitch != phases * round_up(values_[size_t(f.in[0])].shape.c, 8) || !k::conv_tc_stats_supported(q, num_sms)) continue;
+            stats_conv[fi] = ci;
+            stats_phases[fi] = phases * k::conv_tc_stats_reps(q);  // replicas are more column groups to the norm
+            stats_off[size_t(ci)] = counter_total;
+            counter_total += (size_t(N) * k::conv_tc_stats_reps(q) * q.c_out_pitch * 2 * sizeof(double) + sizeof(unsigned int) + 255) & ~size_t(255);
+        }
+    }
+
     // graph inputs: NHWC copies produced by the boundary conversion
     for (int v : input_values_) off[size_t(v)] = arena.alloc(input_bytes(v));
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
@@ -1061,6 +1091,10 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                     q.split_ws = reinterpret_cast<float*>(abase + scratch2[fi].off);
                     q.split_counters = reinterpret_cast<unsigned int*>(static_cast<char*>(plan->counters) + counter_off[fi]);
                 }
+                if (stats_off[fi] != size_t(-1)) {
+                    q.stats = reinterpret_cast<double*>(static_cast<char*>(plan->counters) + stats_off[fi]);
+                    suffix += "+stats";
+                }
                 if (f.transposed) {
                     __half* stuffed = reinterpret_cast<__half*>(abase + scratch[fi].off);
                     const Filter* fp = &f;
@@ -1118,6 +1152,17 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 std::string what = group_size > 1 ? "group_norm" : "instance_norm";
                 if (f.unfold_w) what += "+unfold";
                 if (f.norm_padded) what += f.norm_s2d ? "+pad+s2d" : f.out2 >= 0 ? "+pad+plain" : "+pad";
+                if (stats_conv[fi] >= 0) {  // statistics from the producing convolution: one pass
+                    const Filter& c = filters_[size_t(stats_conv[fi])];
+                    double* stats = reinterpret_cast<double*>(static_cast<char*>(plan->counters) + stats_off[size_t(stats_conv[fi])]);
+                    const int phases = stats_phases[fi];
+                    unsigned int* counter = reinterpret_cast<unsigned int*>(stats + size_t(N) * phases * icp * 2);
+                    (void)c;
+                    add_step(what + "<-stats " + name,
+                             [=](cudaStream_t st) { return k::instance_norm_from_stats(x, y, N, is.h * is.w, icp, ga, be, eps, act, stats, counter, phases, st, &store); }, 0,
+                             io_bytes);
+                    break;
+                }
                 add_step(what + " " + name,
                          [=](cudaStream_t st) { return k::instance_norm(x, y, N, is.h * is.w, icp, ga, be, eps, act, partials, st, group_size, channels, &store); }, 0,
                          io_bytes);  // algorithmic bytes: one read + one write (the second pass finds its images in L2)

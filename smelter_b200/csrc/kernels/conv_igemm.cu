@@ -845,6 +845,24 @@ bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms) {
     return pairable(alone) && pairable(q);
 }
 
+bool conv_tc_stats_supported(const ConvTcProblem& q, int num_sms) {
+    if (q.pair < 0 || (q.pair == 0 && getenv("SMELTER_NO_PAIR")) || num_sms < 2 || q.splits > 1 || q.residual || q.side_x || q.act != ACT_NONE) return false;
+    const int P = (q.h + q.pad_t + q.pad_b - q.dil_h * (q.k_h - 1) - 1) / q.stride_h + 1;
+    const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (q.k_w - 1) - 1) / q.stride_w + 1;
+    if (P <= 0 || Q <= 0 || (long(P) * Q) % 128) return false;
+    const ConvTcPlanInfo info = conv_tc_plan(q, num_sms);
+    return info.splits == 1 && (info.block_n == 64 || info.block_n == 128 || info.block_n == 256);
+}
+
+int conv_tc_stats_reps(const ConvTcProblem& q) {
+    const int P = (q.h + q.pad_t + q.pad_b - q.dil_h * (q.k_h - 1) - 1) / q.stride_h + 1;
+    const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (q.k_w - 1) - 1) / q.stride_w + 1;
+    const long tiles = long(P) * Q / kBlockM;
+    int reps = 1;
+    while (reps < 16 && reps * 2 * 16 <= tiles && long(q.c_out_pitch) * reps * 2 <= 1024) reps <<= 1;
+    return reps;
+}
+
 namespace {
 
 // A-operand map of a TILED / IM2COL / PACKED_ROW problem: [128 pixels x 64 channels] boxes, 128-byte swizzle.
@@ -1027,6 +1045,12 @@ bool conv_tc_prepare(ConvTcLaunch* L, const ConvTcProblem& q, int num_sms, std::
     // ---- B: packed weights [Cout][taps][kc]; two-CTA clusters (conv_pair.cu): each CTA loads half of the weight tile ----
     const bool want_pair = (q.pair > 0 || (q.pair == 0 && !getenv("SMELTER_NO_PAIR"))) && plan.splits == 1 && (block_n == 64 || block_n == 128 || block_n == 256) && num_sms >= 2;
     L->pair = want_pair ? 1 : 0;
+    if (q.stats) {
+        if (!want_pair || q.residual || q.act != ACT_NONE || (long(P) * Q) % kBlockM) { if (err) *err = "conv: epilogue statistics need the two-CTA kernel (see conv_tc_stats_supported)"; return false; }
+        p.stats = q.stats;
+        p.stats_rows = P * Q;
+        p.stats_reps = conv_tc_stats_reps(q);
+    }
     L->num_sms = num_sms;
     L->balanced_grid = 0;
     if (!encode_b_map(&L->tm_b, q.w_packed, kc, taps, q.c_out, want_pair ? block_n / 2 : block_n, err)) return false;

@@ -45,6 +45,12 @@ struct ConvKernelParams {
     int side_mode;           // CONV_MODE_TILED (stride 1) or CONV_MODE_IM2COL
     int side_stride_h, side_stride_w;
     const float* bias2;      // the shortcut's bias, added to `bias` in the epilogue (nullptr = none)
+    // Statistics for the instance norm behind the layer (conv_pair.cu only, no residual): every 128-row tile adds the column sums and
+    // sums of squares of its fp16 outputs to stats[image][column] = {sum, sum of squares} (fp64 reductions; zero before the launch).
+    // Layout [image][replica][column][2]: tile t of an image adds to replica t mod stats_reps (a power of two), the norm adds them up.
+    double* stats;           // nullptr = none
+    int stats_rows;          // output rows per image (a multiple of 128: no tile straddles two images)
+    int stats_reps;
 };
 
 struct ConvTcProblem {
@@ -74,6 +80,7 @@ struct ConvTcProblem {
     int splits;             // 0 = auto (conv_tc_plan), 1 = no split-K
     float* split_ws;        // workspace of conv_tc_plan().ws_bytes when splits > 1
     unsigned int* split_counters;  // conv_tc_plan().counter_bytes, zero-initialised once; the kernel leaves them zero
+    double* stats;          // ConvKernelParams::stats: [n][conv_tc_stats_reps()][c_out_pitch][2], zero before the launch (see conv_tc_stats_supported)
 };
 
 struct ConvTcPlanInfo {
@@ -85,6 +92,11 @@ ConvTcPlanInfo conv_tc_plan(const ConvTcProblem& q, int num_sms);
 // Whether a problem with a projection shortcut (side_*) can run as one launch: the two-CTA kernel without split-K must be the
 // choice for the problem both with and without the extra k-blocks.
 bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms);
+// Whether the layer can accumulate per-image column statistics in its epilogue (ConvTcProblem::stats): the two-CTA kernel without
+// split-K, residual or activation, output rows per image a multiple of 128.
+bool conv_tc_stats_supported(const ConvTcProblem& q, int num_sms);
+// Accumulator replicas per image for that: enough that few tiles meet on one address, few enough that the norm's prologue stays short
+int conv_tc_stats_reps(const ConvTcProblem& q);
 
 struct ConvTcLaunch {
     CUtensorMap tm_a, tm_b, tm_out, tm_res;

@@ -52,12 +52,16 @@ constexpr uint32_t kBiasSlotBytes = kChunkN * 4;
 constexpr uint32_t kBarrierBytes = 512;
 constexpr uint32_t kSmemLimit = 227 * 1024;
 
-template <int BLOCK_N, bool HAS_RES>
+// EPI: 0 = plain epilogue, 1 = residual tensor added (two staging buffers per warp), 2 = per-tile column statistics for the instance
+// norm behind the layer (ConvKernelParams::stats)
+template <int BLOCK_N, int EPI>
 struct Cfg {
+    static constexpr bool HAS_RES = EPI == 1;
+    static constexpr uint32_t kStatBytes = EPI == 2 ? 8192u : 0u;  // [item parity][group][row warp][lane] float4
     static constexpr uint32_t kBBytes = (BLOCK_N / 2) * kBlockK * 2;  // this CTA's half of the weight tile
     static constexpr uint32_t kStageBytes = kABytes + kBBytes;
     static constexpr int kEpiBufs = HAS_RES ? 2 : 1;
-    static constexpr uint32_t kEpiBytes = kEpilogueWarps * (kEpiBufs * kEpiBufBytes + kBiasSlotBytes);
+    static constexpr uint32_t kEpiBytes = kEpilogueWarps * (kEpiBufs * kEpiBufBytes + kBiasSlotBytes) + kStatBytes;
     static constexpr int kStagesFit = int((kSmemLimit - kEpiBytes - kBarrierBytes) / kStageBytes);
     static constexpr int kStages = kStagesFit > 8 ? 8 : kStagesFit;
     static constexpr uint32_t kTmemCols = (2 * BLOCK_N <= 128) ? 128 : (2 * BLOCK_N <= 256 ? 256 : 512);
@@ -95,10 +99,10 @@ enum ProducerKind : int { PROD_A_TILED = 0, PROD_A_IM2COL = 1, PROD_B = 2 };
 
 // One elected thread per producer warp (see conv_igemm.cu produce()).  Work items are (m-pair, n-tile): cluster c visits items
 // c, c + #clusters, ...; this CTA's rows are m-tile 2 * pair + rank, its weight half is rows n0 + rank * BLOCK_N / 2.
-template <int KIND, int BLOCK_N, bool HAS_RES>
+template <int KIND, int BLOCK_N, int EPI>
 __device__ __forceinline__ void produce(const CUtensorMap* tm, const CUtensorMap* tm_side, const ConvKernelParams& p, uint32_t smem_base, uint32_t bar_base,
                                         int me, int n_prod, int num_items, int main_kb, uint32_t rank) {
-    using C = Cfg<BLOCK_N, HAS_RES>;
+    using C = Cfg<BLOCK_N, EPI>;
     constexpr uint32_t kTxBytes = KIND == PROD_B ? C::kBBytes : kABytes;
     const int n_clusters = int(gridDim.x) >> 1;
     const int kpt = p.kblocks_per_tap, taps_w = p.taps_w, nn = p.num_n_tiles;
@@ -189,17 +193,18 @@ __device__ __forceinline__ void produce(const CUtensorMap* tm, const CUtensorMap
     }
 }
 
-template <int BLOCK_N, bool HAS_RES>
+template <int BLOCK_N, int EPI>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b,
                  const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ CUtensorMap tm_res,
                  const __grid_constant__ CUtensorMap tm_a2, const __grid_constant__ CUtensorMap tm_b2, const ConvKernelParams p) {
-    using C = Cfg<BLOCK_N, HAS_RES>;
+    using C = Cfg<BLOCK_N, EPI>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     const uint32_t smem_base = smem_u32(smem_raw);
     if (smem_base & 1023u) __trap();
     const uint32_t epi_base = smem_base + C::kStages * C::kStageBytes;
     const uint32_t bias_base = epi_base + kEpilogueWarps * C::kEpiBufs * kEpiBufBytes;
+    const uint32_t stat_base = bias_base + kEpilogueWarps * kBiasSlotBytes;
     const uint32_t bar_base = epi_base + C::kEpiBytes;
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
     auto empty_bar = [&](int s) { return bar_base + 8u * (C::kStages + s); };
@@ -224,6 +229,7 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const int total_kb = main_kb + p.side_kb;
     const int my_tiles = cluster_id < num_items ? (num_items - 1 - cluster_id) / n_clusters + 1 : 0;
     constexpr bool kSplit = C::kChunks >= 2;  // both epilogue groups share every tile (see conv_igemm.cu)
+    constexpr bool HAS_RES = C::HAS_RES;
 
     if (threadIdx.x == 0) chain_stamp(p, 0);
     if (warp == 0 && lane == 0) {
@@ -266,10 +272,10 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             if (is_a) {
                 if (p.use_pdl) grid_dep_wait();
                 if (me == 0) chain_stamp(p, 1);
-                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
-                else produce<PROD_A_IM2COL, BLOCK_N, HAS_RES>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
+                if (p.mode == CONV_MODE_TILED) produce<PROD_A_TILED, BLOCK_N, EPI>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
+                else produce<PROD_A_IM2COL, BLOCK_N, EPI>(&tm_a, &tm_a2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
             } else {
-                produce<PROD_B, BLOCK_N, HAS_RES>(&tm_b, &tm_b2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
+                produce<PROD_B, BLOCK_N, EPI>(&tm_b, &tm_b2, p, smem_base, bar_base, me, n_prod, num_items, main_kb, rank);
             }
         }
     } else if (warp == kMmaWarp) {
@@ -451,6 +457,45 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                     tma_store_commit();
                 }
                 epi_stamp(p, stamper, item, 5);
+                if (EPI == 2) {
+                    // Column sums and sums of squares of this warp's 32 x 64 box for the instance norm behind the layer, read back from
+                    // the staging buffer (the fp16 values the norm itself would read; lane l owns columns 2l, 2l + 1: one conflict-free
+                    // 128-byte row per load).  The four row warps of the group add theirs up in shared memory (fixed order); one warp
+                    // per work item sends the 128-row sums to the image's fp64 accumulators.
+                    const uint32_t cg = uint32_t(lane) >> 2, cw = (uint32_t(lane) & 3u) << 2;
+                    float4 st = make_float4(0.f, 0.f, 0.f, 0.f);  // sum, sum of squares of column 2l; the same of column 2l + 1
+#pragma unroll
+                    for (int r = 0; r < 32; ++r) {
+                        uint32_t hv;
+                        asm volatile("ld.shared.b32 %0, [%1];" : "=r"(hv) : "r"(buf + uint32_t(r) * 128u + ((cg ^ uint32_t(r & 7)) << 4) + cw) : "memory");
+                        const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&hv));
+                        st.x += f2.x; st.y = fmaf(f2.x, f2.x, st.y);
+                        st.z += f2.y; st.w = fmaf(f2.y, f2.y, st.w);
+                    }
+                    const uint32_t slot0 = stat_base + (uint32_t((item & 1) * 2 + group) << 11);  // [item parity][group][row warp][lane] float4
+                    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(slot0 + (uint32_t(ew) << 9) + (uint32_t(lane) << 4)), "f"(st.x), "f"(st.y), "f"(st.z), "f"(st.w) : "memory");
+                    asm volatile("bar.sync %0, 128;" ::"r"(1 + group) : "memory");
+                    const int tile_row0 = m_row0 - ew * 32;
+                    const int col = col0 + 2 * lane;
+                    if ((item & 3) == ew && tile_row0 < p.M && col < p.out_pitch) {
+                        float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+                        for (int w4 = 0; w4 < 4; ++w4) {
+                            float4 t;
+                            asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(t.x), "=f"(t.y), "=f"(t.z), "=f"(t.w) : "r"(slot0 + (uint32_t(w4) << 9) + (uint32_t(lane) << 4)) : "memory");
+                            a.x += t.x; a.y += t.y; a.z += t.z; a.w += t.w;
+                        }
+                        // replica = tile index mod stats_reps: same-address reductions serialise in L2 (~30 ns each, measured: 512 tiles
+                        // of one image on one accumulator set made a 14 us layer 31 us)
+                        const int img = tile_row0 / p.stats_rows;
+                        const int rep = ((tile_row0 - img * p.stats_rows) >> 7) & (p.stats_reps - 1);
+                        double* dst = p.stats + (size_t(img * p.stats_reps + rep) * size_t(p.out_pitch) + size_t(col)) * 2;
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst), "d"(double(a.x)) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 1), "d"(double(a.y)) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 2), "d"(double(a.z)) : "memory");
+                        asm volatile("red.global.add.f64 [%0], %1;" ::"l"(dst + 3), "d"(double(a.w)) : "memory");
+                    }
+                }
             }
         }
         if (kInstr && lane == 0 && group_tiles > 0) chain_stamp(p, 4);
@@ -470,9 +515,11 @@ conv_pair_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
 template <int BLOCK_N>
 cudaError_t set_attr_t() {
-    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, false>::kSmemBytes));
+    cudaError_t e = cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, 0>::kSmemBytes));
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, true>::kSmemBytes));
+    e = cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, 2>::kSmemBytes));
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(conv_pair_kernel<BLOCK_N, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(Cfg<BLOCK_N, 1>::kSmemBytes));
 }
 
 template <int BLOCK_N>
@@ -480,7 +527,7 @@ cudaError_t launch_t(const ConvTcLaunch& L, int grid, cudaStream_t stream) {
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(unsigned(grid));
     cfg.blockDim = dim3(kThreads);
-    cfg.dynamicSmemBytes = L.p.has_residual ? Cfg<BLOCK_N, true>::kSmemBytes : Cfg<BLOCK_N, false>::kSmemBytes;
+    cfg.dynamicSmemBytes = L.p.has_residual ? Cfg<BLOCK_N, 1>::kSmemBytes : L.p.stats ? Cfg<BLOCK_N, 2>::kSmemBytes : Cfg<BLOCK_N, 0>::kSmemBytes;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -491,8 +538,9 @@ cudaError_t launch_t(const ConvTcLaunch& L, int grid, cudaStream_t stream) {
     attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = L.use_pdl ? 2 : 1;
-    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, true>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
-    return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, false>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
+    if (L.p.has_residual) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, 1>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
+    if (L.p.stats) return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, 2>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
+    return cudaLaunchKernelEx(&cfg, conv_pair_kernel<BLOCK_N, 0>, L.tm_a, L.tm_b, L.tm_out, L.tm_res, L.tm_a2, L.tm_b2, L.p);
 }
 
 }  // namespace

@@ -78,6 +78,11 @@ struct NormStore {
 };
 cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps,
                           int act, float* partials, cudaStream_t s, int group_size = 1, int channels = 0, const NormStore* store = nullptr);
+// The same normalisation behind a convolution that accumulated the statistics in its epilogue (ConvTcProblem::stats, conv_igemm.h):
+// ONE launch, x read once.  stats: [n][phases][cp] fp64 {sum, sum of squares} (phases = F^2 behind a phase-column convolution whose
+// columns are phase * cp + channel, else 1); the kernel leaves stats and *counter zero for the next encode.
+cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
+                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store = nullptr);
 // copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s);

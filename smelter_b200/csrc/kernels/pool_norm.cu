@@ -541,11 +541,24 @@ __device__ __forceinline__ void ring_pixel(const NormDst& d, unsigned j, unsigne
 }
 // pass 2: y = act(x * scale + shift).  Blocks past `chunks` write the reflection border (NormStore::pad_*): one task per (border
 // pixel, 8 channels), source pixel re-read.
+// STATS: the statistics come from the producing convolution's epilogue (ConvKernelParams::stats: fp64 {sum, sum of squares} per
+// (image, phase, channel), `phases` = 1, or F^2 column groups behind a phase-column convolution): every block derives scale / shift
+// of its image in shared memory, the last block to finish puts the accumulators and the arrival counter back to zero.
+struct NormStats {
+    double* stats;
+    const float* gamma;
+    const float* beta;
+    unsigned int* counter;
+    float eps;
+    int phases;
+};
+template <bool STATS>
 __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
-                                                              int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain) {
+                                                              int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns) {
     pdl_prologue();
     const int img = blockIdx.y;
-    const float* sm = params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
+    extern __shared__ float sm_params[];  // STATS: [cp][2]
+    const float* sm = STATS ? sm_params : params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
     // streaming part: block-tiled, eight 128-bit loads in flight per thread; when kThreads % cp8 == 0 a thread meets the same 8
     // channels in every vector it handles and keeps their scale / shift in registers
     constexpr int U = 8;
@@ -580,6 +593,38 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
             o[u] = padded_vec(dst, oy, ox, unsigned(cp8)) + g;
         }
     }
+    if (STATS) {  // (the loads above are in flight)
+        // `parts` threads share a channel, each adding every parts-th column group; fixed order within the block
+        __shared__ double2 red[kThreads];
+        const int cp = cp8 * 8;
+        const int parts = (cp <= kThreads && kThreads % cp == 0) ? min(kThreads / cp, ns.phases) : 1;
+        for (int ch0 = 0; ch0 < cp; ch0 += kThreads / parts) {
+            const int ch = ch0 + int(threadIdx.x) % (kThreads / parts), part = int(threadIdx.x) / (kThreads / parts);
+            double a = 0.0, b = 0.0;
+            if (ch < cp && part < parts) {
+#pragma unroll 4
+                for (int ph = part; ph < ns.phases; ph += parts) {
+                    const double2 t = __ldcg(reinterpret_cast<const double2*>(ns.stats + ((size_t(img) * ns.phases + ph) * cp + ch) * 2));
+                    a += t.x; b += t.y;
+                }
+            }
+            if (parts > 1) {
+                red[threadIdx.x] = make_double2(a, b);
+                __syncthreads();
+                if (part == 0) for (int q = 1; q < parts; ++q) { a += red[threadIdx.x + q * (kThreads / parts)].x; b += red[threadIdx.x + q * (kThreads / parts)].y; }
+            }
+            if (ch < cp && part == 0) {
+                const double mean = a / double(hw);
+                double var = b / double(hw) - mean * mean;
+                if (var < 0.0) var = 0.0;
+                const float rstd = float(1.0 / sqrt(var + double(ns.eps)));
+                const float scl = rstd * ns.gamma[ch];
+                sm_params[ch * 2] = scl;
+                sm_params[ch * 2 + 1] = ns.beta[ch] - float(mean) * scl;
+            }
+        }
+        __syncthreads();
+    }
     const bool fixed = (kThreads % cp8) == 0;
     float sc[8], sh[8];
     if (fixed) {
@@ -605,6 +650,19 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
         }
         st8(yb + o[u] * 8, pack(f));
         if (y_plain && !ring) st8(y_plain + (size_t(img) * n8 + o2[u]) * 8, pack(f));
+    }
+    if (STATS) {
+        __shared__ unsigned int s_last;
+        if (threadIdx.x == 0) {
+            __threadfence();
+            s_last = atomicAdd(ns.counter, 1u) == gridDim.x * gridDim.y - 1u;
+        }
+        __syncthreads();
+        if (s_last) {  // every block has read its statistics: zero for the next encode's convolution
+            const size_t total = size_t(gridDim.y) * ns.phases * cp8 * 16;
+            for (size_t i = threadIdx.x; i < total; i += kThreads) ns.stats[i] = 0.0;
+            if (threadIdx.x == 0) *ns.counter = 0u;
+        }
     }
 }
 
@@ -940,11 +998,12 @@ int inorm_cluster_size(int hw, int group_size) {
     if (off || group_size < 1 || group_size > 16 || (group_size & (group_size - 1))) return 0;
     int csz = inorm_max_cluster();
     while (csz > 1 && hw / csz < 512) csz >>= 1;
-    // measured (TransformerNet, one image): 64 KiB per CTA (128 x 128 pixels) 16 -> 10 us against the three-launch form, but 256 KiB /
-    // 1 MiB per CTA (256^2, 512^2 pixels) 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches.
+    // measured (TransformerNet, one image): 32-64 KiB per CTA (128 x 128 pixels) 16 -> 10 us against the three-launch form, but 128 KiB
+    // per CTA (256^2 x 64 in 16-CTA clusters) ~20 against ~17 us (the whole encode 0.404 -> 0.397 ms with those two norms in three
+    // launches) and 256 KiB / 1 MiB per CTA 17 -> 27 us / 34 -> 77 us -- too few CTAs stream the image; those keep the three launches.
     // 1024-thread CTAs do not change that (256^2 x 64: 24 us either way, 512^2 x 32: 52 us against 30 us for three launches): a slab
     // is 32 bytes of every 128-byte line, so the passes are bound by the lines a CTA touches, not by the bytes it keeps in flight.
-    if (size_t(hw) / csz * 32 > (size_t(128) << 10)) return 0;
+    if (size_t(hw) / csz * 32 > (size_t(64) << 10)) return 0;
     return csz;
 }
 int instance_norm_launches(int n, int hw, int cp, int group_size) {
@@ -977,12 +1036,9 @@ int inorm_max_cluster() {
     return best;
 }
 
-cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                          float* partials, cudaStream_t s, int group_size, int channels, const NormStore* store) {
-    if (group_size < 1) group_size = 1;
-    if (channels <= 0) channels = cp;
+namespace {
+cudaError_t norm_dst_of(const NormStore* store, const __half* x, const __half* y, int hw, NormDst* out) {
     NormDst dst{};
-    __half* y_plain = store && store->padded() ? store->plain : nullptr;
     if (store) {
         if (x == y && (store->unfold_w || store->padded())) return cudaErrorInvalidValue;
         if (store->unfold_f != 2 && store->unfold_f != 4) return cudaErrorInvalidValue;
@@ -1002,6 +1058,35 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
             if (dst.s2d && ((dst.s2d != 2 && dst.s2d != 4) || dst.ho % dst.s2d || dst.wo % dst.s2d)) return cudaErrorInvalidValue;
         }
     }
+    *out = dst;
+    return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
+                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store) {
+    NormDst dst{};
+    if (cudaError_t e = norm_dst_of(store, x, y, hw, &dst); e != cudaSuccess) return e;
+    __half* y_plain = store && store->padded() ? store->plain : nullptr;
+    const int cp8 = cp / 8;
+    if (cp8 > kThreads || phases < 1 || n > 65535) return cudaErrorInvalidValue;
+    const size_t n8 = size_t(hw) * cp8;
+    const int chunks = int(std::max<size_t>(1, (n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)));
+    const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
+    const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
+    NormStats ns{stats, gamma, beta, counter, eps, phases};
+    (void)launch_pdl_smem(inorm_apply_kernel<true>, dim3(chunks + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
+                          static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns);
+    return cudaGetLastError();
+}
+
+cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
+                          float* partials, cudaStream_t s, int group_size, int channels, const NormStore* store) {
+    if (group_size < 1) group_size = 1;
+    if (channels <= 0) channels = cp;
+    NormDst dst{};
+    if (cudaError_t e = norm_dst_of(store, x, y, hw, &dst); e != cudaSuccess) return e;
+    __half* y_plain = store && store->padded() ? store->plain : nullptr;
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
     if (const int csz = inorm_cluster_size(hw, group_size); csz > 0 && n <= 65535) {
@@ -1045,7 +1130,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         if (e != cudaSuccess) return e;
         const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
         const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
-        (void)launch_pdl(inorm_apply_kernel, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr);
+        (void)launch_pdl(inorm_apply_kernel<false>, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr, NormStats{});
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

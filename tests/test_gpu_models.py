@@ -508,6 +508,7 @@ def test_upsample_folded_convolution(ctx, monkeypatch, c_in, c_out, hw, batch, c
     want = _oracle(model, xin)
     if not cluster:
         monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+        monkeypatch.setenv("SMELTER_NO_CONV_STATS", "1")  # the norm's own statistics in every plan below
 
     def run():
         g = ONNXGraph(model, context=ctx)
@@ -554,6 +555,7 @@ def test_pad_written_by_the_instance_norm(ctx, monkeypatch, c, hw, pad, k, batch
     want = _oracle(model, xin)
     if not cluster:
         monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+        monkeypatch.setenv("SMELTER_NO_CONV_STATS", "1")  # the norm's own statistics in every plan below
 
     def run():
         g = ONNXGraph(model, context=ctx)
@@ -635,6 +637,7 @@ def test_input_folded_convolution(ctx, monkeypatch, c_in, c_out, k, hw, mode, ba
     want = _oracle(model, xin)
     if not cluster:
         monkeypatch.setenv("SMELTER_NO_CLUSTER_NORM", "1")
+        monkeypatch.setenv("SMELTER_NO_CONV_STATS", "1")  # the norm's own statistics in every plan below
 
     def run():
         g = ONNXGraph(model, context=ctx)
@@ -652,3 +655,62 @@ def test_input_folded_convolution(ctx, monkeypatch, c_in, c_out, k, hw, mode, ba
     plain, dump0, n0 = run()
     assert "input-fold4" not in dump0 and n0 == n + 1
     assert np.abs(out - plain).max() <= 6e-3 * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("kind,c_in,c_out,hw,batch", [("plain", 32, 32, (16, 24), 2), ("plain", 32, 32, (128, 128), 1), ("plain", 64, 128, (32, 32), 1), ("plain", 16, 24, (8, 16), 3),
+                                                      ("plain", 128, 256, (16, 16), 5), ("plain1x1", 64, 320, (16, 8), 2), ("stride2", 32, 64, (32, 32), 2),
+                                                      ("upfold", 64, 32, (16, 16), 2), ("infold", 3, 32, (64, 32), 2), ("ragged", 32, 32, (10, 12), 2)])
+def test_instance_norm_statistics_from_the_convolution_epilogue(ctx, monkeypatch, kind, c_in, c_out, hw, batch):
+    """Conv -> InstanceNorm with output rows per image a multiple of 128: the two-CTA convolution kernel adds every tile's column sums
+    and sums of squares to per-image fp64 accumulators (ConvKernelParams::stats) and the norm is one pass
+    (k::instance_norm_from_stats; phase-column convolutions keep a column per (phase, channel)).  Same result as the plan with the
+    norm's own statistics and the oracle; repeated encodes agree (the norm's last block re-zeroes the accumulators); ragged image
+    sizes keep the norm's own statistics."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c_in + c_out, name="convstats")
+    x = b.input("input", [batch, c_in, h, w])
+    oh, ow = h, w
+    if kind == "upfold":
+        y = b.conv(b.pad(b.upsample(b.relu(b.conv(x, c_in, 1)), 2), 1, "reflect"), c_out, 3, 1, 0)
+        oh, ow = 2 * h, 2 * w
+    elif kind == "infold":
+        y = b.conv(b.pad(x, 4, "reflect"), c_out, 9, 1, 0)
+    elif kind == "plain1x1":
+        y = b.conv(b.relu(b.conv(x, c_in, 3, 1, 1)), c_out, 1)
+    elif kind == "stride2":
+        y = b.conv(b.relu(b.conv(x, c_in, 3, 1, 1)), c_out, 3, 2, 1)
+        oh, ow = h // 2, w // 2
+    else:
+        y = b.conv(b.relu(b.conv(x, c_in, 3, 1, 1)), c_out, 3, 1, 1)
+    y = b.relu(b.instancenorm(y))
+    y = b.conv(b.pad(y, 1, "reflect"), 8, 3, 1, 0)
+    b.output(y, [batch, 8, oh, ow])
+    model = b.model().serialize()
+    xin = (np.random.default_rng(h).standard_normal((batch, c_in, h, w)) * 2 + 0.5).astype(np.float16)
+    want = _oracle(model, xin)
+
+    def run(repeats=1):
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray().copy() for _ in range(repeats)]
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return outs, dump, n
+
+    outs, dump, n = run(3)
+    src = [l for l in dump.splitlines() if " Conv " in l][-2]  # the convolution in front of the norm
+    fused = kind != "ragged" and src.startswith("conv_pair[")   # small problems are planned on the single-CTA kernel (32-column tiles / split-K)
+    assert fused or kind == "ragged" or c_out < 64
+    assert ("+stats" in src) == fused and ("<-stats" in dump) == fused
+    scale = max(1.0, np.abs(want).max())
+    assert outs[0].shape == want.shape
+    assert np.abs(outs[0] - want).max() <= TOL * scale
+    for o in outs[1:]:  # fp64 reductions in a different order at most: far below one fp16 step of the result
+        assert np.abs(o - outs[0]).max() <= 1e-3 * scale
+    monkeypatch.setenv("SMELTER_NO_CONV_STATS", "1")
+    (plain,), dump0, n0 = run()
+    assert "stats" not in dump0 and n0 >= n
+    assert np.abs(outs[0] - plain).max() <= 4e-3 * scale

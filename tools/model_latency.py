@@ -1,6 +1,6 @@
 """Latency / throughput of the other BASELINE.json configurations through the public API (CUDA-graph replay, inputs resident,
 CUDA events around `iters` back-to-back encodes after 5 warm-ups).  Writes gpurun_out/model_latency.json.
-Usage: python tools/model_latency.py"""
+Usage: python tools/model_latency.py [mobilenet|tnet|resnet ...]   (default: all)"""
 import json, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
@@ -38,13 +38,19 @@ def run(name, model, shape, iters=200, gflop_per_image=None):
     g.close()
 
 
-mb = onnx2mps.convert_bytes(modelzoo.mobilenet_v2(seed=0, fold_bn=False).serialize(), half=True)
-run("MobileNetV2 fp16 batch 1 (BASELINE configs[1])", mb, (1, 3, 224, 224), 500, 0.6015)
-run("MobileNetV2 fp16 batch 32", mb, (32, 3, 224, 224), 200, 0.6015)
-tn = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=512).serialize(), half=True)
-run("TransformerNet fp16 1x3x512x512 (BASELINE configs[3])", tn, (1, 3, 512, 512), 100, 80.63)
-rn = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
-for b in (1, 8, 32, 128, 256):
-    run(f"ResNet-50 fp16 batch {b}", rn, (b, 3, 224, 224), 100 if b <= 32 else 30, 8.178)
+which = set(sys.argv[1:]) or {"mobilenet", "tnet", "resnet"}
+if "mobilenet" in which:
+    mb = onnx2mps.convert_bytes(modelzoo.mobilenet_v2(seed=0, fold_bn=False).serialize(), half=True)
+    run("MobileNetV2 fp16 batch 1 (BASELINE configs[1])", mb, (1, 3, 224, 224), 500, 0.6015)
+    run("MobileNetV2 fp16 batch 32", mb, (32, 3, 224, 224), 200, 0.6015)
+if "tnet" in which:
+    tn = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=512).serialize(), half=True)
+    run("TransformerNet fp16 1x3x512x512 (BASELINE configs[3])", tn, (1, 3, 512, 512), 100, 80.63)
+    if "tnet8" in which:
+        run("TransformerNet fp16 8x3x512x512", tn, (8, 3, 512, 512), 30, 80.63)
+if "resnet" in which:
+    rn = onnx2mps.convert_bytes(modelzoo.resnet50(seed=0, fold_bn=False).serialize(), half=True)
+    for b in (1, 8, 32, 128, 256):
+        run(f"ResNet-50 fp16 batch {b}", rn, (b, 3, 224, 224), 100 if b <= 32 else 30, 8.178)
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(rows, open("gpurun_out/model_latency.json", "w"), indent=1)

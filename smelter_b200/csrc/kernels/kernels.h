@@ -83,6 +83,9 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
 // columns are phase * cp + channel, else 1); the kernel leaves stats and *counter zero for the next encode.
 cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
                                      double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store = nullptr);
+// counter == nullptr: the accumulators are left as they are (the caller owns them).
+// The accumulators of a tensor that no convolution epilogue produced (benchmarks / tests of the one-pass norm alone): [n][cp][2]
+cudaError_t instance_norm_stats_f64(const __half* x, int n, int hw, int cp, float* partials, double* stats, cudaStream_t s);
 // copy `c_src_pitch` channels of every pixel of src into dst at channel offset c_off
 cudaError_t concat_channels(const __half* src, __half* dst, size_t pixels, int c_src, int c_src_pitch, int c_dst_pitch, int c_off,
                             cudaStream_t s);

@@ -551,10 +551,13 @@ struct NormStats {
     unsigned int* counter;
     float eps;
     int phases;
+    double inv_hw;
 };
+// (STATS: two blocks per SM -- at three the compiler spills part of v[] around the prologue, which makes the prologue wait for the loads)
 template <bool STATS>
-__global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
-                                                              int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns) {
+__global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
+                                                              int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns,
+                                                              int cpb) {
     pdl_prologue();
     const int img = blockIdx.y;
     extern __shared__ float sm_params[];  // STATS: [cp][2]
@@ -564,13 +567,22 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
     constexpr int U = 8;
     const size_t n8 = size_t(hw) * cp8;
     const bool plain = !dst.unfold_w && !dst.ho;
-    const bool ring = int(blockIdx.x) >= chunks;
+    // a streaming block takes `cpb` consecutive chunks (STATS: the scale / shift prologue is paid once per block)
+    const int sblocks = (chunks + cpb - 1) / cpb;
+    const bool ring = int(blockIdx.x) >= sblocks;
     const size_t tasks = ring ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : n8;
     const __half* xb = x + size_t(img) * n8 * 8;
     __half* yb = y + size_t(img) * (dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) * 8;
-    const size_t base = size_t(ring ? int(blockIdx.x) - chunks : int(blockIdx.x)) * (kThreads * U) + threadIdx.x;
+    const int c_lo = ring ? int(blockIdx.x) - sblocks : int(blockIdx.x) * cpb;
+    const int c_hi = ring ? c_lo + 1 : min(chunks, c_lo + cpb);
+    const bool fixed = (kThreads % cp8) == 0;
+    float sc[8], sh[8];
+  for (int chunk = c_lo; chunk < c_hi; ++chunk) {
+    const size_t base = size_t(chunk) * (kThreads * U) + threadIdx.x;
+    // (32-bit store offsets -- vector indices inside one image -- and three blocks per SM: with 64-bit offsets the kernel took 146
+    // registers, one block per SM, and a block's 32 KiB in flight did not cover its prologue)
     Half8 v[U];
-    size_t o[U], o2[U];
+    unsigned o[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
         const size_t i = base + u * kThreads;
@@ -578,22 +590,21 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
         if (!ring) {
             v[u] = ld8(xb + i * 8);
             if (plain) {
-                o[u] = i;
+                o[u] = unsigned(i);
             } else {
                 const unsigned pix = unsigned(i / size_t(cp8));
                 unsigned q;
-                o[u] = norm_dst_vec(dst, pix, unsigned(cp8), q) + (i - size_t(pix) * cp8);
-                o2[u] = size_t(q) * cp8 + (i - size_t(pix) * cp8);
+                o[u] = unsigned(norm_dst_vec(dst, pix, unsigned(cp8), q) + (i - size_t(pix) * cp8));
             }
         } else {
             const unsigned j = unsigned(i / size_t(cp8)), g = unsigned(i - size_t(j) * cp8);
             unsigned oy, ox, src;
             ring_pixel(dst, j, oy, ox, src);
             v[u] = ld8(xb + (size_t(src) * cp8 + g) * 8);
-            o[u] = padded_vec(dst, oy, ox, unsigned(cp8)) + g;
+            o[u] = unsigned(padded_vec(dst, oy, ox, unsigned(cp8)) + g);
         }
     }
-    if (STATS) {  // (the loads above are in flight)
+    if (STATS && chunk == c_lo) {  // (the loads above are in flight)
         // `parts` threads share a channel, each adding every parts-th column group; fixed order within the block
         __shared__ double2 red[kThreads];
         const int cp = cp8 * 8;
@@ -614,10 +625,9 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
                 if (part == 0) for (int q = 1; q < parts; ++q) { a += red[threadIdx.x + q * (kThreads / parts)].x; b += red[threadIdx.x + q * (kThreads / parts)].y; }
             }
             if (ch < cp && part == 0) {
-                const double mean = a / double(hw);
-                double var = b / double(hw) - mean * mean;
-                if (var < 0.0) var = 0.0;
-                const float rstd = float(1.0 / sqrt(var + double(ns.eps)));
+                const double inv = ns.inv_hw, mean = a * inv;
+                const float var = fmaxf(float(fma(b, inv, -mean * mean)), 0.f);  // the cancellation is done in fp64, the root in fp32
+                const float rstd = rsqrtf(var + ns.eps);
                 const float scl = rstd * ns.gamma[ch];
                 sm_params[ch * 2] = scl;
                 sm_params[ch * 2 + 1] = ns.beta[ch] - float(mean) * scl;
@@ -625,9 +635,7 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
         }
         __syncthreads();
     }
-    const bool fixed = (kThreads % cp8) == 0;
-    float sc[8], sh[8];
-    if (fixed) {
+    if (fixed && chunk == c_lo) {
         const int c0 = int(threadIdx.x % unsigned(cp8)) * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) { sc[j] = sm[(c0 + j) * 2]; sh[j] = sm[(c0 + j) * 2 + 1]; }
@@ -648,10 +656,15 @@ __global__ void __launch_bounds__(kThreads) inorm_apply_kernel(const __half* __r
             const float r = fmaf(f[j], sc[j], sh[j]);
             f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
         }
-        st8(yb + o[u] * 8, pack(f));
-        if (y_plain && !ring) st8(y_plain + (size_t(img) * n8 + o2[u]) * 8, pack(f));
+        st8(yb + size_t(o[u]) * 8, pack(f));
+        if (y_plain && !ring) {  // the un-padded copy for the other readers (position worked out here: rare, and eight registers less)
+            const unsigned pix = unsigned(i / size_t(cp8));
+            const unsigned q = dst.unfold_w ? unfold_pixel(pix, unsigned(dst.unfold_w), unsigned(dst.unfold_f)) : pix;
+            st8(y_plain + (size_t(img) * n8 + size_t(q) * cp8 + (i - size_t(pix) * cp8)) * 8, pack(f));
+        }
     }
-    if (STATS) {
+  }
+    if (STATS && ns.counter) {
         __shared__ unsigned int s_last;
         if (threadIdx.x == 0) {
             __threadfence();
@@ -993,7 +1006,10 @@ int inorm_group(int n, int hw, int cp) {
 // Largest cluster the device schedules for inorm_cluster_kernel: 16 CTAs (non-portable size, one cluster per GPC) where the driver
 // allows it, else the portable 8.  Asked once.
 int inorm_max_cluster();
-int inorm_cluster_size(int hw, int group_size) {
+int inorm_cluster_size(int hw, int group_size, size_t tensor_bytes) {
+    // both passes of a cluster stream 32-byte slabs of 128-byte lines: fine out of L2, 2x slower than the three launches from HBM
+    // (64 x 128 x 128 x 128, 537 MB: 0.279 ms against 0.143 ms)
+    if (tensor_bytes > (size_t(48) << 20)) return 0;
     const bool off = getenv("SMELTER_NO_CLUSTER_NORM") != nullptr;  // read on every call: tests switch it inside one process
     if (off || group_size < 1 || group_size > 16 || (group_size & (group_size - 1))) return 0;
     int csz = inorm_max_cluster();
@@ -1007,7 +1023,7 @@ int inorm_cluster_size(int hw, int group_size) {
     return csz;
 }
 int instance_norm_launches(int n, int hw, int cp, int group_size) {
-    if (inorm_cluster_size(hw, group_size)) return 1;
+    if (inorm_cluster_size(hw, group_size, size_t(n) * hw * cp * 2)) return 1;
     const int group = inorm_group(n, hw, cp);
     return 3 * ((n + group - 1) / group);
 }
@@ -1071,12 +1087,40 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     const int cp8 = cp / 8;
     if (cp8 > kThreads || phases < 1 || n > 65535) return cudaErrorInvalidValue;
     const size_t n8 = size_t(hw) * cp8;
+    if ((dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) >> 32) return cudaErrorInvalidValue;  // 32-bit vector offsets inside an image
     const int chunks = int(std::max<size_t>(1, (n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)));
     const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
     const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
-    NormStats ns{stats, gamma, beta, counter, eps, phases};
-    (void)launch_pdl_smem(inorm_apply_kernel<true>, dim3(chunks + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
-                          static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns);
+    NormStats ns{stats, gamma, beta, counter, eps, phases, 1.0 / double(hw)};
+    // chunks per block: measured with up to 8 (the prologue paid once per 256 KiB): slower (64 x 128 x 128 x 128: 0.122 -> 0.134 ms), one it is
+    const int cpb = 1;
+    (void)launch_pdl_smem(inorm_apply_kernel<true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
+                          static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb);
+    return cudaGetLastError();
+}
+
+namespace {
+__global__ void __launch_bounds__(kThreads) inorm_partials_to_stats_kernel(const float* __restrict__ partials, double* __restrict__ stats, int cp, int splits) {
+    const int img = blockIdx.x;
+    for (int ch = threadIdx.x; ch < cp; ch += kThreads) {
+        double a = 0.0, b = 0.0;
+        for (int sp = 0; sp < splits; ++sp) {
+            a += partials[((size_t(img) * splits + sp) * cp + ch) * 2];
+            b += partials[((size_t(img) * splits + sp) * cp + ch) * 2 + 1];
+        }
+        stats[(size_t(img) * cp + ch) * 2] = a;
+        stats[(size_t(img) * cp + ch) * 2 + 1] = b;
+    }
+}
+}  // namespace
+cudaError_t instance_norm_stats_f64(const __half* x, int n, int hw, int cp, float* partials, double* stats, cudaStream_t s) {
+    const int cp8 = cp / 8;
+    if (cp8 > kThreads || n > 65535) return cudaErrorInvalidValue;
+    const int splits = instance_norm_splits(hw, cp);
+    const int lanes = kThreads / cp8;
+    (void)launch_pdl_smem(inorm_stats_kernel, dim3(splits, n), dim3(kThreads), size_t(lanes) * cp * 2 * sizeof(float), s, x, partials, hw, cp8, splits);
+    if (cudaError_t e = cudaGetLastError(); e != cudaSuccess) return e;
+    inorm_partials_to_stats_kernel<<<n, kThreads, 0, s>>>(partials, stats, cp, splits);
     return cudaGetLastError();
 }
 
@@ -1089,7 +1133,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
     __half* y_plain = store && store->padded() ? store->plain : nullptr;
     const int cp8 = cp / 8;
     if (cp8 > kThreads) return cudaErrorInvalidValue;  // > 2048 channels: not on any supported model
-    if (const int csz = inorm_cluster_size(hw, group_size); csz > 0 && n <= 65535) {
+    if (const int csz = inorm_cluster_size(hw, group_size, size_t(n) * hw * cp * 2); csz > 0 && n <= 65535) {
         cudaLaunchConfig_t cfg{};
         cfg.gridDim = dim3(unsigned((cp8 + 1) / 2 * csz), unsigned(n));
         cfg.blockDim = dim3(kThreads);
@@ -1105,6 +1149,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         cfg.numAttrs = 2;
         return cudaLaunchKernelEx(&cfg, inorm_cluster_kernel, x, y, gamma, beta, hw, cp8, eps, act, group_size, channels, dst, y_plain);
     }
+    if ((dst.ho ? size_t(dst.ho) * dst.wo * cp8 : size_t(hw) * cp8) >> 32) return cudaErrorInvalidValue;  // 32-bit vector offsets inside an image
     const int splits = instance_norm_splits(hw, cp);
     const int lanes = kThreads / cp8;
     const size_t smem1 = size_t(lanes) * cp * 2 * sizeof(float);
@@ -1130,7 +1175,7 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         if (e != cudaSuccess) return e;
         const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
         const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
-        (void)launch_pdl(inorm_apply_kernel<false>, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr, NormStats{});
+        (void)launch_pdl(inorm_apply_kernel<false>, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr, NormStats{}, 1);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -195,6 +195,22 @@ def test_instance_norm_cluster_form_matches_three_launch_form(ctx, shape, act, m
     assert np.abs(one.astype(np.float32) - three.astype(np.float32)).max() <= 4e-3
 
 
+@pytest.mark.parametrize("shape,act", [((2, 128, 128, 128), 1), ((1, 24, 61, 47), 0), ((3, 40, 9, 200), 1), ((2, 32, 256, 256), 0), ((1, 320, 16, 16), 1)])
+def test_instance_norm_one_pass_form_with_supplied_statistics(ctx, shape, act):
+    """The apply pass of the norm behind a convolution that accumulated the statistics (k::instance_norm_from_stats; here the fp64
+    sums come from the norm's own statistics kernel): scale / shift derived per block, one read and one write of the tensor."""
+    from smelter_b200.api import run_elementwise
+
+    x = (_rand(shape, 31).astype(np.float32) * 3 - 0.25).astype(np.float16)
+    rng = np.random.default_rng(32)
+    g, b = rng.uniform(0.5, 1.5, shape[1]).astype(np.float32), rng.standard_normal(shape[1]).astype(np.float32)
+    ref = F.instance_norm(_t(x), weight=torch.from_numpy(g), bias=torch.from_numpy(b), eps=1e-5)
+    if act:
+        ref = ref.relu()
+    y, _ = run_elementwise(ctx, "instance_norm", _img(ctx, x), p0=g, p1=b, out_shape=shape, alpha=1e-5, act=act, sub=1, iters=2)
+    _close(y.toFloatArray(), ref, 4e-3)
+
+
 @pytest.mark.parametrize("shape", SHAPES + [(32, 3, 224, 224)])
 def test_layout_roundtrip_is_exact(ctx, shape):
     from smelter_b200.api import run_elementwise

@@ -35,6 +35,8 @@ CASES = [
     ("concat 64x128+128x56x56", "concat", (N, 128, 56, 56), (N, 256, 56, 56), dict(c2=128), 2, False),
     ("instance_norm+relu 16x32x512x512", "instance_norm", (16, 32, 512, 512), (16, 32, 512, 512), dict(alpha=1e-5, act=1), 1, True),
     ("instance_norm 64x128x128x128", "instance_norm", (64, 128, 128, 128), (64, 128, 128, 128), dict(alpha=1e-5), 1, True),
+    ("instance_norm+relu<-conv statistics 16x32x512x512", "instance_norm", (16, 32, 512, 512), (16, 32, 512, 512), dict(alpha=1e-5, act=1, sub=1), 1, True),
+    ("instance_norm<-conv statistics 64x128x128x128", "instance_norm", (64, 128, 128, 128), (64, 128, 128, 128), dict(alpha=1e-5, sub=1), 1, True),
     ("layout nhwc copy 64x256x56x56", "layout_roundtrip", (N, 256, 56, 56), (N, 256, 56, 56), dict(), 1, False),
 ]
 out = []

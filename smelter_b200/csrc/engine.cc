@@ -923,6 +923,33 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         }
     }
 
+    // ---- norm tail: InstanceNorm -> Add(skip) (-> ReLU) -> Pad, the end of a residual block ----
+    // The one-pass norm (statistics from its convolution) also reads the skip tensor and stores the padded sum, and the plain sum
+    // while the next block's skip connection reads it: the Add+Pad kernel (Filter::pad_add) runs inside the norm's launch.  Decided
+    // per plan because the one-pass form is; the Pad must be the next live filter.  SMELTER_NO_NORM_TAIL=1 turns it off.
+    std::vector<int> tail_of(filters_.size(), -1);
+    if (!getenv("SMELTER_NO_NORM_TAIL")) {
+        for (size_t fi = 0; fi < filters_.size(); ++fi) {
+            const Filter& f = filters_[fi];
+            if (stats_conv[fi] < 0 || f.norm_padded || f.unfold_w || f.out2 >= 0) continue;
+            const int nr = root_of(f.out);
+            if (nr == out_root || reads[size_t(nr)] != 1) continue;
+            size_t pi = fi + 1;
+            while (pi < filters_.size() && (filters_[pi].removed || absorbed[pi] || filters_[pi].kind == FilterKind::Alias)) ++pi;
+            if (pi >= filters_.size()) continue;
+            const Filter& pd = filters_[pi];
+            if (pd.kind != FilterKind::Pad || !pd.pad_add || pd.s2d_out || (pd.sub != k::PAD_REFLECT && pd.sub != k::PAD_EDGE) || pd.in.size() != 2) continue;
+            const int a = root_of(pd.in[0]), b = root_of(pd.in[1]);
+            if ((a == nr) == (b == nr)) continue;
+            const ImageShape& sh = values_[size_t(f.out)].shape;
+            if (pd.sub == k::PAD_REFLECT && (pd.pads[0] >= sh.h || pd.pads[2] >= sh.h || pd.pads[1] >= sh.w || pd.pads[3] >= sh.w)) continue;
+            const int skip = a == nr ? b : a;
+            tail_of[fi] = int(pi);
+            absorbed[pi] = 1;
+            if (last_use[size_t(skip)] == int(pi)) last_use[size_t(skip)] = int(fi);
+        }
+    }
+
     // graph inputs: NHWC copies produced by the boundary conversion
     for (int v : input_values_) off[size_t(v)] = arena.alloc(input_bytes(v));
     for (size_t fi = 0; fi < filters_.size(); ++fi) {
@@ -963,8 +990,14 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 scratch[fi].off = arena.alloc(scratch[fi].bytes);
             }
         }
-        off[size_t(f.out)] = arena.alloc(bytes_of(f.out));
-        if (f.out2 >= 0) off[size_t(f.out2)] = arena.alloc(bytes_of(f.out2));
+        if (tail_of[fi] >= 0) {  // the norm writes the absorbed Pad's outputs; its own result never exists
+            const Filter& pd = filters_[size_t(tail_of[fi])];
+            off[size_t(pd.out)] = arena.alloc(bytes_of(pd.out));
+            if (pd.out2 >= 0) off[size_t(pd.out2)] = arena.alloc(bytes_of(pd.out2));
+        } else {
+            off[size_t(f.out)] = arena.alloc(bytes_of(f.out));
+            if (f.out2 >= 0) off[size_t(f.out2)] = arena.alloc(bytes_of(f.out2));
+        }
         if (scratch[fi].off != size_t(-1)) arena.release(scratch[fi].off, scratch[fi].bytes);
         if (scratch2[fi].off != size_t(-1)) arena.release(scratch2[fi].off, scratch2[fi].bytes);
         // release inputs whose last use is this filter
@@ -972,6 +1005,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
         for (int i : f.in) roots.push_back(root_of(i));
         if (f.residual >= 0 && side_of[fi] < 0) roots.push_back(root_of(f.residual));
         if (side_of[fi] >= 0) roots.push_back(root_of(filters_[size_t(side_of[fi])].in[0]));
+        if (tail_of[fi] >= 0) for (int i : filters_[size_t(tail_of[fi])].in) roots.push_back(root_of(i));
         std::sort(roots.begin(), roots.end());
         roots.erase(std::unique(roots.begin(), roots.end()), roots.end());
         for (int r : roots)
@@ -1158,6 +1192,21 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                     const int phases = stats_phases[fi];
                     unsigned int* counter = reinterpret_cast<unsigned int*>(stats + size_t(N) * phases * icp * 2);
                     (void)c;
+                    if (tail_of[fi] >= 0) {
+                        const Filter& pd = filters_[size_t(tail_of[fi])];
+                        const int skip = root_of(pd.in[0]) == root_of(f.out) ? pd.in[1] : pd.in[0];
+                        const __half* res = ptr_of(skip);
+                        __half* yp = ptr_of(pd.out);
+                        store.pad_t = pd.pads[0]; store.pad_l = pd.pads[1]; store.pad_b = pd.pads[2]; store.pad_r = pd.pads[3];
+                        store.s2d = 0; store.pad_mode = pd.sub;
+                        store.plain = pd.out2 >= 0 ? ptr_of(pd.out2) : nullptr;
+                        const int act2 = pd.act;
+                        const ImageShape ps = values_[size_t(pd.out)].shape;
+                        add_step(what + "+add+pad" + (pd.out2 >= 0 ? "+sum" : "") + "<-stats " + f.op_type + " " + values_[size_t(pd.out)].name,
+                                 [=](cudaStream_t st) { return k::instance_norm_from_stats(x, yp, N, is.h * is.w, icp, ga, be, eps, act, stats, counter, phases, st, &store, res, act2); }, 0,
+                                 double(N) * (2.0 * is.h * is.w + double(ps.h) * ps.w + (pd.out2 >= 0 ? double(is.h) * is.w : 0.0)) * icp * 2);
+                        break;
+                    }
                     add_step(what + "<-stats " + name,
                              [=](cudaStream_t st) { return k::instance_norm_from_stats(x, y, N, is.h * is.w, icp, ga, be, eps, act, stats, counter, phases, st, &store); }, 0,
                              io_bytes);

@@ -82,7 +82,8 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
 // ONE launch, x read once.  stats: [n][phases][cp] fp64 {sum, sum of squares} (phases = F^2 behind a phase-column convolution whose
 // columns are phase * cp + channel, else 1); the kernel leaves stats and *counter zero for the next encode.
 cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store = nullptr);
+                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store = nullptr,
+                                     const __half* res = nullptr, int act2 = 0);  // res: y = act2(act(norm(x)) + res), res in x's (plain) pixel order
 // counter == nullptr: the accumulators are left as they are (the caller owns them).
 // The accumulators of a tensor that no convolution epilogue produced (benchmarks / tests of the one-pass norm alone): [n][cp][2]
 cudaError_t instance_norm_stats_f64(const __half* x, int n, int hw, int cp, float* partials, double* stats, cudaStream_t s);

@@ -554,19 +554,22 @@ struct NormStats {
     double inv_hw;
 };
 // (STATS: two blocks per SM -- at three the compiler spills part of v[] around the prologue, which makes the prologue wait for the loads)
-template <bool STATS>
+// RES: a residual tensor (plain row-major pixels, the shape of x) is added behind the norm's own activation, `act2` follows the sum --
+// the Add (-> ReLU) -> Pad tail of a residual block (engine.cc "norm tail"); four vectors of each operand in flight per thread.
+template <bool STATS, bool RES>
 __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
                                                               int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns,
-                                                              int cpb) {
+                                                              int cpb, const __half* __restrict__ res, int act2) {
     pdl_prologue();
     const int img = blockIdx.y;
     extern __shared__ float sm_params[];  // STATS: [cp][2]
     const float* sm = STATS ? sm_params : params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
     // streaming part: block-tiled, eight 128-bit loads in flight per thread; when kThreads % cp8 == 0 a thread meets the same 8
     // channels in every vector it handles and keeps their scale / shift in registers
-    constexpr int U = 8;
+    constexpr int U = RES ? 4 : 8;
     const size_t n8 = size_t(hw) * cp8;
     const bool plain = !dst.unfold_w && !dst.ho;
+    const __half* rb = RES ? res + size_t(img) * n8 * 8 : nullptr;
     // a streaming block takes `cpb` consecutive chunks (STATS: the scale / shift prologue is paid once per block)
     const int sblocks = (chunks + cpb - 1) / cpb;
     const bool ring = int(blockIdx.x) >= sblocks;
@@ -581,7 +584,7 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
     const size_t base = size_t(chunk) * (kThreads * U) + threadIdx.x;
     // (32-bit store offsets -- vector indices inside one image -- and three blocks per SM: with 64-bit offsets the kernel took 146
     // registers, one block per SM, and a block's 32 KiB in flight did not cover its prologue)
-    Half8 v[U];
+    Half8 v[U], r[RES ? U : 1];
     unsigned o[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -589,6 +592,7 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
         if (i >= tasks) break;
         if (!ring) {
             v[u] = ld8(xb + i * 8);
+            if (RES) r[u] = ld8(rb + i * 8);
             if (plain) {
                 o[u] = unsigned(i);
             } else {
@@ -601,6 +605,7 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
             unsigned oy, ox, src;
             ring_pixel(dst, j, oy, ox, src);
             v[u] = ld8(xb + (size_t(src) * cp8 + g) * 8);
+            if (RES) r[u] = ld8(rb + (size_t(src) * cp8 + g) * 8);
             o[u] = unsigned(padded_vec(dst, oy, ox, unsigned(cp8)) + g);
         }
     }
@@ -653,8 +658,17 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
         unpack(v[u], f);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            const float r = fmaf(f[j], sc[j], sh[j]);
-            f[j] = act == ACT_RELU ? fmaxf(r, 0.f) : r;
+            const float t = fmaf(f[j], sc[j], sh[j]);
+            f[j] = act == ACT_RELU ? fmaxf(t, 0.f) : t;
+        }
+        if (RES) {
+            float rf[8];
+            unpack(r[u], rf);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const float t = f[j] + rf[j];
+                f[j] = act2 == ACT_RELU ? fmaxf(t, 0.f) : t;
+            }
         }
         st8(yb + size_t(o[u]) * 8, pack(f));
         if (y_plain && !ring) {  // the un-padded copy for the other readers (position worked out here: rare, and eight registers less)
@@ -1080,7 +1094,7 @@ cudaError_t norm_dst_of(const NormStore* store, const __half* x, const __half* y
 }  // namespace
 
 cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, int cp, const float* gamma, const float* beta, float eps, int act,
-                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store) {
+                                     double* stats, unsigned int* counter, int phases, cudaStream_t s, const NormStore* store, const __half* res, int act2) {
     NormDst dst{};
     if (cudaError_t e = norm_dst_of(store, x, y, hw, &dst); e != cudaSuccess) return e;
     __half* y_plain = store && store->padded() ? store->plain : nullptr;
@@ -1088,14 +1102,20 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     if (cp8 > kThreads || phases < 1 || n > 65535) return cudaErrorInvalidValue;
     const size_t n8 = size_t(hw) * cp8;
     if ((dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) >> 32) return cudaErrorInvalidValue;  // 32-bit vector offsets inside an image
-    const int chunks = int(std::max<size_t>(1, (n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)));
+    if (res && (dst.unfold_w || (act2 != ACT_NONE && act2 != ACT_RELU))) return cudaErrorInvalidValue;  // the residual is read in x's pixel order
+    const size_t per_block = size_t(kThreads) * (res ? 4 : 8);
+    const int chunks = int(std::max<size_t>(1, (n8 + per_block - 1) / per_block));
     const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
-    const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
+    const int ring_chunks = int((ring8 + per_block - 1) / per_block);
     NormStats ns{stats, gamma, beta, counter, eps, phases, 1.0 / double(hw)};
     // chunks per block: measured with up to 8 (the prologue paid once per 256 KiB): slower (64 x 128 x 128 x 128: 0.122 -> 0.134 ms), one it is
     const int cpb = 1;
-    (void)launch_pdl_smem(inorm_apply_kernel<true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
-                          static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb);
+    if (res)
+        (void)launch_pdl_smem(inorm_apply_kernel<true, true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
+                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
+    else
+        (void)launch_pdl_smem(inorm_apply_kernel<true, false>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
+                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
     return cudaGetLastError();
 }
 
@@ -1175,7 +1195,8 @@ cudaError_t instance_norm(const __half* x, __half* y, int n, int hw, int cp, con
         if (e != cudaSuccess) return e;
         const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
         const int ring_chunks = int((ring8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8));
-        (void)launch_pdl(inorm_apply_kernel<false>, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr, NormStats{}, 1);
+        (void)launch_pdl(inorm_apply_kernel<false, false>, dim3(dim3(chunks + ring_chunks, gn)), dim3(kThreads), s, xg, yg, params, hw, cp8, act, dst, chunks, y_plain ? y_plain + size_t(i0) * n8 * 8 : nullptr, NormStats{}, 1,
+                         static_cast<const __half*>(nullptr), 0);
         e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }

@@ -714,3 +714,52 @@ def test_instance_norm_statistics_from_the_convolution_epilogue(ctx, monkeypatch
     (plain,), dump0, n0 = run()
     assert "stats" not in dump0 and n0 >= n
     assert np.abs(outs[0] - plain).max() <= 4e-3 * scale
+
+
+@pytest.mark.parametrize("mode,relu,second_reader,c,hw,batch", [("reflect", False, True, 128, (32, 32), 1), ("reflect", True, False, 64, (16, 24), 2),
+                                                               ("edge", False, True, 64, (32, 16), 3), ("reflect", False, False, 128, (16, 16), 2),
+                                                               ("constant", False, True, 64, (16, 16), 1)])
+def test_residual_tail_inside_the_one_pass_norm(ctx, monkeypatch, mode, relu, second_reader, c, hw, batch):
+    """Conv -> InstanceNorm -> Add(skip) (-> ReLU) -> Pad, the end of a TransformerNet residual block: with the statistics from the
+    convolution's epilogue the norm's single pass also reads the skip tensor and stores the padded sum (and the plain sum while the
+    next block reads it) -- the Add+Pad kernel runs inside the norm's launch (engine.cc "norm tail").  Same result as the plan with
+    the separate Add+Pad kernel and the oracle; constant pads keep their own kernel."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=h + c, name="normtail")
+    x = b.input("input", [batch, c, h, w])
+    a = b.relu(b.conv(x, c, 3, 1, 1))
+    z = b.instancenorm(b.conv(b.pad(a, 1, "reflect"), c, 3, 1, 0))
+    y = b.add(z, a)
+    if relu:
+        y = b.relu(y)
+    t = b.conv(b.pad(y, 1, mode), c, 3, 1, 0)
+    if second_reader:
+        t = b.add(t, y)
+    b.output(t, [batch, c, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(h).standard_normal((batch, c, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+
+    def run(repeats=1):
+        g = ONNXGraph(model, context=ctx)
+        nn = g.metalGraph()
+        outs = [nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray().copy() for _ in range(repeats)]
+        dump, n = nn.planDump(batch), nn.numLaunches(batch)
+        g.close()
+        return outs, dump, n
+
+    outs, dump, n = run(2)
+    fused = mode != "constant"
+    assert "<-stats" in dump
+    assert ("+add+pad" in dump and "add+pad " not in dump) == fused, dump
+    assert ("+add+pad+sum<-stats" in dump) == (fused and second_reader)
+    scale = max(1.0, np.abs(want).max())
+    assert np.abs(outs[0] - want).max() <= TOL * scale
+    assert np.abs(outs[1] - outs[0]).max() <= 1e-3 * scale
+    monkeypatch.setenv("SMELTER_NO_NORM_TAIL", "1")
+    (plain,), dump0, n0 = run()
+    assert "+add+pad" not in dump0 and n0 == n + (1 if fused else 0)
+    assert np.abs(outs[0] - plain).max() <= 2e-3 * scale

@@ -401,6 +401,23 @@ int ONNXGraph::build() {
     if (cfg_.enable_fusion) fuse();
     for (auto& f : filters_) {
         if (f.removed || f.kind != FilterKind::Conv) continue;
+        // Grouped convolution other than depthwise (Converters.swift:57-75 hands MPS the grouped descriptor): run as the dense
+        // convolution with a block-diagonal weight tensor -- OHWI [Cout][R][S][Cin] with zeros outside each output channel's group.
+        // `groups` times the arithmetic of the grouped form on the tensor cores, no kernel of its own; exact (the zeros add nothing).
+        if (f.groups > 1 && !f.transposed && !(f.groups == f.c_in_g * f.groups && f.groups == f.c_out && f.c_in_g == 1)) {
+            const int G = f.groups, cig = f.c_in_g, cin = cig * G, taps = f.k_h * f.k_w;
+            if (f.c_out % G) return fail(SMELTER_ERR_INCONSISTENT_STATE, "output channels not divisible by group (" + std::to_string(G) + ")");
+            if (f.w.size() != size_t(f.c_out) * taps * cig) return fail(SMELTER_ERR_INCONSISTENT_STATE, "grouped convolution: weight size mismatch");
+            const int cog = f.c_out / G;
+            std::vector<float> dense(size_t(f.c_out) * taps * cin, 0.f);
+            for (int co = 0; co < f.c_out; ++co)
+                for (int t = 0; t < taps; ++t)
+                    std::copy_n(&f.w[(size_t(co) * taps + t) * cig], cig, &dense[(size_t(co) * taps + t) * cin + size_t(co / cog) * cig]);
+            f.w.swap(dense);
+            f.c_in_g = cin;
+            f.group_expanded = G;
+            f.groups = 1;
+        }
         f.conv_mode = pick_conv_mode(f.c_in_g * f.groups, f.c_out, f.groups, f.k_h, f.k_w, f.stride_h, f.stride_w, f.dil_w, f.pads);
         if (f.transposed) f.conv_mode = (f.k_h == 1 && f.k_w == 1) ? k::CONV_MODE_TILED : k::CONV_MODE_IM2COL;  // reads a materialised image
         if (f.conv_mode < 0)
@@ -1095,6 +1112,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 const __half* res = f.residual >= 0 && !side ? ptr_of(f.residual) : nullptr;
                 std::string suffix = f.act == k::ACT_RELU ? "+relu" : f.act == k::ACT_CLIP ? "+clip" : f.act == k::ACT_SIGMOID ? "+sigmoid" : "";
                 if (res) suffix = "+add" + suffix;
+                if (f.group_expanded) suffix = "/groups" + std::to_string(f.group_expanded) + "-as-dense" + suffix;
                 if (side) suffix = "+conv1x1(" + values_[size_t(side->in[0])].name + ")" + suffix;
                 const double flops = f.transposed ? 2.0 * N * is.h * is.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w
                                                   : 2.0 * N * osz.h * osz.w * double(f.c_out) * f.c_in_g * f.k_h * f.k_w;

@@ -763,3 +763,33 @@ def test_residual_tail_inside_the_one_pass_norm(ctx, monkeypatch, mode, relu, se
     (plain,), dump0, n0 = run()
     assert "+add+pad" not in dump0 and n0 == n + (1 if fused else 0)
     assert np.abs(outs[0] - plain).max() <= 2e-3 * scale
+
+
+@pytest.mark.parametrize("c_in,c_out,groups,k,stride,hw,batch", [(64, 64, 2, 3, 1, (14, 14), 2), (32, 64, 4, 3, 2, (16, 12), 1), (128, 128, 32, 3, 1, (8, 8), 3),
+                                                                 (24, 48, 3, 1, 1, (9, 7), 2), (16, 32, 16, 3, 1, (10, 10), 1)])
+def test_grouped_convolution_as_block_diagonal_dense(ctx, c_in, c_out, groups, k, stride, hw, batch):
+    """Grouped convolutions other than depthwise (ResNeXt-style cardinality, channel multipliers; Converters.swift:57-75) run as the
+    dense convolution with block-diagonal weights on the tensor-core path; depthwise keeps its own kernel.  Engine vs the oracle's
+    grouped F.conv2d."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c_in + groups, name="grouped")
+    x = b.input("input", [batch, c_in, h, w])
+    y = b.relu(b.conv(x, c_in, 1))
+    y = b.relu(b.conv(y, c_out, k, stride, k // 2, groups=groups))
+    y = b.conv(y, c_out, 3, 1, 1, groups=c_out)  # depthwise: its own kernel
+    oh, ow = (h + 2 * (k // 2) - k) // stride + 1, (w + 2 * (k // 2) - k) // stride + 1
+    b.output(y, [batch, c_out, oh, ow])
+    model = b.model().serialize()
+    xin = np.random.default_rng(groups).standard_normal((batch, c_in, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+    g = ONNXGraph(model, context=ctx)
+    nn = g.metalGraph()
+    out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+    dump = nn.planDump(batch)
+    g.close()
+    assert f"/groups{groups}-as-dense" in dump and "depthwise" in dump
+    assert out.shape == want.shape
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())

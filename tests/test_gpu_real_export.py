@@ -14,9 +14,9 @@ pytestmark = pytest.mark.gpu
 
 # densenet121: BatchNorm in front of its convolution (un-fused scale/shift kernel), Concat, AveragePool, Pad; squeezenet1_1: Concat and
 # weights aliased through Identity nodes (the exporter de-duplicates equal initializers); googlenet: four-branch Concat, pools with
-# ceil_mode emulated by the exporter
+# ceil_mode emulated by the exporter; resnext50_32x4d: grouped convolutions (cardinality 32) as block-diagonal dense ones
 @pytest.mark.parametrize("arch,fold_in_exporter", [("resnet50", False), ("resnet50", True), ("mobilenet_v2", False), ("resnet18", False),
-                                                   ("resnet34", False), ("densenet121", False), ("squeezenet1_1", False), ("googlenet", False)])
+                                                   ("resnet34", False), ("densenet121", False), ("squeezenet1_1", False), ("googlenet", False), ("resnext50_32x4d", False)])
 def test_torchvision_model_exported_by_torch_matches_eager(ctx, arch, fold_in_exporter):
     from smelter_b200 import onnx2mps
     from smelter_b200 import onnx_proto as op

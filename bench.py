@@ -426,6 +426,16 @@ def run_native(args) -> int:
     e2e_s = max_over_ranks(e2e_s)
     e2e_value = world * B * K / e2e_s
     clocks = sampler.stop(lo, hi)
+    # the host link alone: the same pinned -> device copies back to back with the GPU otherwise idle (what bounds e2e when the step is
+    # shorter than its upload)
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    h0.record(copy_stream)
+    for i in range(32):
+        dev_in[i % slots].copyFromPointer(run.host_in[i % run.sets].data_ptr(), n_in, copy_stream.cuda_stream)
+    h1.record(copy_stream)
+    torch.cuda.synchronize()
+    h2d_alone_ms = h0.elapsed_time(h1) / 32
 
     # ---- multi-GPU: weak-scaling figure, 1-GPU batch-256 base, shard parity ----------------------------------------------------
     extra = {}
@@ -531,7 +541,8 @@ def run_native(args) -> int:
                        "cuda_graph": True, "accumulate": "fp32 (TMEM)"},
             "one_in_flight": {"ms_per_step": one_ms, "value": world * B / (one_ms * 1e-3), "unit": "images/s", "steps": K1},
             "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": n_in * 2, "d2h_bytes_per_step": B * 1000 * 4,
-                    "ms_per_step": e2e_s / K * 1e3, "how": "pinned host fp16 batch -> Image.copyFromPointer (copy stream) -> encode -> "
+                    "ms_per_step": e2e_s / K * 1e3, "h2d_alone_ms_per_step": h2d_alone_ms, "h2d_alone_gbs": n_in * 2 / (h2d_alone_ms * 1e-3) / 1e9,
+                    "link_bound_images_per_s": world * B / (h2d_alone_ms * 1e-3), "how": "pinned host fp16 batch -> Image.copyFromPointer (copy stream) -> encode -> "
                     f"toFloatArrayAsync (fp32 logits into pinned host memory every step), {slots} batches in flight: the host reads a slot's logits "
                     "before it reuses the slot, the last steps' before the clock stops; wall clock"},
             "gpu_launches": launches, "launches_per_step": nn.numLaunches(B), "clocks": clocks, "roofline": roofline}

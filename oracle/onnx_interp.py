@@ -189,6 +189,10 @@ class Interpreter:
                     y = F.avg_pool2d(x, tuple(k), tuple(st), (pd[0], pd[1]), ceil_mode=False, count_include_pad=True)
             elif t == "GlobalAveragePool":
                 y = x.mean(dim=(2, 3), keepdim=True)
+            elif t == "ReduceMean":  # extension (not in the reference registry): spatial mean only
+                axes = sorted(v % 4 for v in (a["axes"].ints if "axes" in a else _ints(host(n.input[1]))))
+                assert axes == [2, 3], axes
+                y = x.mean(dim=(2, 3), keepdim=True)
             elif t == "Flatten":
                 y = x.reshape(x.shape[0], -1)
             elif t == "Reshape":

@@ -222,12 +222,20 @@ int add_binary(ONNXGraph& g, const NodeProto& node, int kind) {
     const ImageShape* sa = g.shape(node.input[0]);
     const ImageShape* sb = g.shape(node.input[1]);
     if (a < 0 || b < 0 || !sa || !sb) return err(SMELTER_ERR_NO_SUCH_OUTPUT, node, "both operands must be image nodes");
-    if (!(*sa == *sb)) return err(SMELTER_ERR_UNSUPPORTED, node, "operand shapes differ (no broadcasting)");
     Filter f;
     f.kind = FilterKind::Binary;
     f.op_type = node.op_type;
     f.sub = kind;
     f.in = {a, b};
+    if (!(*sa == *sb)) {
+        // One pixel per image against a whole image ([N, C, 1, 1] x [N, C, H, W], the gate of a squeeze-and-excitation block): MPS
+        // arithmetic nodes broadcast a 1 x 1 source (Converters.swift:430-464 passes the images straight through).  Nothing else.
+        const bool b_pixel = sb->c == sa->c && sb->h == 1 && sb->w == 1;
+        const bool a_pixel = sa->c == sb->c && sa->h == 1 && sa->w == 1 && (kind == k::BIN_ADD || kind == k::BIN_MUL);
+        if (!b_pixel && !a_pixel) return err(SMELTER_ERR_UNSUPPORTED, node, "operand shapes differ (only a [C,1,1] operand is broadcast)");
+        f.bcast = true;
+        if (!b_pixel) { f.in = {b, a}; return g.addFilter(std::move(f), *sb, node.output); }
+    }
     return g.addFilter(std::move(f), *sa, node.output);
 }
 int convert_add(ONNXGraph& g, int ni) { return add_binary(g, g.node(ni), k::BIN_ADD); }
@@ -307,6 +315,18 @@ int convert_global_avgpool(ONNXGraph& g, int ni) {  // :578-605
     f.op_type = node.op_type;
     f.in = {input};
     return g.addFilter(std::move(f), ImageShape{s->c, 1, 1}, node.output);
+}
+// ReduceMean over the spatial axes: NOT in the reference's registry -- how newer torch exporters write x.mean([2, 3]) (MNASNet, the
+// squeeze of squeeze-and-excitation blocks).  axes must be {2, 3} (attribute, or initializer input from opset 18); keepdims either way.
+int convert_reduce_mean(ONNXGraph& g, int ni) {
+    const NodeProto& node = g.node(ni);
+    std::vector<int64_t> axes;
+    if (const AttributeProto* a = node.attr("axes")) axes.assign(a->ints.begin(), a->ints.end());
+    else if (node.input.size() >= 2) { const TensorProto* t = g.tensor(node.input[1]); if (!t || !t->integers(&axes)) axes.clear(); }
+    for (auto& v : axes) if (v < 0) v += 4;
+    std::sort(axes.begin(), axes.end());
+    if (axes != std::vector<int64_t>{2, 3}) return err(SMELTER_ERR_UNSUPPORTED, node, "only ReduceMean over axes {2, 3} (global average pooling)");
+    return convert_global_avgpool(g, ni);
 }
 int convert_pool(ONNXGraph& g, int ni) {  // AveragePool :607-650, MaxPool :652-695
     const NodeProto& node = g.node(ni);
@@ -587,6 +607,7 @@ void ONNXGraph::registerBuiltins() {
     // extensions (not in the reference registry)
     registerConverter("Clip", convert_clip);
     registerConverter("Identity", convert_identity);
+    registerConverter("ReduceMean", convert_reduce_mean);
 }
 
 }  // namespace smelter

@@ -344,7 +344,7 @@ void ONNXGraph::fuse() {
     // 2. Conv -> Add(residual) : the other operand must already exist when the conv runs.
     for (size_t ai = 0; ai < filters_.size(); ++ai) {
         Filter& add = filters_[ai];
-        if (add.removed || add.kind != FilterKind::Binary || add.sub != k::BIN_ADD || add.act != k::ACT_NONE) continue;
+        if (add.removed || add.kind != FilterKind::Binary || add.sub != k::BIN_ADD || add.act != k::ACT_NONE || add.bcast) continue;
         for (int side = 0; side < 2; ++side) {
             Filter* conv = producer(add.in[size_t(side)]);
             const int other = add.in[size_t(1 - side)];
@@ -1245,8 +1245,10 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
             case FilterKind::Binary: {
                 const __half* x2 = ptr_of(f.in[1]);
                 const int kind = f.sub, act = f.act;
-                add_step("binary " + name, [=](cudaStream_t st) { return k::binary(x, x2, y, size_t(N) * is.h * is.w * icp, kind, act, st, is.c, icp); }, 0,
-                         io_bytes + double(N) * is.h * is.w * icp * 2);
+                const size_t bcast = f.bcast ? size_t(is.h) * is.w : 0;
+                add_step(std::string(f.bcast ? "binary/broadcast " : "binary ") + name,
+                         [=](cudaStream_t st) { return k::binary(x, x2, y, size_t(N) * is.h * is.w * icp, kind, act, st, is.c, icp, bcast); }, 0,
+                         io_bytes + double(N) * (f.bcast ? 1 : is.h * is.w) * icp * 2);
                 break;
             }
             case FilterKind::Pool: {

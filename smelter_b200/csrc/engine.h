@@ -78,6 +78,7 @@ struct Filter {
 
     // Conv / Gemm
     int c_out = 0, c_in_g = 0, k_h = 1, k_w = 1, stride_h = 1, stride_w = 1, dil_h = 1, dil_w = 1, groups = 1;
+    bool bcast = false;      // Binary: in[1] is [C, 1, 1] and is broadcast over in[0]'s pixels
     int group_expanded = 0;  // G > 1: a grouped convolution running as the dense one with block-diagonal weights (engine.cc build())
     int pads[4] = {0, 0, 0, 0};    // top, left, bottom, right
     std::vector<float> w;          // OHWI fp32 [c_out][k_h][k_w][c_in_g]

@@ -147,7 +147,7 @@ __global__ void __launch_bounds__(kThreads) unary_kernel(const __half* __restric
 }
 
 __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restrict__ pa, const __half* __restrict__ pb,
-                                                         __half* __restrict__ y, size_t n8, int kind, int act, int cp8, int tail) {
+                                                         __half* __restrict__ y, size_t n8, int kind, int act, int cp8, int tail, size_t bcast) {
     pdl_prologue();
     constexpr size_t step = kThreads;
     const size_t base = size_t(blockIdx.x) * (kThreads * kU2) + threadIdx.x;
@@ -155,8 +155,10 @@ __global__ void __launch_bounds__(kThreads) binary_kernel(const __half* __restri
 #pragma unroll
     for (int u = 0; u < kU2; ++u)
         if (base + u * step < n8) {
-            va[u] = ld8(pa + (base + u * step) * 8);
-            vb[u] = ld8(pb + (base + u * step) * 8);
+            const size_t i = base + u * step;
+            va[u] = ld8(pa + i * 8);
+            // bcast = vectors per image of a: b is one pixel per image ([N, C, 1, 1], the gate of a squeeze-and-excitation block)
+            vb[u] = ld8(pb + (bcast ? (i / bcast) * size_t(cp8) + i % size_t(cp8) : i) * 8);
         }
 #pragma unroll
     for (int u = 0; u < kU2; ++u) {
@@ -699,10 +701,11 @@ cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float al
     (void)launch_pdl(unary_kernel, dim3(tiled_grid(n8, kU1)), dim3(kThreads), s, x, y, n8, kind, alpha, beta, cp > 0 ? cp / 8 : 1, tail);
     return cudaGetLastError();
 }
-cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c, int cp) {
+cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c, int cp, size_t bcast_pixels) {
     const size_t n8 = n_elems / 8;
     const int tail = cp > 0 ? (c & 7) : 0;
-    (void)launch_pdl(binary_kernel, dim3(tiled_grid(n8, kU2)), dim3(kThreads), s, a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail);
+    if (bcast_pixels && cp <= 0) return cudaErrorInvalidValue;
+    (void)launch_pdl(binary_kernel, dim3(tiled_grid(n8, kU2)), dim3(kThreads), s, a, b, y, n8, kind, act, cp > 0 ? cp / 8 : 1, tail, bcast_pixels * size_t(cp > 0 ? cp / 8 : 1));
     return cudaGetLastError();
 }
 cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act, cudaStream_t s) {

@@ -42,7 +42,9 @@ cudaError_t zero_stuff2d(const __half* x, __half* y, int n, int h, int w, int cp
 cudaError_t resize_planes(const __half* src, __half* dst, int planes, int hs, int ws, int hd, int wd, int mode, cudaStream_t s);
 // `c` logical channels at pitch `cp` (0 = dense, no padded lanes): the padded lanes of a pixel are written as zeros, never f(0)
 cudaError_t unary(const __half* x, __half* y, size_t n_elems, int kind, float alpha, float beta, cudaStream_t s, int c = 0, int cp = 0);
-cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c = 0, int cp = 0);
+// bcast_pixels = H * W of a: b holds one pixel per image ([N, C, 1, 1]) and is broadcast over a's pixels
+cudaError_t binary(const __half* a, const __half* b, __half* y, size_t n_elems, int kind, int act, cudaStream_t s, int c = 0, int cp = 0,
+                   size_t bcast_pixels = 0);
 // y = act(x * scale[c] + shift[c])  (un-fused BatchNormalization)
 cudaError_t scale_shift(const __half* x, __half* y, size_t pixels, int cp, const float* scale, const float* shift, int act,
                         cudaStream_t s);

@@ -793,3 +793,34 @@ def test_grouped_convolution_as_block_diagonal_dense(ctx, c_in, c_out, groups, k
     assert f"/groups{groups}-as-dense" in dump and "depthwise" in dump
     assert out.shape == want.shape
     assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())
+
+
+@pytest.mark.parametrize("c,hw,batch,op,gate_first", [(64, (14, 14), 2, "Mul", False), (20, (9, 7), 3, "Mul", True), (40, (28, 28), 1, "Add", False),
+                                                     (24, (5, 5), 2, "Sub", False), (136, (7, 7), 4, "Div", False)])
+def test_pixel_operand_broadcast_in_binary_ops(ctx, c, hw, batch, op, gate_first):
+    """[N, C, 1, 1] against [N, C, H, W] (the gate of a squeeze-and-excitation block: GlobalAveragePool / ReduceMean -> 1x1
+    convolutions -> Sigmoid -> Mul): the one-pixel operand is broadcast over the image, also with C % 8 != 0 and as the first operand
+    of a commutative op; ReduceMean over {2, 3} is the global pool.  Engine vs oracle."""
+    from smelter_b200 import modelzoo
+    from smelter_b200.api import Image, ONNXGraph
+
+    h, w = hw
+    b = modelzoo.GraphBuilder(seed=c + h, name="se")
+    x = b.input("input", [batch, c, h, w])
+    a = b.relu(b.conv(x, c, 3, 1, 1))
+    pooled = b._node("ReduceMean", [a], {"axes": [2, 3], "keepdims": 1}, c) if c % 16 == 8 else b.gap(a)
+    gate = b.sigmoid(b.conv(b.relu(b.conv(pooled, max(8, c // 4), 1)), c, 1))
+    y = b._node(op, [gate, a] if gate_first else [a, gate], {}, c)
+    y = b.conv(y, 16, 1)
+    b.output(y, [batch, 16, h, w])
+    model = b.model().serialize()
+    xin = np.random.default_rng(c).standard_normal((batch, c, h, w)).astype(np.float16)
+    want = _oracle(model, xin)
+    g = ONNXGraph(model, context=ctx)
+    nn = g.metalGraph()
+    out = nn.encode(sourceImages=[Image.fromArray(ctx, xin)]).toFloatArray()
+    dump = nn.planDump(batch)
+    g.close()
+    assert "binary/broadcast" in dump
+    assert out.shape == want.shape and np.isfinite(out).all()
+    assert np.abs(out - want).max() <= TOL * max(1.0, np.abs(want).max())

@@ -176,7 +176,7 @@ def test_conv_transpose_group_norm_pow_against_torch_modules():
     assert torch.allclose(got_mps, want, atol=1e-5)
 
 
-@pytest.mark.parametrize("arch", ["squeezenet1_1", "densenet121", "googlenet", "resnext50_32x4d"])
+@pytest.mark.parametrize("arch", ["squeezenet1_1", "densenet121", "googlenet", "resnext50_32x4d", "regnet_y_400mf", "mnasnet1_0", "mobilenet_v3_small"])
 def test_oracle_on_models_exported_by_torch(arch):
     """The oracle against EAGER torchvision modules on files written by torch's own exporter (a writer and model definitions this
     repository did not author): fp32 on the plain export, and within the fp16 tolerance after the ONNX2MPS restatement with --half.

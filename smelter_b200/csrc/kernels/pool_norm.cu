@@ -556,8 +556,10 @@ struct NormStats {
 // (STATS: two blocks per SM -- at three the compiler spills part of v[] around the prologue, which makes the prologue wait for the loads)
 // RES: a residual tensor (plain row-major pixels, the shape of x) is added behind the norm's own activation, `act2` follows the sum --
 // the Add (-> ReLU) -> Pad tail of a residual block (engine.cc "norm tail"); four vectors of each operand in flight per thread.
-template <bool STATS, bool RES>
-__global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
+// EARLY (STATS only): the prologue runs before the loads are issued, nothing is live across it and three blocks fit an SM -- the form
+// for tensors large enough to be bandwidth-bound; small ones keep the loads in flight behind the prologue (latency-bound).
+template <bool STATS, bool RES, bool EARLY = false>
+__global__ void __launch_bounds__(kThreads, (STATS && !EARLY) ? 2 : 3) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
                                                               int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns,
                                                               int cpb, const __half* __restrict__ res, int act2) {
     pdl_prologue();
@@ -580,36 +582,7 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
     const int c_hi = ring ? c_lo + 1 : min(chunks, c_lo + cpb);
     const bool fixed = (kThreads % cp8) == 0;
     float sc[8], sh[8];
-  for (int chunk = c_lo; chunk < c_hi; ++chunk) {
-    const size_t base = size_t(chunk) * (kThreads * U) + threadIdx.x;
-    // (32-bit store offsets -- vector indices inside one image -- and three blocks per SM: with 64-bit offsets the kernel took 146
-    // registers, one block per SM, and a block's 32 KiB in flight did not cover its prologue)
-    Half8 v[U], r[RES ? U : 1];
-    unsigned o[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) {
-        const size_t i = base + u * kThreads;
-        if (i >= tasks) break;
-        if (!ring) {
-            v[u] = ld8(xb + i * 8);
-            if (RES) r[u] = ld8(rb + i * 8);
-            if (plain) {
-                o[u] = unsigned(i);
-            } else {
-                const unsigned pix = unsigned(i / size_t(cp8));
-                unsigned q;
-                o[u] = unsigned(norm_dst_vec(dst, pix, unsigned(cp8), q) + (i - size_t(pix) * cp8));
-            }
-        } else {
-            const unsigned j = unsigned(i / size_t(cp8)), g = unsigned(i - size_t(j) * cp8);
-            unsigned oy, ox, src;
-            ring_pixel(dst, j, oy, ox, src);
-            v[u] = ld8(xb + (size_t(src) * cp8 + g) * 8);
-            if (RES) r[u] = ld8(rb + (size_t(src) * cp8 + g) * 8);
-            o[u] = unsigned(padded_vec(dst, oy, ox, unsigned(cp8)) + g);
-        }
-    }
-    if (STATS && chunk == c_lo) {  // (the loads above are in flight)
+    auto norm_prologue = [&]() {
         // `parts` threads share a channel, each adding every parts-th column group; fixed order within the block
         __shared__ double2 red[kThreads];
         const int cp = cp8 * 8;
@@ -639,7 +612,38 @@ __global__ void __launch_bounds__(kThreads, STATS ? 2 : 3) inorm_apply_kernel(co
             }
         }
         __syncthreads();
+    };
+    if (STATS && EARLY) norm_prologue();
+  for (int chunk = c_lo; chunk < c_hi; ++chunk) {
+    const size_t base = size_t(chunk) * (kThreads * U) + threadIdx.x;
+    // (32-bit store offsets -- vector indices inside one image -- and three blocks per SM: with 64-bit offsets the kernel took 146
+    // registers, one block per SM, and a block's 32 KiB in flight did not cover its prologue)
+    Half8 v[U], r[RES ? U : 1];
+    unsigned o[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const size_t i = base + u * kThreads;
+        if (i >= tasks) break;
+        if (!ring) {
+            v[u] = ld8(xb + i * 8);
+            if (RES) r[u] = ld8(rb + i * 8);
+            if (plain) {
+                o[u] = unsigned(i);
+            } else {
+                const unsigned pix = unsigned(i / size_t(cp8));
+                unsigned q;
+                o[u] = unsigned(norm_dst_vec(dst, pix, unsigned(cp8), q) + (i - size_t(pix) * cp8));
+            }
+        } else {
+            const unsigned j = unsigned(i / size_t(cp8)), g = unsigned(i - size_t(j) * cp8);
+            unsigned oy, ox, src;
+            ring_pixel(dst, j, oy, ox, src);
+            v[u] = ld8(xb + (size_t(src) * cp8 + g) * 8);
+            if (RES) r[u] = ld8(rb + (size_t(src) * cp8 + g) * 8);
+            o[u] = unsigned(padded_vec(dst, oy, ox, unsigned(cp8)) + g);
+        }
     }
+    if (STATS && !EARLY && chunk == c_lo) norm_prologue();  // (the loads above are in flight)
     if (fixed && chunk == c_lo) {
         const int c0 = int(threadIdx.x % unsigned(cp8)) * 8;
 #pragma unroll
@@ -1110,7 +1114,11 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     NormStats ns{stats, gamma, beta, counter, eps, phases, 1.0 / double(hw)};
     // chunks per block: measured with up to 8 (the prologue paid once per 256 KiB): slower (64 x 128 x 128 x 128: 0.122 -> 0.134 ms), one it is
     const int cpb = 1;
-    if (res)
+    const bool early = !res && size_t(chunks) * n >= size_t(148) * 3 * 4;  // several rounds of blocks: bandwidth-bound
+    if (early)
+        (void)launch_pdl_smem(inorm_apply_kernel<true, false, true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
+                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
+    else if (res)
         (void)launch_pdl_smem(inorm_apply_kernel<true, true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
                               static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
     else

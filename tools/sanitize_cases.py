@@ -59,6 +59,22 @@ model(modelzoo.decoder_ops(seed=3).serialize(), rng.standard_normal((1, 32, 10, 
 model(modelzoo.synthetic_ops(seed=0).serialize(), rng.random((2, 16, 12, 12), dtype=np.float32).astype(np.float16), 1e-2, "sigmoid / concat / avgpool / softmax")
 tn = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=0, hw=64, width_div=4).serialize(), half=True)
 model(tn, rng.random((1, 3, 64, 64), dtype=np.float32).astype(np.float16), 3e-2, "transformer_net (pad / instance norm / upsample)")
+# epilogue statistics, one-pass norms, residual tails (round 2): a TransformerNet large enough for the two-CTA kernel at every layer
+tn2 = onnx2mps.convert_bytes(modelzoo.transformer_net(seed=1, hw=128).serialize(), half=True)
+gph = ONNXGraph(tn2, Configuration(), context=ctx)
+dump = gph.metalGraph().planDump(2)
+print(f"transformer_net 128x128 batch 2: {dump.count('+stats')} convolutions with statistics, {dump.count('<-stats')} one-pass norms, {dump.count('+add+pad')} tails", flush=True)
+assert dump.count("+stats") >= 10 and dump.count("+add+pad") >= 4
+gph.close()
+model(tn2, rng.random((2, 3, 128, 128), dtype=np.float32).astype(np.float16), 3e-2, "transformer_net 128x128 (epilogue statistics / one-pass norm / tails)")
+# grouped convolution as block-diagonal dense, broadcast gate, ReduceMean
+b = modelzoo.GraphBuilder(seed=5, name="se_grouped")
+xi = b.input("input", [2, 24, 9, 7])
+a_ = b.relu(b.conv(xi, 48, 3, 1, 1, groups=3))
+gate = b.sigmoid(b.conv(b._node("ReduceMean", [a_], {"axes": [2, 3], "keepdims": 1}, 48), 48, 1))
+yo = b.conv(b._node("Mul", [a_, gate], {}, 48), 20, 1)
+b.output(yo, [2, 20, 9, 7])
+model(b.model().serialize(), rng.standard_normal((2, 24, 9, 7)).astype(np.float16), 1e-2, "grouped conv / ReduceMean / broadcast Mul")
 px = rng.integers(0, 256, size=(1, 9, 11, 4), dtype=np.uint8)
 got = Image.fromBytes(ctx, px, channels=3).toHalfArray()
 assert got.shape == (1, 3, 9, 11)

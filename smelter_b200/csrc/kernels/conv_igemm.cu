@@ -847,6 +847,7 @@ bool conv_tc_side_supported(const ConvTcProblem& q, int num_sms) {
 
 bool conv_tc_stats_supported(const ConvTcProblem& q, int num_sms) {
     if (q.pair < 0 || (q.pair == 0 && getenv("SMELTER_NO_PAIR")) || num_sms < 2 || q.splits > 1 || q.residual || q.side_x || q.act != ACT_NONE) return false;
+    if (q.n > 65535) return false;  // the one-pass norm's grid.y is the image
     const int P = (q.h + q.pad_t + q.pad_b - q.dil_h * (q.k_h - 1) - 1) / q.stride_h + 1;
     const int Q = (q.w + q.pad_l + q.pad_r - q.dil_w * (q.k_w - 1) - 1) / q.stride_w + 1;
     if (P <= 0 || Q <= 0 || (long(P) * Q) % 128) return false;

@@ -763,6 +763,78 @@ __global__ void __launch_bounds__(128) nchw_to_s2d_rows_kernel(const __half* __r
     }
 }
 
+// Three-channel form of the row-staged kernel (every RGB stem): ROWS folded rows per block, the source rows in shared memory between
+// eight zero halves on either side (no bounds tests: the horizontal padding is read), every load of a thread issued before the first
+// use, and a folded pixel assembled from six 32-bit pairs (one horizontal pixel pair of one channel and source row each; a funnel
+// shift where the left pad is odd) with byte permutes instead of twelve 16-bit loads.  ResNet-50 batch 32: 17.8 -> 13.2 us event-bracketed, the encode 0.519 -> 0.514 ms.
+template <int ROWS>
+__global__ void __launch_bounds__(256) nchw_to_s2d_rgb_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int h, int w, int pt, int pl,
+                                                             int h2, int w2) {
+    extern __shared__ __align__(16) __half rows[];  // [ROWS * 2][3][w + 16]
+    const int pitch = w + 16;
+    const int y20 = blockIdx.x * ROWS, img = blockIdx.y;
+    const size_t plane = size_t(h) * w;
+    const int vec_per_row = w / 8;
+    const int total = ROWS * 2 * 3 * vec_per_row;
+    constexpr int L = 4;  // loads in flight per thread
+    for (int i0 = threadIdx.x; i0 < total; i0 += 256 * L) {
+        uint4 v[L];
+#pragma unroll
+        for (int u = 0; u < L; ++u) {
+            const int i = i0 + u * 256;
+            v[u] = make_uint4(0u, 0u, 0u, 0u);
+            if (i < total) {
+                const int r = i / vec_per_row, vx = i - r * vec_per_row;
+                const int ry = r / 3, ch = r - ry * 3;  // ry = folded row * 2 + dy
+                const int sy = 2 * y20 + ry - pt;
+                if (sy >= 0 && sy < h) v[u] = __ldg(reinterpret_cast<const uint4*>(src + (size_t(img) * 3 + ch) * plane + size_t(sy) * w) + vx);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < L; ++u) {
+            const int i = i0 + u * 256;
+            if (i < total) {
+                const int r = i / vec_per_row, vx = i - r * vec_per_row;
+                reinterpret_cast<uint4*>(rows + size_t(r) * pitch + 8)[vx] = v[u];
+            }
+        }
+    }
+    for (int i = threadIdx.x; i < ROWS * 2 * 3 * 2; i += 256) {  // the zero borders
+        const int r = i >> 1;
+        *reinterpret_cast<uint4*>(rows + size_t(r) * pitch + ((i & 1) ? 8 + w : 0)) = make_uint4(0u, 0u, 0u, 0u);
+    }
+    __syncthreads();
+    const bool odd = pl & 1;
+    for (int t = threadIdx.x; t < ROWS * w2; t += 256) {
+        const int r = t / w2, x2 = t - r * w2;
+        const int y2 = y20 + r;
+        if (y2 >= h2) break;
+        const int idx = 2 * x2 - pl + 8;  // first half of the pair inside a padded row (>= 0 for pl <= 8)
+        uint32_t pr[2][3];
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+            for (int ch = 0; ch < 3; ++ch) {
+                const uint32_t* row32 = reinterpret_cast<const uint32_t*>(rows + size_t((r * 2 + dy) * 3 + ch) * pitch);
+                if (!odd) pr[dy][ch] = row32[idx >> 1];
+                else pr[dy][ch] = __byte_perm(row32[(idx - 1) >> 1], row32[(idx + 1) >> 1], 0x5432);
+            }
+        // channel d * 3 + ch of the folded pixel, d = dy * 2 + dx: {P00.lo P01.lo P02.lo P00.hi P01.hi P02.hi P10.lo P11.lo | P12.lo P10.hi P11.hi P12.hi 0 0 0 0}
+        uint4 o0, o1;
+        o0.x = __byte_perm(pr[0][0], pr[0][1], 0x5410);
+        o0.y = __byte_perm(pr[0][2], pr[0][0], 0x7610);
+        o0.z = __byte_perm(pr[0][1], pr[0][2], 0x7632);
+        o0.w = __byte_perm(pr[1][0], pr[1][1], 0x5410);
+        o1.x = __byte_perm(pr[1][2], pr[1][0], 0x7610);
+        o1.y = __byte_perm(pr[1][1], pr[1][2], 0x7632);
+        o1.z = 0u;
+        o1.w = 0u;
+        uint4* d = reinterpret_cast<uint4*>(dst + ((size_t(img) * h2 + y2) * w2 + x2) * 16);
+        d[0] = o0;
+        d[1] = o1;
+    }
+}
+
 // Row-staged variant: one block per (image, folded row): its 4 * c source rows (reflected / clamped as the pad mode says) go to
 // shared memory with coalesced 128-bit loads, then one thread per (folded pixel, dy) assembles 32 bytes.
 __global__ void __launch_bounds__(kThreads) nchw_to_s2d4_rows_kernel(const __half* __restrict__ src, __half* __restrict__ dst, int c, int h, int w,
@@ -825,6 +897,14 @@ cudaError_t nchw_to_s2d4(const __half* src, __half* dst, int n, int c, int h, in
 cudaError_t nchw_to_s2d(const __half* src, __half* dst, int n, int c, int h, int w, int pad_t, int pad_l, int h2, int w2, cudaStream_t s) {
     if (c < 1 || c > 4) return cudaErrorInvalidValue;
     const size_t smem = size_t(2) * c * w * sizeof(__half);
+    constexpr int kRows = 4;
+    const size_t smem3 = size_t(kRows) * 2 * 3 * (w + 16) * sizeof(__half);
+    // right border: the last pair of a row ends at column 2 * w2 - pl - 1 < w + 8
+    if (c == 3 && w % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && smem3 <= 48 * 1024 && n <= 65535 && pad_l >= 0 && pad_l <= 8 &&
+        2 * w2 - pad_l <= w + 8 && !getenv("SMELTER_NO_S2D_RGB")) {
+        nchw_to_s2d_rgb_kernel<kRows><<<dim3(unsigned((h2 + kRows - 1) / kRows), unsigned(n)), 256, smem3, s>>>(src, dst, h, w, pad_t, pad_l, h2, w2);
+        return cudaGetLastError();
+    }
     if (w % 8 == 0 && (reinterpret_cast<uintptr_t>(src) & 15) == 0 && smem <= 48 * 1024 && n <= 65535) {
         nchw_to_s2d_rows_kernel<<<dim3(unsigned(h2), unsigned(n)), 128, smem, s>>>(src, dst, c, h, w, pad_t, pad_l, h2, w2);
         return cudaGetLastError();

@@ -1205,11 +1205,9 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
                 if (f.unfold_w) what += "+unfold";
                 if (f.norm_padded) what += f.norm_s2d ? "+pad+s2d" : f.out2 >= 0 ? "+pad+plain" : "+pad";
                 if (stats_conv[fi] >= 0) {  // statistics from the producing convolution: one pass
-                    const Filter& c = filters_[size_t(stats_conv[fi])];
                     double* stats = reinterpret_cast<double*>(static_cast<char*>(plan->counters) + stats_off[size_t(stats_conv[fi])]);
                     const int phases = stats_phases[fi];
                     unsigned int* counter = reinterpret_cast<unsigned int*>(stats + size_t(N) * phases * icp * 2);
-                    (void)c;
                     if (tail_of[fi] >= 0) {
                         const Filter& pd = filters_[size_t(tail_of[fi])];
                         const int skip = root_of(pd.in[0]) == root_of(f.out) ? pd.in[1] : pd.in[0];

@@ -14,6 +14,9 @@
 // Projection shortcut (ConvKernelParams::side_kb): after the main k-blocks of a tile, `side_kb` more k-blocks read a second activation
 // tensor (tm_a2: 1x1, own stride, same output grid) against a second weight matrix (tm_b2) into the same accumulator -- the 1x1
 // "downsample" convolution of a residual block is part of its block's last GEMM instead of a launch of its own.
+// Instance-norm statistics (ConvKernelParams::stats, epilogue form EPI = 2): a layer whose only reader is an InstanceNormalization
+// adds the column sums and sums of squares of every 128-row tile -- read back from the fp16 staging buffer of the TMA store -- to
+// per-image fp64 accumulators, so the norm behind it is one pass over the tensor (pool_norm.cu inorm_apply_kernel<true, ..>).
 // Everything else (operand modes, epilogue, fusion, PDL) is conv_igemm.cu's.  Default for 64/128/256-column tiles without split-K
 // (same-box A/B on ResNet-50: -1.2 % step time at batch 32, +6..8 % images/s at batch 128/256); SMELTER_NO_PAIR=1 turns it off.
 #include <cstdio>

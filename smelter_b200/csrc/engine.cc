@@ -205,7 +205,8 @@ struct Plan {
     std::vector<ImageShape> src_shapes;
     Tensor result;
     cudaGraphExec_t exec = nullptr;
-    void* counters = nullptr;  // split-K arrival counters of every conv in the plan (zero between launches)
+    void* counters = nullptr;  // split-K arrival counters and instance-norm accumulators of every conv in the plan (zero between encodes)
+    size_t counter_bytes = 0;
     std::vector<__half*> resized;  // per graph input: NCHW staging the source is resized into under .forceInputScale (lazily allocated)
     std::vector<void*> blobs;  // further device allocations owned by the plan (none today)
     ~Plan() {
@@ -1042,6 +1043,7 @@ int ONNXGraph::plan_for(int batch, Plan** out, cudaStream_t stream) {
     if (counter_total) {
         SM_CUDA(cudaMalloc(&plan->counters, counter_total));
         SM_CUDA(cudaMemset(plan->counters, 0, counter_total));
+        plan->counter_bytes = counter_total;
     }
     char* abase = static_cast<char*>(plan->arena);
     // values without a buffer (outputs of convolutions that run inside their consumer's launch) have no address
@@ -1431,7 +1433,11 @@ int ONNXGraph::encode(cudaStream_t stream, const Tensor* const* sources, int n_s
             NvtxRange range(st.desc);
             cudaError_t e = st.run(stream);
             if (e == cudaSuccess && debug_sync) e = cudaStreamSynchronize(stream);
-            if (e != cudaSuccess) return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
+            if (e != cudaSuccess) {
+                // an encode cut short leaves counters / accumulators that the kernels behind the failed step would have put back to zero
+                if (plan->counters) { cudaStreamSynchronize(stream); cudaMemset(plan->counters, 0, plan->counter_bytes); }
+                return fail(SMELTER_ERR_CUDA, "launch failed at '" + st.desc + "': " + cudaGetErrorString(e));
+            }
         }
     }
     *result = &plan->result;

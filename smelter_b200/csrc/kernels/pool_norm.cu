@@ -559,7 +559,9 @@ struct NormStats {
 // the Add (-> ReLU) -> Pad tail of a residual block (engine.cc "norm tail"); four vectors of each operand in flight per thread.
 // EARLY (STATS only): the prologue runs before the loads are issued, nothing is live across it and three blocks fit an SM -- the form
 // for tensors large enough to be bandwidth-bound; small ones keep the loads in flight behind the prologue (latency-bound).
-template <bool STATS, bool RES, bool EARLY = false>
+// UU: vectors per thread (0 = 8, or 4 with a residual).  Small tensors take 4 so that the grid is about two blocks per SM: one image
+// of TransformerNet's 128 x 128 x 128 layers is 128 blocks at 8 vectors per thread -- less than one per SM (instance_norm_from_stats()).
+template <bool STATS, bool RES, bool EARLY = false, int UU = 0>
 __global__ void __launch_bounds__(kThreads, (STATS && !EARLY) ? 2 : 3) inorm_apply_kernel(const __half* __restrict__ x, __half* __restrict__ y, const float* __restrict__ params,
                                                               int hw, int cp8, int act, NormDst dst, int chunks, __half* __restrict__ y_plain, NormStats ns,
                                                               int cpb, const __half* __restrict__ res, int act2) {
@@ -569,7 +571,7 @@ __global__ void __launch_bounds__(kThreads, (STATS && !EARLY) ? 2 : 3) inorm_app
     const float* sm = STATS ? sm_params : params + size_t(img) * cp8 * 16;  // [cp][2] scale, shift of this image
     // streaming part: block-tiled, eight 128-bit loads in flight per thread; when kThreads % cp8 == 0 a thread meets the same 8
     // channels in every vector it handles and keeps their scale / shift in registers
-    constexpr int U = RES ? 4 : 8;
+    constexpr int U = UU ? UU : (RES ? 4 : 8);
     const size_t n8 = size_t(hw) * cp8;
     const bool plain = !dst.unfold_w && !dst.ho;
     const __half* rb = RES ? res + size_t(img) * n8 * 8 : nullptr;
@@ -1108,7 +1110,11 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     const size_t n8 = size_t(hw) * cp8;
     if ((dst.ho ? size_t(dst.ho) * dst.wo * cp8 : n8) >> 32) return cudaErrorInvalidValue;  // 32-bit vector offsets inside an image
     if (res && (dst.unfold_w || (act2 != ACT_NONE && act2 != ACT_RELU))) return cudaErrorInvalidValue;  // the residual is read in x's pixel order
-    const size_t per_block = size_t(kThreads) * (res ? 4 : 8);
+    // vectors per thread: 8 (4 with a residual), or 4 where 8 would give fewer than two blocks per SM.  Measured on TransformerNet's
+    // 128 x 128 x 128 norms (one image, event-bracketed): 8 -> 13.6 us (128 blocks), 4 -> 11.5 us (256), 2 -> 13.9 us (512: every block
+    // pays the prologue); the residual form 4 -> 11.7, 2 -> 15.8 us.  The encode 0.297 -> 0.289 ms.
+    const int vpt = (res || ((n8 + size_t(kThreads) * 8 - 1) / (size_t(kThreads) * 8)) * size_t(n) < size_t(2) * 148) ? 4 : 8;
+    const size_t per_block = size_t(kThreads) * vpt;
     const int chunks = int(std::max<size_t>(1, (n8 + per_block - 1) / per_block));
     const size_t ring8 = dst.ho ? size_t(dst.ho * dst.wo - dst.h * dst.w) * cp8 : 0;
     const int ring_chunks = int((ring8 + per_block - 1) / per_block);
@@ -1118,16 +1124,16 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     // runs TransformerNet at 0.316 instead of 0.298 ms and batch 8 at 1.47 instead of 1.42 ms -- the compiler schedules the
     // straight-line form differently (121 / 78 instead of 128 / 80 registers), and the measured form wins.
     const int cpb = 1;
-    const bool early = !res && size_t(chunks) * n >= size_t(148) * 3 * 4;  // several rounds of blocks: bandwidth-bound
-    if (early)
-        (void)launch_pdl_smem(inorm_apply_kernel<true, false, true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
-                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
-    else if (res)
-        (void)launch_pdl_smem(inorm_apply_kernel<true, true>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
-                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
-    else
-        (void)launch_pdl_smem(inorm_apply_kernel<true, false>, dim3((chunks + cpb - 1) / cpb + ring_chunks, n), dim3(kThreads), size_t(cp) * 2 * sizeof(float), s, x, y,
-                              static_cast<const float*>(nullptr), hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2);
+    const bool early = !res && vpt == 8 && size_t(chunks) * n >= size_t(148) * 3 * 4;  // several rounds of blocks: bandwidth-bound
+    const dim3 grid(chunks + ring_chunks, n);
+    const size_t smem = size_t(cp) * 2 * sizeof(float);
+    const float* none = nullptr;
+#define SMELTER_NORM_LAUNCH(...) (void)launch_pdl_smem(inorm_apply_kernel<__VA_ARGS__>, grid, dim3(kThreads), smem, s, x, y, none, hw, cp8, act, dst, chunks, y_plain, ns, cpb, res, act2)
+    if (early) SMELTER_NORM_LAUNCH(true, false, true);
+    else if (res) SMELTER_NORM_LAUNCH(true, true);
+    else if (vpt == 8) SMELTER_NORM_LAUNCH(true, false);
+    else SMELTER_NORM_LAUNCH(true, false, false, 4);
+#undef SMELTER_NORM_LAUNCH
     return cudaGetLastError();
 }
 

@@ -1124,7 +1124,9 @@ cudaError_t instance_norm_from_stats(const __half* x, __half* y, int n, int hw, 
     // runs TransformerNet at 0.316 instead of 0.298 ms and batch 8 at 1.47 instead of 1.42 ms -- the compiler schedules the
     // straight-line form differently (121 / 78 instead of 128 / 80 registers), and the measured form wins.
     const int cpb = 1;
-    const bool early = !res && vpt == 8 && size_t(chunks) * n >= size_t(148) * 3 * 4;  // several rounds of blocks: bandwidth-bound
+    // several rounds of blocks: bandwidth-bound.  (Threshold swept on TransformerNet: from 3 blocks per SM on, batch 1 0.289 -> 0.294 ms;
+    // never, batch 8 1.42 -> 1.46 ms.)
+    const bool early = !res && vpt == 8 && size_t(chunks) * n >= size_t(148) * 3 * 4;
     const dim3 grid(chunks + ring_chunks, n);
     const size_t smem = size_t(cp) * 2 * sizeof(float);
     const float* none = nullptr;

@@ -182,7 +182,9 @@ class Interpreter:
                 z = env[n.input[1]]
                 y = {"Add": torch.add, "Sub": torch.sub, "Mul": torch.mul, "Div": torch.div}[t](x, z)
             elif t in ("MaxPool", "AveragePool"):
-                k, st, pd = a["kernel_shape"].ints, a["strides"].ints, a["pads"].ints
+                k = a["kernel_shape"].ints
+                st = a["strides"].ints if "strides" in a else [1, 1]          # ONNX defaults
+                pd = a["pads"].ints if "pads" in a else [0, 0, 0, 0]
                 if t == "MaxPool":
                     y = F.max_pool2d(x, tuple(k), tuple(st), (pd[0], pd[1]), ceil_mode=False)
                 else:

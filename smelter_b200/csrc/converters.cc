@@ -335,17 +335,18 @@ int convert_pool(ONNXGraph& g, int ni) {  // AveragePool :607-650, MaxPool :652-
     const AttributeProto* strides = node.attr("strides");
     const int input = node.input.empty() ? -1 : g.output(node.input[0]);
     const ImageShape* s = node.input.empty() ? nullptr : g.shape(node.input[0]);
-    // the reference guards on all of these at once and throws noSuchOutput (:654-661)
-    if (input < 0 || !s || node.attribute.size() < 3 || !ks || !pads || !strides || ks->ints.size() < 2 || pads->ints.size() < 2 ||
-        strides->ints.size() < 2)
-        return err(SMELTER_ERR_NO_SUCH_OUTPUT, node, "needs an image input and kernel_shape, pads, strides attributes");
+    // The reference guards on all three attributes at once and throws noSuchOutput (:654-661).  Here `pads` and `strides` fall back
+    // to their ONNX defaults (0 and 1) when absent -- torch's exporter writes AdaptiveAvgPool2d without `pads` (VGG, AlexNet) -- and
+    // only a missing input or kernel_shape is the reference's error (DESIGN.md "ONNX semantics win").
+    if (input < 0 || !s || !ks || ks->ints.size() < 2 || (pads && pads->ints.size() < 2) || (strides && strides->ints.size() < 2))
+        return err(SMELTER_ERR_NO_SUCH_OUTPUT, node, "needs an image input and a kernel_shape attribute (pads / strides default to 0 / 1)");
     Filter f;
     f.kind = FilterKind::Pool;
     f.op_type = node.op_type;
     f.sub = node.op_type == "MaxPool" ? 1 : 0;
     f.k_h = int(ks->ints[0]); f.k_w = int(ks->ints[1]);
-    f.stride_h = int(strides->ints[0]); f.stride_w = int(strides->ints[1]);
-    f.pool_pad_h = int(pads->ints[0]); f.pool_pad_w = int(pads->ints[1]);  // symmetric from pads[0..1]
+    f.stride_h = strides ? int(strides->ints[0]) : 1; f.stride_w = strides ? int(strides->ints[1]) : 1;
+    f.pool_pad_h = pads ? int(pads->ints[0]) : 0; f.pool_pad_w = pads ? int(pads->ints[1]) : 0;  // symmetric from pads[0..1]
     if (f.k_h < 1 || f.k_w < 1 || f.stride_h < 1 || f.stride_w < 1) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "bad kernel/stride");
     ImageShape out{s->c, pool_output_size(s->h, f.k_h, f.stride_h, f.pool_pad_h), pool_output_size(s->w, f.k_w, f.stride_w, f.pool_pad_w)};
     if (out.h <= 0 || out.w <= 0) return err(SMELTER_ERR_INCONSISTENT_STATE, node, "empty output");
